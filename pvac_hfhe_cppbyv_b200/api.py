@@ -1,0 +1,373 @@
+"""Python host-side mirror of the reference API over libpvacb.so (include/pvacb.h).
+
+The reference is a header-only C++ library; its boundary for this path is
+    keygen / enc_value / ct_add / ct_sub / ct_mul / dec_value          (pvac/ops/*.hpp, pvac/crypto/keygen.hpp)
+Here each of them takes an ARRAY of independent items and runs as CUDA kernels on one B200. There is no CPU fallback:
+importing this module loads the CUDA library, and Engine() raises if no sm_100 device is present.
+
+    eng = Engine(device=0)
+    eng.keygen(tape_state=1)                       # or eng.import_keys(...)
+    a = eng.enc_value(np.array([42, 17], np.uint64), batch_seed=1000)
+    b = eng.enc_value(np.array([5, 6], np.uint64), batch_seed=2000)
+    s, p = eng.ct_add(a, b), eng.ct_mul(a, b, batch_seed=3000)
+    eng.dec_value(p)                                # -> uint64 array [n, 2] (lo, hi) of Fp values
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpvacb.so")
+
+B = 337
+M_WORDS = 128
+N_COLS = 16384
+LPN_WORDS = 64
+KEY_BLOB_BYTES = (748 + 16384 * 128) * 8
+PRF_FAITHFUL, PRF_LIVE = 0, 1
+
+STATUS = {0: "OK", 1: "E_ARG", 2: "E_CUDA", 3: "E_OOM", 4: "E_NOKEYS", 5: "E_EDGE_BUDGET", 6: "E_LAYER_GRAPH", 7: "E_RARE_PATH",
+          8: "E_DUP_EDGE", 9: "E_FORMAT", 10: "E_SHAPE"}
+
+# every symbol include/pvacb.h declares
+SYMBOLS = [
+    "pvacb_ctx_create", "pvacb_ctx_destroy", "pvacb_last_error", "pvacb_set_prf_mode", "pvacb_get_prf_mode", "pvacb_stream", "pvacb_sync",
+    "pvacb_stats", "pvacb_stats_reset", "pvacb_keygen", "pvacb_keys_import_raw", "pvacb_keys_export_raw", "pvacb_keys_device_blob",
+    "pvacb_keys_alloc_blob", "pvacb_keys_adopt_blob", "pvacb_enc_value", "pvacb_enc_value_ex", "pvacb_ct_mul_ex", "pvacb_ct_add", "pvacb_ct_sub", "pvacb_ct_scale", "pvacb_ct_mul",
+    "pvacb_dec_value", "pvacb_batch_free", "pvacb_batch_count", "pvacb_batch_totals", "pvacb_batch_device_bytes", "pvacb_batch_offsets",
+    "pvacb_batch_slice", "pvacb_batch_export_soa", "pvacb_batch_import_soa", "pvacb_batch_wire_size", "pvacb_batch_export_wire",
+    "pvacb_batch_import_wire", "pvacb_batch_synthetic", "pvacb_prf", "pvacb_sigma_from_H", "pvacb_fp_op",
+]
+
+
+class PvacbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pvacb status {code} ({STATUS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libpvacb.so (built by pvac_hfhe_cppbyv_b200.build). Fails loudly if it is missing: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m pvac_hfhe_cppbyv_b200.build` (needs nvcc)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, u16, u8, i32, sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint16, C.c_uint8, C.c_int, C.c_size_t
+    P = C.POINTER
+    sig = {
+        "pvacb_ctx_create": (i32, [i32, P(vp)]),
+        "pvacb_ctx_destroy": (None, [vp]),
+        "pvacb_last_error": (C.c_char_p, [vp]),
+        "pvacb_set_prf_mode": (i32, [vp, i32]),
+        "pvacb_get_prf_mode": (i32, [vp]),
+        "pvacb_stream": (vp, [vp]),
+        "pvacb_sync": (i32, [vp]),
+        "pvacb_stats": (None, [vp, P(u64), P(u64), P(u64)]),
+        "pvacb_stats_reset": (None, [vp]),
+        "pvacb_keygen": (i32, [vp, u64]),
+        "pvacb_keys_import_raw": (i32, [vp, u64, P(u8), P(u64), P(u64), P(u64), P(u64)]),
+        "pvacb_keys_export_raw": (i32, [vp, P(u64), P(u8), P(u64), P(u64), P(u64), P(u64)]),
+        "pvacb_keys_device_blob": (i32, [vp, P(vp), P(sz)]),
+        "pvacb_keys_alloc_blob": (i32, [vp, P(vp)]),
+        "pvacb_keys_adopt_blob": (i32, [vp]),
+        "pvacb_enc_value": (i32, [vp, P(u64), sz, u64, P(vp)]),
+        "pvacb_enc_value_ex": (i32, [vp, P(u64), sz, u64, P(u64), P(vp)]),
+        "pvacb_ct_mul_ex": (i32, [vp, vp, vp, u64, P(u64), P(vp)]),
+        "pvacb_ct_add": (i32, [vp, vp, vp, P(vp)]),
+        "pvacb_ct_sub": (i32, [vp, vp, vp, P(vp)]),
+        "pvacb_ct_scale": (i32, [vp, vp, P(u64), P(vp)]),
+        "pvacb_ct_mul": (i32, [vp, vp, vp, u64, P(vp)]),
+        "pvacb_dec_value": (i32, [vp, vp, P(u64)]),
+        "pvacb_batch_free": (None, [vp]),
+        "pvacb_batch_count": (sz, [vp]),
+        "pvacb_batch_totals": (i32, [vp, P(u64), P(u64)]),
+        "pvacb_batch_device_bytes": (sz, [vp]),
+        "pvacb_batch_offsets": (i32, [vp, vp, P(u32), P(u32)]),
+        "pvacb_batch_slice": (i32, [vp, vp, sz, sz, P(vp)]),
+        "pvacb_batch_export_soa": (i32, [vp, vp, P(u32), P(u32), P(u8), P(u64), P(u64), P(u64), P(u32), P(u32), P(u32), P(u16), P(u8), P(u64), P(u64)]),
+        "pvacb_batch_import_soa": (i32, [vp, sz, P(u32), P(u32), P(u8), P(u64), P(u64), P(u64), P(u32), P(u32), P(u32), P(u16), P(u8), P(u64), P(u64), P(vp)]),
+        "pvacb_batch_wire_size": (i32, [vp, vp, P(sz)]),
+        "pvacb_batch_export_wire": (i32, [vp, vp, vp, sz, P(sz)]),
+        "pvacb_batch_import_wire": (i32, [vp, vp, sz, P(vp)]),
+        "pvacb_batch_synthetic": (i32, [vp, sz, i32, u64, P(vp)]),
+        "pvacb_prf": (i32, [vp, sz, P(u64), P(u64), P(u64), i32, P(u64), P(u64)]),
+        "pvacb_sigma_from_H": (i32, [vp, sz, P(u64), P(u64), P(u64), P(u16), P(u8), P(u64), P(u64)]),
+        "pvacb_fp_op": (i32, [vp, i32, sz, P(u64), P(u64), P(u64)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Batch:
+    """Device-resident array of ciphertexts (the batched pvac::Cipher). Freed on garbage collection or .free()."""
+
+    def __init__(self, eng, handle):
+        self.eng = eng
+        self.h = handle
+
+    def __len__(self):
+        return int(load_library().pvacb_batch_count(self.h))
+
+    def totals(self):
+        nl, ne = C.c_uint64(), C.c_uint64()
+        load_library().pvacb_batch_totals(self.h, C.byref(nl), C.byref(ne))
+        return int(nl.value), int(ne.value)
+
+    def device_bytes(self):
+        return int(load_library().pvacb_batch_device_bytes(self.h))
+
+    def free(self):
+        if self.h:
+            load_library().pvacb_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One B200: context + replicated keys. Mirrors the reference's free functions as methods over batches."""
+
+    def __init__(self, device=0, prf_mode=PRF_FAITHFUL):
+        L = load_library()
+        h = C.c_void_p()
+        rc = L.pvacb_ctx_create(device, C.byref(h))
+        if rc:
+            raise PvacbError(rc, f"cannot create a context on CUDA device {device} (an sm_100-class GPU is required; there is no CPU fallback)")
+        self.L, self.h, self.device = L, h, device
+        self.set_prf_mode(prf_mode)
+
+    def close(self):
+        if self.h:
+            self.L.pvacb_ctx_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        if rc:
+            raise PvacbError(rc, self.L.pvacb_last_error(self.h).decode(errors="replace"))
+
+    # ---- context
+    def set_prf_mode(self, mode):
+        self._ck(self.L.pvacb_set_prf_mode(self.h, mode))
+
+    @property
+    def stream(self):
+        return self.L.pvacb_stream(self.h)
+
+    def sync(self):
+        self._ck(self.L.pvacb_sync(self.h))
+
+    def stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.L.pvacb_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(kernel_launches=int(a.value), aes_blocks=int(b.value), sigma_edges=int(c.value))
+
+    def stats_reset(self):
+        self.L.pvacb_stats_reset(self.h)
+
+    # ---- keys (crypto/keygen.hpp:35)
+    def keygen(self, tape_state):
+        self._ck(self.L.pvacb_keygen(self.h, tape_state))
+
+    def import_keys(self, canon_tag, H_digest, H, powg, prf_k, lpn_s):
+        hd = np.ascontiguousarray(H_digest, np.uint8)
+        Hc = _u64(H) if H is not None else None
+        gc = _u64(powg) if powg is not None else None
+        pk, ls = _u64(prf_k), _u64(lpn_s)
+        self._ck(self.L.pvacb_keys_import_raw(self.h, int(canon_tag), _p(hd, C.c_uint8), _p(Hc, C.c_uint64), _p(gc, C.c_uint64), _p(pk, C.c_uint64), _p(ls, C.c_uint64)))
+
+    def export_keys(self, with_H=True):
+        ct = C.c_uint64()
+        hd = np.zeros(32, np.uint8)
+        H = np.zeros((N_COLS, M_WORDS), np.uint64) if with_H else None
+        powg = np.zeros((B, 2), np.uint64)
+        prf_k = np.zeros(4, np.uint64)
+        lpn_s = np.zeros(LPN_WORDS, np.uint64)
+        self._ck(self.L.pvacb_keys_export_raw(self.h, C.byref(ct), _p(hd, C.c_uint8), _p(H, C.c_uint64), _p(powg, C.c_uint64), _p(prf_k, C.c_uint64), _p(lpn_s, C.c_uint64)))
+        return dict(canon_tag=int(ct.value), H_digest=hd, H=H, powg=powg, prf_k=prf_k, lpn_s=lpn_s)
+
+    def key_blob_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.pvacb_keys_device_blob(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def alloc_key_blob(self):
+        p = C.c_void_p()
+        self._ck(self.L.pvacb_keys_alloc_blob(self.h, C.byref(p)))
+        return int(p.value), KEY_BLOB_BYTES
+
+    def adopt_key_blob(self):
+        self._ck(self.L.pvacb_keys_adopt_blob(self.h))
+
+    # ---- hot path
+    def enc_value(self, values, batch_seed=0, tape_states=None):
+        v = _u64(values)
+        out = C.c_void_p()
+        st = _u64(tape_states) if tape_states is not None else None
+        self._ck(self.L.pvacb_enc_value_ex(self.h, _p(v, C.c_uint64), len(v), batch_seed, _p(st, C.c_uint64), C.byref(out)))
+        return Batch(self, out)
+
+    def ct_add(self, a, b):
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_ct_add(self.h, a.h, b.h, C.byref(out)))
+        return Batch(self, out)
+
+    def ct_sub(self, a, b):
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_ct_sub(self.h, a.h, b.h, C.byref(out)))
+        return Batch(self, out)
+
+    def ct_scale(self, a, s):
+        ss = _u64(s)
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_ct_scale(self.h, a.h, _p(ss, C.c_uint64), C.byref(out)))
+        return Batch(self, out)
+
+    def ct_mul(self, a, b, batch_seed=0, tape_states=None):
+        out = C.c_void_p()
+        st = _u64(tape_states) if tape_states is not None else None
+        self._ck(self.L.pvacb_ct_mul_ex(self.h, a.h, b.h, batch_seed, _p(st, C.c_uint64), C.byref(out)))
+        return Batch(self, out)
+
+    def dec_value(self, c):
+        out = np.zeros((len(c), 2), np.uint64)
+        self._ck(self.L.pvacb_dec_value(self.h, c.h, _p(out, C.c_uint64)))
+        return out
+
+    # ---- batches
+    def offsets(self, b):
+        n = len(b)
+        lo, eo = np.zeros(n + 1, np.uint32), np.zeros(n + 1, np.uint32)
+        self._ck(self.L.pvacb_batch_offsets(self.h, b.h, _p(lo, C.c_uint32), _p(eo, C.c_uint32)))
+        return lo, eo
+
+    def slice(self, b, first, count):
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_batch_slice(self.h, b.h, first, count, C.byref(out)))
+        return Batch(self, out)
+
+    def export_soa(self, b, with_sigma=True, pinned=None):
+        """-> dict of numpy arrays for the whole batch (offsets + concatenated layer / edge arrays)."""
+        n = len(b)
+        nL, nE = b.totals()
+        d = dict(
+            loff=np.zeros(n + 1, np.uint32), eoff=np.zeros(n + 1, np.uint32),
+            rule=np.zeros(nL, np.uint8), ztag=np.zeros(nL, np.uint64), nlo=np.zeros(nL, np.uint64), nhi=np.zeros(nL, np.uint64),
+            pa=np.zeros(nL, np.uint32), pb=np.zeros(nL, np.uint32),
+            lid=np.zeros(nE, np.uint32), idx=np.zeros(nE, np.uint16), ch=np.zeros(nE, np.uint8), w=np.zeros((nE, 2), np.uint64),
+            sigma=(pinned if pinned is not None else np.zeros((nE, M_WORDS), np.uint64)) if with_sigma else None,
+        )
+        self._ck(self.L.pvacb_batch_export_soa(
+            self.h, b.h, _p(d["loff"], C.c_uint32), _p(d["eoff"], C.c_uint32), _p(d["rule"], C.c_uint8), _p(d["ztag"], C.c_uint64),
+            _p(d["nlo"], C.c_uint64), _p(d["nhi"], C.c_uint64), _p(d["pa"], C.c_uint32), _p(d["pb"], C.c_uint32), _p(d["lid"], C.c_uint32),
+            _p(d["idx"], C.c_uint16), _p(d["ch"], C.c_uint8), _p(d["w"], C.c_uint64), _p(d["sigma"], C.c_uint64) if with_sigma else None))
+        return d
+
+    def import_soa(self, d):
+        n = len(d["loff"]) - 1
+        out = C.c_void_p()
+        sg = d.get("sigma")
+        arr = {k: np.ascontiguousarray(v) for k, v in d.items() if v is not None}
+        self._ck(self.L.pvacb_batch_import_soa(
+            self.h, n, _p(arr["loff"], C.c_uint32), _p(arr["eoff"], C.c_uint32), _p(arr["rule"], C.c_uint8), _p(arr["ztag"], C.c_uint64),
+            _p(arr["nlo"], C.c_uint64), _p(arr["nhi"], C.c_uint64), _p(arr["pa"], C.c_uint32), _p(arr["pb"], C.c_uint32), _p(arr["lid"], C.c_uint32),
+            _p(arr["idx"], C.c_uint16), _p(arr["ch"], C.c_uint8), _p(arr["w"], C.c_uint64), _p(arr["sigma"], C.c_uint64) if sg is not None else None,
+            C.byref(out)))
+        return Batch(self, out)
+
+    def export_wire(self, b) -> bytes:
+        n = C.c_size_t()
+        self._ck(self.L.pvacb_batch_wire_size(self.h, b.h, C.byref(n)))
+        buf = (C.c_char * n.value)()
+        w = C.c_size_t()
+        self._ck(self.L.pvacb_batch_export_wire(self.h, b.h, buf, n.value, C.byref(w)))
+        return bytes(buf[: w.value])
+
+    def import_wire(self, data: bytes):
+        out = C.c_void_p()
+        buf = C.create_string_buffer(data, len(data))
+        self._ck(self.L.pvacb_batch_import_wire(self.h, buf, len(data), C.byref(out)))
+        return Batch(self, out)
+
+    def synthetic(self, n, edges_per_layer=20, batch_seed=1):
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_batch_synthetic(self.h, n, edges_per_layer, batch_seed, C.byref(out)))
+        return Batch(self, out)
+
+    # ---- building blocks (device kernels) for parity tests
+    def prf(self, ztag, nlo, nhi, family=0, want_ybits=False):
+        z, lo, hi = _u64(ztag), _u64(nlo), _u64(nhi)
+        n = len(z)
+        out = np.zeros((n, 2), np.uint64)
+        wpc = 2 if self.L.pvacb_get_prf_mode(self.h) == PRF_LIVE else 256
+        yb = np.zeros((n * 3, wpc), np.uint64) if want_ybits else None
+        self._ck(self.L.pvacb_prf(self.h, n, _p(z, C.c_uint64), _p(lo, C.c_uint64), _p(hi, C.c_uint64), family, _p(out, C.c_uint64), _p(yb, C.c_uint64)))
+        return (out, yb) if want_ybits else out
+
+    def sigma_from_H(self, ztag, nlo, nhi, idx, ch, salt):
+        z, lo, hi, s = _u64(ztag), _u64(nlo), _u64(nhi), _u64(salt)
+        i = np.ascontiguousarray(idx, np.uint16)
+        c = np.ascontiguousarray(ch, np.uint8)
+        out = np.zeros((len(z), M_WORDS), np.uint64)
+        self._ck(self.L.pvacb_sigma_from_H(self.h, len(z), _p(z, C.c_uint64), _p(lo, C.c_uint64), _p(hi, C.c_uint64), _p(i, C.c_uint16), _p(c, C.c_uint8),
+                                           _p(s, C.c_uint64), _p(out, C.c_uint64)))
+        return out
+
+    def fp_op(self, op, a, b=None):
+        aa = _u64(a).reshape(-1, 2)
+        bb = _u64(b).reshape(-1, 2) if b is not None else None
+        out = np.zeros_like(aa)
+        self._ck(self.L.pvacb_fp_op(self.h, op, len(aa), _p(aa, C.c_uint64), _p(bb, C.c_uint64), _p(out, C.c_uint64)))
+        return out
+
+
+def split_items(d):
+    """Splits an export_soa() dict into one dict per ciphertext (same keys as the oracle's export)."""
+    out = []
+    for i in range(len(d["loff"]) - 1):
+        l0, l1, e0, e1 = int(d["loff"][i]), int(d["loff"][i + 1]), int(d["eoff"][i]), int(d["eoff"][i + 1])
+        out.append(dict(
+            rule=d["rule"][l0:l1], ztag=d["ztag"][l0:l1], nlo=d["nlo"][l0:l1], nhi=d["nhi"][l0:l1], pa=d["pa"][l0:l1], pb=d["pb"][l0:l1],
+            lid=d["lid"][e0:e1], idx=d["idx"][e0:e1], ch=d["ch"][e0:e1], w=d["w"][e0:e1],
+            sigma=d["sigma"][e0:e1] if d.get("sigma") is not None else None))
+    return out
+
+
+def join_items(items):
+    """Inverse of split_items."""
+    loff = np.zeros(len(items) + 1, np.uint32)
+    eoff = np.zeros(len(items) + 1, np.uint32)
+    for i, it in enumerate(items):
+        loff[i + 1] = loff[i] + len(it["rule"])
+        eoff[i + 1] = eoff[i] + len(it["lid"])
+
+    def cat(k, dt, shape=()):
+        parts = [np.asarray(it[k], dt).reshape((-1,) + shape) for it in items]
+        return np.concatenate(parts) if parts else np.zeros((0,) + shape, dt)
+
+    d = dict(loff=loff, eoff=eoff, rule=cat("rule", np.uint8), ztag=cat("ztag", np.uint64), nlo=cat("nlo", np.uint64), nhi=cat("nhi", np.uint64),
+             pa=cat("pa", np.uint32), pb=cat("pb", np.uint32), lid=cat("lid", np.uint32), idx=cat("idx", np.uint16), ch=cat("ch", np.uint8),
+             w=cat("w", np.uint64, (2,)))
+    d["sigma"] = cat("sigma", np.uint64, (M_WORDS,)) if all(it.get("sigma") is not None for it in items) else None
+    return d

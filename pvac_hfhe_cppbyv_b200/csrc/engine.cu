@@ -1,0 +1,522 @@
+// Host side of the pvacb engine: context, key replication blob, device batches (structure-of-arrays), import/export,
+// and the extern "C" boundary declared in include/pvacb.h.
+#include "engine.h"
+#include "sha256.cuh"
+#include "../../include/pvacb.h"
+
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include <unordered_map>
+
+namespace pvacb {
+
+int keygen_host(uint64_t tape_state, std::vector<uint64_t>& blob);   // keygen.cu
+
+// ------------------------------------------------------------------ memory
+int dev_alloc(Ctx* ctx, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->last_error = std::string("cudaMallocAsync(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+        cudaGetLastError();
+        *p = nullptr;
+        return e == cudaErrorMemoryAllocation ? PV_E_OOM : PV_E_CUDA;
+    }
+    return PV_OK;
+}
+void dev_free(Ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out) {
+    Batch* b = new Batch();
+    b->ctx = ctx; b->n = n; b->nL = nL; b->nE = nE;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 1); return o; };
+    size_t o_loff = take((n + 1) * 4), o_eoff = take((n + 1) * 4);
+    size_t o_rule = take(nL), o_ztag = take(nL * 8), o_nlo = take(nL * 8), o_nhi = take(nL * 8), o_pa = take(nL * 4), o_pb = take(nL * 4);
+    size_t o_lid = take(nE * 4), o_idx = take(nE * 2), o_ch = take(nE), o_w = take(nE * 16), o_sig = take(nE * (size_t)kMWords * 8);
+    b->bytes = off;
+    int rc = dev_alloc(ctx, &b->base, off);
+    if (rc) { delete b; return rc; }
+    char* p = (char*)b->base;
+    b->loff = (uint32_t*)(p + o_loff); b->eoff = (uint32_t*)(p + o_eoff);
+    b->rule = (uint8_t*)(p + o_rule); b->ztag = (uint64_t*)(p + o_ztag); b->nlo = (uint64_t*)(p + o_nlo); b->nhi = (uint64_t*)(p + o_nhi);
+    b->pa = (uint32_t*)(p + o_pa); b->pb = (uint32_t*)(p + o_pb);
+    b->lid = (uint32_t*)(p + o_lid); b->idx = (uint16_t*)(p + o_idx); b->ch = (uint8_t*)(p + o_ch); b->w = (Fp*)(p + o_w);
+    b->sigma = (uint64_t*)(p + o_sig);
+    *out = b;
+    return PV_OK;
+}
+void batch_free(Batch* b) {
+    if (!b) return;
+    dev_free(b->ctx, b->base);
+    delete b;
+}
+
+// ------------------------------------------------------------------ keys
+static void derive_key_view(Ctx* ctx) {
+    const uint64_t* h = ctx->h_hdr.data();
+    KeyView& kv = ctx->kv;
+    kv.canon_tag = h[0];
+    // block 0 of derive_aes_key's message: prf_k[0..3] || canon_tag || H_digest[0..23]  (crypto/lpn.hpp:174-181)
+    uint64_t q[8] = {h[5], h[6], h[7], h[8], h[0], h[1], h[2], h[3]};
+    uint32_t w[16];
+    sha_block_from_le64(q, w);
+    ShaState st;
+    sha_init(st);
+    sha_compress(st, w);
+    for (int i = 0; i < 8; i++) kv.kd_mid[i] = st.h[i];
+    kv.digest3 = h[4];
+    kv.powg = reinterpret_cast<const Fp*>(ctx->d_blob + 73);
+    kv.H = ctx->d_blob + kBlobHdrWords;
+    kv.T0 = ctx->d_aes->t0;
+    kv.sbox = ctx->d_aes->sbox;
+    for (int i = 0; i < kLpnWords; i++) ctx->lpn_s.w[i] = h[9 + i];
+    ctx->have_keys = true;
+}
+
+static int ensure_blob(Ctx* ctx) {
+    if (ctx->d_blob) return PV_OK;
+    PV_CUDA(cudaMalloc((void**)&ctx->d_blob, kBlobBytes));
+    return PV_OK;
+}
+
+static int keys_from_host_blob(Ctx* ctx, const uint64_t* blob) {
+    int rc = ensure_blob(ctx);
+    if (rc) return rc;
+    PV_CUDA(cudaMemcpyAsync(ctx->d_blob, blob, kBlobBytes, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->h_hdr.assign(blob, blob + kBlobHdrWords);
+    derive_key_view(ctx);
+    return PV_OK;
+}
+
+// libstdc++ bucket counts: every value _Prime_rehash_policy::_M_next_bkt can return, ascending.
+static void build_prime_table(std::vector<uint64_t>& t) {
+    std::__detail::_Prime_rehash_policy pol;
+    uint64_t n = 1;
+    for (;;) {
+        uint64_t p = (uint64_t)pol._M_next_bkt((std::size_t)n);
+        if (!t.empty() && p <= t.back()) break;
+        t.push_back(p);
+        if (p >= (1ull << 40)) break;
+        n = p + 1;
+    }
+}
+
+}  // namespace pvacb
+
+using namespace pvacb;
+
+struct pvacb_ctx { Ctx c; };
+struct pvacb_batch { Batch b; };
+static inline Ctx* C(pvacb_ctx* x) { return reinterpret_cast<Ctx*>(x); }
+static inline const Ctx* C(const pvacb_ctx* x) { return reinterpret_cast<const Ctx*>(x); }
+static inline Batch* Bt(pvacb_batch* x) { return reinterpret_cast<Batch*>(x); }
+static inline const Batch* Bt(const pvacb_batch* x) { return reinterpret_cast<const Batch*>(x); }
+
+extern "C" {
+
+int pvacb_ctx_create(int device, pvacb_ctx** out) {
+    if (!out) return PV_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return PV_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return PV_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PV_E_CUDA;
+    if (prop.major < 10) {
+        fprintf(stderr, "pvacb: device %d is sm_%d%d; this library only contains sm_100a code\n", device, prop.major, prop.minor);
+        return PV_E_CUDA;
+    }
+    Ctx* ctx = new Ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PV_E_CUDA; }
+    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    AesTables t;
+    aes_make_tables(t);
+    if (cudaMalloc((void**)&ctx->d_aes, sizeof(AesTables)) != cudaSuccess) { delete ctx; return PV_E_CUDA; }
+    cudaMemcpy(ctx->d_aes, &t, sizeof t, cudaMemcpyHostToDevice);
+    std::vector<uint64_t> primes;
+    build_prime_table(primes);
+    ctx->n_primes = (int)primes.size();
+    cudaMalloc((void**)&ctx->d_primes, primes.size() * 8);
+    cudaMemcpy(ctx->d_primes, primes.data(), primes.size() * 8, cudaMemcpyHostToDevice);
+    *out = reinterpret_cast<pvacb_ctx*>(ctx);
+    return PV_OK;
+}
+
+void pvacb_ctx_destroy(pvacb_ctx* x) {
+    if (!x) return;
+    Ctx* ctx = C(x);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_blob);
+    cudaFree(ctx->d_aes);
+    cudaFree(ctx->d_primes);
+    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+
+const char* pvacb_last_error(const pvacb_ctx* x) { return x ? C(x)->last_error.c_str() : "null context"; }
+int pvacb_set_prf_mode(pvacb_ctx* x, int mode) {
+    if (!x || (mode != PRF_FAITHFUL && mode != PRF_LIVE)) return PV_E_ARG;
+    C(x)->prf_mode = mode;
+    return PV_OK;
+}
+int pvacb_get_prf_mode(const pvacb_ctx* x) { return C(x)->prf_mode; }
+void* pvacb_stream(pvacb_ctx* x) { return (void*)C(x)->stream; }
+int pvacb_sync(pvacb_ctx* x) {
+    Ctx* ctx = C(x);
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+void pvacb_stats(const pvacb_ctx* x, uint64_t* k, uint64_t* a, uint64_t* s) {
+    if (k) *k = C(x)->stat_kernel_launches;
+    if (a) *a = C(x)->stat_aes_blocks;
+    if (s) *s = C(x)->stat_sigma_edges;
+}
+void pvacb_stats_reset(pvacb_ctx* x) { C(x)->stat_kernel_launches = C(x)->stat_aes_blocks = C(x)->stat_sigma_edges = 0; }
+
+// ---- keys
+int pvacb_keygen(pvacb_ctx* x, uint64_t tape_state) {
+    Ctx* ctx = C(x);
+    std::vector<uint64_t> blob;
+    int rc = keygen_host(tape_state, blob);
+    if (rc) return rc;
+    return keys_from_host_blob(ctx, blob.data());
+}
+
+int pvacb_keys_import_raw(pvacb_ctx* x, uint64_t canon_tag, const uint8_t h_digest[32], const uint64_t* H, const uint64_t* powg,
+                          const uint64_t prf_k[4], const uint64_t* lpn_s) {
+    Ctx* ctx = C(x);
+    if (!h_digest || !prf_k || !lpn_s) return PV_E_ARG;
+    std::vector<uint64_t> blob(kBlobWords, 0);
+    blob[0] = canon_tag;
+    memcpy(&blob[1], h_digest, 32);
+    memcpy(&blob[5], prf_k, 32);
+    memcpy(&blob[9], lpn_s, kLpnWords * 8);
+    for (int i = 0; i < kB; i++) {
+        blob[73 + 2 * i] = powg ? powg[2 * i] : 1;
+        blob[73 + 2 * i + 1] = powg ? powg[2 * i + 1] : 0;
+    }
+    if (H) memcpy(&blob[kBlobHdrWords], H, (size_t)kNBits * kMWords * 8);
+    return keys_from_host_blob(ctx, blob.data());
+}
+
+int pvacb_keys_export_raw(pvacb_ctx* x, uint64_t* canon_tag, uint8_t h_digest[32], uint64_t* H, uint64_t* powg, uint64_t prf_k[4],
+                          uint64_t* lpn_s) {
+    Ctx* ctx = C(x);
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    const uint64_t* h = ctx->h_hdr.data();
+    if (canon_tag) *canon_tag = h[0];
+    if (h_digest) memcpy(h_digest, &h[1], 32);
+    if (prf_k) memcpy(prf_k, &h[5], 32);
+    if (lpn_s) memcpy(lpn_s, &h[9], kLpnWords * 8);
+    if (powg) memcpy(powg, &h[73], kB * 16);
+    if (H) {
+        PV_CUDA(cudaMemcpyAsync(H, ctx->d_blob + kBlobHdrWords, (size_t)kNBits * kMWords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return PV_OK;
+}
+
+int pvacb_keys_device_blob(pvacb_ctx* x, void** dptr, size_t* bytes) {
+    Ctx* ctx = C(x);
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    *dptr = ctx->d_blob;
+    if (bytes) *bytes = kBlobBytes;
+    return PV_OK;
+}
+int pvacb_keys_alloc_blob(pvacb_ctx* x, void** dptr) {
+    Ctx* ctx = C(x);
+    int rc = ensure_blob(ctx);
+    if (rc) return rc;
+    *dptr = ctx->d_blob;
+    return PV_OK;
+}
+int pvacb_keys_adopt_blob(pvacb_ctx* x) {
+    Ctx* ctx = C(x);
+    if (!ctx->d_blob) return PV_E_NOKEYS;
+    ctx->h_hdr.resize(kBlobHdrWords);
+    PV_CUDA(cudaMemcpy(ctx->h_hdr.data(), ctx->d_blob, kBlobHdrWords * 8, cudaMemcpyDeviceToHost));
+    derive_key_view(ctx);
+    return PV_OK;
+}
+
+// ---- ops
+int pvacb_enc_value_ex(pvacb_ctx* x, const uint64_t* values, size_t n, uint64_t seed, const uint64_t* tape_states, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    if (!out || (n && !values)) return PV_E_ARG;
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    cudaSetDevice(ctx->device);
+    Batch* b = nullptr;
+    int rc = op_enc_value(ctx, values, false, n, seed, tape_states, &b);
+    *out = reinterpret_cast<pvacb_batch*>(b);
+    return rc;
+}
+int pvacb_enc_value(pvacb_ctx* x, const uint64_t* values, size_t n, uint64_t seed, pvacb_batch** out) {
+    return pvacb_enc_value_ex(x, values, n, seed, nullptr, out);
+}
+static int binop(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, int mode, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    if (!a || !b || !out) return PV_E_ARG;
+    if (Bt(a)->n != Bt(b)->n) { ctx->last_error = "batches differ in length"; return PV_E_SHAPE; }
+    cudaSetDevice(ctx->device);
+    Batch* o = nullptr;
+    int rc = op_ct_add(ctx, Bt(a), Bt(b), mode, &o);
+    *out = reinterpret_cast<pvacb_batch*>(o);
+    return rc;
+}
+int pvacb_ct_add(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, pvacb_batch** out) { return binop(x, a, b, 0, out); }
+int pvacb_ct_sub(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, pvacb_batch** out) { return binop(x, a, b, 1, out); }
+int pvacb_ct_scale(pvacb_ctx* x, const pvacb_batch* a, const uint64_t s[2], pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    if (!a || !s || !out) return PV_E_ARG;
+    cudaSetDevice(ctx->device);
+    Batch* o = nullptr;
+    int rc = op_ct_scale(ctx, Bt(a), fp_from_words(s[0], s[1]), &o);
+    *out = reinterpret_cast<pvacb_batch*>(o);
+    return rc;
+}
+int pvacb_ct_mul_ex(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, uint64_t seed, const uint64_t* tape_states, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    if (!a || !b || !out) return PV_E_ARG;
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    if (Bt(a)->n != Bt(b)->n) { ctx->last_error = "batches differ in length"; return PV_E_SHAPE; }
+    cudaSetDevice(ctx->device);
+    Batch* o = nullptr;
+    int rc = op_ct_mul(ctx, Bt(a), Bt(b), seed, tape_states, &o);
+    *out = reinterpret_cast<pvacb_batch*>(o);
+    return rc;
+}
+int pvacb_ct_mul(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, uint64_t seed, pvacb_batch** out) {
+    return pvacb_ct_mul_ex(x, a, b, seed, nullptr, out);
+}
+int pvacb_dec_value(pvacb_ctx* x, const pvacb_batch* c, uint64_t* out) {
+    Ctx* ctx = C(x);
+    if (!c || !out) return PV_E_ARG;
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    cudaSetDevice(ctx->device);
+    return op_dec_value(ctx, Bt(c), out);
+}
+
+// ---- batches
+void pvacb_batch_free(pvacb_batch* b) { batch_free(Bt(b)); }
+size_t pvacb_batch_count(const pvacb_batch* b) { return b ? (size_t)Bt(b)->n : 0; }
+int pvacb_batch_totals(const pvacb_batch* b, uint64_t* nl, uint64_t* ne) {
+    if (!b) return PV_E_ARG;
+    if (nl) *nl = Bt(b)->nL;
+    if (ne) *ne = Bt(b)->nE;
+    return PV_OK;
+}
+size_t pvacb_batch_device_bytes(const pvacb_batch* b) { return b ? Bt(b)->bytes : 0; }
+
+int pvacb_batch_offsets(pvacb_ctx* x, const pvacb_batch* pb, uint32_t* loff, uint32_t* eoff) {
+    Ctx* ctx = C(x);
+    const Batch* b = Bt(pb);
+    if (loff) PV_CUDA(cudaMemcpyAsync(loff, b->loff, (b->n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (eoff) PV_CUDA(cudaMemcpyAsync(eoff, b->eoff, (b->n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+
+int pvacb_batch_export_soa(pvacb_ctx* x, const pvacb_batch* pb, uint32_t* loff, uint32_t* eoff, uint8_t* rule, uint64_t* ztag,
+                           uint64_t* nlo, uint64_t* nhi, uint32_t* pa, uint32_t* pbb, uint32_t* lid, uint16_t* idx, uint8_t* ch,
+                           uint64_t* w, uint64_t* sigma) {
+    Ctx* ctx = C(x);
+    const Batch* b = Bt(pb);
+    cudaSetDevice(ctx->device);
+    auto cp = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (!dst || !bytes) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    };
+    PV_CUDA(cp(loff, b->loff, (b->n + 1) * 4));
+    PV_CUDA(cp(eoff, b->eoff, (b->n + 1) * 4));
+    PV_CUDA(cp(rule, b->rule, b->nL));
+    PV_CUDA(cp(ztag, b->ztag, b->nL * 8));
+    PV_CUDA(cp(nlo, b->nlo, b->nL * 8));
+    PV_CUDA(cp(nhi, b->nhi, b->nL * 8));
+    PV_CUDA(cp(pa, b->pa, b->nL * 4));
+    PV_CUDA(cp(pbb, b->pb, b->nL * 4));
+    PV_CUDA(cp(lid, b->lid, b->nE * 4));
+    PV_CUDA(cp(idx, b->idx, b->nE * 2));
+    PV_CUDA(cp(ch, b->ch, b->nE));
+    PV_CUDA(cp(w, b->w, b->nE * 16));
+    PV_CUDA(cp(sigma, b->sigma, b->nE * (size_t)kMWords * 8));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+
+int pvacb_batch_import_soa(pvacb_ctx* x, size_t n, const uint32_t* loff, const uint32_t* eoff, const uint8_t* rule, const uint64_t* ztag,
+                           const uint64_t* nlo, const uint64_t* nhi, const uint32_t* pa, const uint32_t* pbb, const uint32_t* lid,
+                           const uint16_t* idx, const uint8_t* ch, const uint64_t* w, const uint64_t* sigma, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    if (!out || !loff || !eoff) return PV_E_ARG;
+    cudaSetDevice(ctx->device);
+    uint64_t nL = loff[n], nE = eoff[n];
+    if (loff[0] != 0 || eoff[0] != 0) return PV_E_FORMAT;
+    // validation the kernels rely on (the reference would index out of bounds instead)
+    for (size_t i = 0; i < n; i++) {
+        if (loff[i + 1] < loff[i] || eoff[i + 1] < eoff[i]) { ctx->last_error = "offsets not monotone"; return PV_E_FORMAT; }
+        uint32_t l = loff[i + 1] - loff[i];
+        for (uint32_t e = eoff[i]; e < eoff[i + 1]; e++) {
+            if (lid[e] >= l || idx[e] >= kB || ch[e] > 1) { ctx->last_error = "edge field out of range"; return PV_E_FORMAT; }
+            uint64_t hi = w[2 * e + 1], lo = w[2 * e];
+            if ((hi >> 63) || (hi == kMask63 && lo == ~0ull)) { ctx->last_error = "edge weight not canonical"; return PV_E_FORMAT; }
+        }
+        for (uint32_t k = loff[i]; k < loff[i + 1]; k++)
+            if (rule[k] > 1) { ctx->last_error = "unknown layer rule"; return PV_E_FORMAT; }
+    }
+    Batch* b = nullptr;
+    int rc = batch_alloc(ctx, n, nL, nE, &b);
+    if (rc) return rc;
+    auto cp = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (!bytes) return cudaSuccess;
+        if (!src) return cudaMemsetAsync(dst, 0, bytes, ctx->stream);
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    PV_CUDA(cp(b->loff, loff, (n + 1) * 4));
+    PV_CUDA(cp(b->eoff, eoff, (n + 1) * 4));
+    PV_CUDA(cp(b->rule, rule, nL));
+    PV_CUDA(cp(b->ztag, ztag, nL * 8));
+    PV_CUDA(cp(b->nlo, nlo, nL * 8));
+    PV_CUDA(cp(b->nhi, nhi, nL * 8));
+    PV_CUDA(cp(b->pa, pa, nL * 4));
+    PV_CUDA(cp(b->pb, pbb, nL * 4));
+    PV_CUDA(cp(b->lid, lid, nE * 4));
+    PV_CUDA(cp(b->idx, idx, nE * 2));
+    PV_CUDA(cp(b->ch, ch, nE));
+    PV_CUDA(cp(b->w, w, nE * 16));
+    PV_CUDA(cp(b->sigma, sigma, nE * (size_t)kMWords * 8));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = reinterpret_cast<pvacb_batch*>(b);
+    return PV_OK;
+}
+
+// ---- wire format (tests/bounty2_test.cpp:17-143)
+static const uint32_t kMagicCT = 0x66699666u, kWireVer = 1;
+
+struct HostSoA {
+    std::vector<uint32_t> loff, eoff, pa, pb, lid;
+    std::vector<uint8_t> rule, ch;
+    std::vector<uint64_t> ztag, nlo, nhi, w, sigma;
+    std::vector<uint16_t> idx;
+};
+
+static int to_host(pvacb_ctx* x, const pvacb_batch* pb, HostSoA& h, bool with_sigma) {
+    const Batch* b = Bt(pb);
+    h.loff.resize(b->n + 1); h.eoff.resize(b->n + 1);
+    h.rule.resize(b->nL); h.ztag.resize(b->nL); h.nlo.resize(b->nL); h.nhi.resize(b->nL); h.pa.resize(b->nL); h.pb.resize(b->nL);
+    h.lid.resize(b->nE); h.idx.resize(b->nE); h.ch.resize(b->nE); h.w.resize(b->nE * 2);
+    if (with_sigma) h.sigma.resize(b->nE * (size_t)kMWords);
+    return pvacb_batch_export_soa(x, pb, h.loff.data(), h.eoff.data(), h.rule.data(), h.ztag.data(), h.nlo.data(), h.nhi.data(), h.pa.data(),
+                                  h.pb.data(), h.lid.data(), h.idx.data(), h.ch.data(), h.w.data(), with_sigma ? h.sigma.data() : nullptr);
+}
+
+int pvacb_batch_wire_size(pvacb_ctx* x, const pvacb_batch* pb, size_t* bytes) {
+    const Batch* b = Bt(pb);
+    HostSoA h;
+    h.rule.resize(b->nL);
+    Ctx* ctx = C(x);
+    PV_CUDA(cudaMemcpy(h.rule.data(), b->rule, b->nL, cudaMemcpyDeviceToHost));
+    size_t s = 16 + b->n * 8;
+    for (uint8_t r : h.rule) s += 1 + (r == 1 ? 8 : 24);
+    s += b->nE * (size_t)(4 + 2 + 1 + 1 + 16 + 4 + kMWords * 8);
+    *bytes = s;
+    return PV_OK;
+}
+
+int pvacb_batch_export_wire(pvacb_ctx* x, const pvacb_batch* pb, void* buf, size_t cap, size_t* written) {
+    Ctx* ctx = C(x);
+    const Batch* b = Bt(pb);
+    HostSoA h;
+    int rc = to_host(x, pb, h, true);
+    if (rc) return rc;
+    uint8_t* p = (uint8_t*)buf;
+    size_t off = 0;
+    auto put = [&](const void* src, size_t nbytes) -> bool {
+        if (off + nbytes > cap) return false;
+        memcpy(p + off, src, nbytes);
+        off += nbytes;
+        return true;
+    };
+    uint64_t cnt = b->n;
+    bool ok = put(&kMagicCT, 4) && put(&kWireVer, 4) && put(&cnt, 8);
+    for (uint64_t i = 0; ok && i < b->n; i++) {
+        uint32_t nl = h.loff[i + 1] - h.loff[i], ne = h.eoff[i + 1] - h.eoff[i];
+        ok = put(&nl, 4) && put(&ne, 4);
+        for (uint32_t k = h.loff[i]; ok && k < h.loff[i + 1]; k++) {
+            ok = put(&h.rule[k], 1);
+            if (h.rule[k] == 0) ok = ok && put(&h.ztag[k], 8) && put(&h.nlo[k], 8) && put(&h.nhi[k], 8);
+            else ok = ok && put(&h.pa[k], 4) && put(&h.pb[k], 4);
+        }
+        for (uint32_t e = h.eoff[i]; ok && e < h.eoff[i + 1]; e++) {
+            uint8_t zero = 0;
+            uint32_t nbits = kMBits;
+            ok = put(&h.lid[e], 4) && put(&h.idx[e], 2) && put(&h.ch[e], 1) && put(&zero, 1) && put(&h.w[2 * e], 16) && put(&nbits, 4) &&
+                 put(&h.sigma[(size_t)e * kMWords], kMWords * 8);
+        }
+    }
+    if (!ok) { ctx->last_error = "wire buffer too small"; return PV_E_ARG; }
+    if (written) *written = off;
+    return PV_OK;
+}
+
+int pvacb_batch_import_wire(pvacb_ctx* x, const void* buf, size_t bytes, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    const uint8_t* p = (const uint8_t*)buf;
+    size_t off = 0;
+    auto get = [&](void* dst, size_t nbytes) -> bool {
+        if (off + nbytes > bytes) return false;
+        memcpy(dst, p + off, nbytes);
+        off += nbytes;
+        return true;
+    };
+    uint32_t magic = 0, ver = 0;
+    uint64_t cnt = 0;
+    if (!get(&magic, 4) || !get(&ver, 4) || !get(&cnt, 8) || magic != kMagicCT || ver != kWireVer) { ctx->last_error = "bad CT header"; return PV_E_FORMAT; }
+    HostSoA h;
+    h.loff.push_back(0); h.eoff.push_back(0);
+    for (uint64_t i = 0; i < cnt; i++) {
+        uint32_t nl = 0, ne = 0;
+        if (!get(&nl, 4) || !get(&ne, 4)) return PV_E_FORMAT;
+        for (uint32_t k = 0; k < nl; k++) {
+            uint8_t r = 0;
+            uint64_t a = 0, b = 0, c = 0;
+            uint32_t pa = 0, pb = 0;
+            if (!get(&r, 1)) return PV_E_FORMAT;
+            if (r == 1) { if (!get(&pa, 4) || !get(&pb, 4)) return PV_E_FORMAT; }
+            else if (!get(&a, 8) || !get(&b, 8) || !get(&c, 8)) return PV_E_FORMAT;
+            h.rule.push_back(r); h.ztag.push_back(a); h.nlo.push_back(b); h.nhi.push_back(c); h.pa.push_back(pa); h.pb.push_back(pb);
+        }
+        for (uint32_t e = 0; e < ne; e++) {
+            uint32_t lid = 0, nbits = 0;
+            uint16_t idx = 0;
+            uint8_t ch = 0, pad = 0;
+            uint64_t w[2];
+            if (!get(&lid, 4) || !get(&idx, 2) || !get(&ch, 1) || !get(&pad, 1) || !get(w, 16) || !get(&nbits, 4)) return PV_E_FORMAT;
+            if (nbits != kMBits) { ctx->last_error = "sigma length is not m_bits"; return PV_E_FORMAT; }
+            size_t so = h.sigma.size();
+            h.sigma.resize(so + kMWords);
+            if (!get(&h.sigma[so], kMWords * 8)) return PV_E_FORMAT;
+            h.lid.push_back(lid); h.idx.push_back(idx); h.ch.push_back(ch); h.w.push_back(w[0]); h.w.push_back(w[1]);
+        }
+        h.loff.push_back((uint32_t)h.rule.size());
+        h.eoff.push_back((uint32_t)h.lid.size());
+    }
+    return pvacb_batch_import_soa(x, cnt, h.loff.data(), h.eoff.data(), h.rule.data(), h.ztag.data(), h.nlo.data(), h.nhi.data(), h.pa.data(),
+                                  h.pb.data(), h.lid.data(), h.idx.data(), h.ch.data(), h.w.data(), h.sigma.data(), out);
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Internal host-side declarations of the pvacb engine (not part of the C ABI; see include/pvacb.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <vector>
+#include <string>
+
+#include "common.cuh"
+#include "fp127.cuh"
+#include "aes256.cuh"
+
+namespace pvacb {
+
+// ---- device-resident key material. One flat "key blob" (what is replicated across GPUs) + derived tables.
+// blob layout (little-endian u64 words):
+//   [0]            canon_tag
+//   [1..4]         H_digest (32 bytes)
+//   [5..8]         prf_k[4]
+//   [9..72]        lpn_s[64]
+//   [73..746]      powg_B[337] as (lo,hi)
+//   [747]          reserved (0)
+//   [748..]        H : 16384 columns x 128 words
+constexpr size_t kBlobHdrWords = 748;
+constexpr size_t kBlobWords = kBlobHdrWords + (size_t)kNBits * kMWords;
+constexpr size_t kBlobBytes = kBlobWords * 8;
+
+struct LpnSecret {
+    uint64_t w[kLpnWords];
+};
+
+struct KeyView {             // passed by value to kernels (pointers into the device blob)
+    uint64_t canon_tag;
+    uint32_t kd_mid[8];      // SHA-256 state after block 0 of derive_aes_key's message (crypto/lpn.hpp:166-192)
+    uint64_t digest3;        // LE64(H_digest[24..31]) = first word of block 1
+    const uint64_t* H;       // [16384][128]
+    const Fp* powg;          // [337]
+    const uint32_t* T0;      // [256] AES T-table
+    const uint8_t* sbox;     // [256]
+};
+
+enum PrfMode : int { PRF_FAITHFUL = 0, PRF_LIVE = 1 };
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;
+    int sm_count = 148;
+    bool have_keys = false;
+    uint64_t* d_blob = nullptr;      // kBlobBytes
+    AesTables* d_aes = nullptr;
+    uint64_t* d_primes = nullptr;    // libstdc++ bucket-count table
+    int n_primes = 0;
+    KeyView kv{};
+    LpnSecret lpn_s{};
+    std::vector<uint64_t> h_hdr;     // host copy of the blob header
+    int prf_mode = PRF_FAITHFUL;
+    int z2 = 3, z3 = 2;              // plan_noise(depth 0)
+    std::string last_error;
+    // statistics of the last call (for bench.py)
+    uint64_t stat_kernel_launches = 0;
+    uint64_t stat_aes_blocks = 0;
+    uint64_t stat_sigma_edges = 0;
+    float stat_ms[8] = {0};          // per-stage CUDA-event timings of the last op when profiling is on
+    int profile = 0;
+    bool lpn_attr_set = false;
+};
+
+// device ciphertext batch, structure-of-arrays
+struct Batch {
+    Ctx* ctx = nullptr;
+    uint64_t n = 0;          // ciphertexts
+    uint64_t nL = 0, nE = 0; // total layers / edges
+    void* base = nullptr;    // one allocation
+    size_t bytes = 0;
+    uint32_t* loff = nullptr;  // [n+1]
+    uint32_t* eoff = nullptr;  // [n+1]
+    uint8_t* rule = nullptr;   // [nL]
+    uint64_t* ztag = nullptr;  // [nL]
+    uint64_t* nlo = nullptr;
+    uint64_t* nhi = nullptr;
+    uint32_t* pa = nullptr;
+    uint32_t* pb = nullptr;
+    uint32_t* lid = nullptr;   // [nE] layer id relative to the ciphertext
+    uint16_t* idx = nullptr;   // [nE]
+    uint8_t* ch = nullptr;     // [nE]
+    Fp* w = nullptr;           // [nE] 16-byte aligned
+    uint64_t* sigma = nullptr; // [nE][128]
+};
+
+// status codes (mirrored in include/pvacb.h)
+enum : int {
+    PV_OK = 0,
+    PV_E_ARG = 1,
+    PV_E_CUDA = 2,
+    PV_E_OOM = 3,
+    PV_E_NOKEYS = 4,
+    PV_E_EDGE_BUDGET = 5,   // result would exceed Params::edge_budget (reference: guard_budget -> compact_edges)
+    PV_E_LAYER_GRAPH = 6,   // parent out of range / cycle (reference: std::abort in layer_R_cached)
+    PV_E_RARE_PATH = 7,     // a 2^-61-probability rejection-sampling branch was hit (not supported on device)
+    PV_E_DUP_EDGE = 8,      // input holds two edges with equal (layer, idx, sign); run compaction first
+    PV_E_FORMAT = 9,
+    PV_E_SHAPE = 10,
+};
+
+#define PV_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ctx->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);           \
+            return (_e == cudaErrorMemoryAllocation) ? PV_E_OOM : PV_E_CUDA;                \
+        }                                                                                   \
+    } while (0)
+
+int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out);
+void batch_free(Batch* b);
+
+// scratch allocator: stream-ordered
+int dev_alloc(Ctx* ctx, void** p, size_t bytes);
+void dev_free(Ctx* ctx, void* p);
+
+// ---- PRF (prf.cu): out[j] = prf_R(seed_j) (family 0) or prf_R_noise(seed_j) (family 1); inactive jobs give 0
+int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_nlo, const uint64_t* d_nhi,
+            const uint8_t* d_flags /*bit0 family, bit1 active*/, Fp* d_out, uint64_t* d_ybits_out /*optional debug: [njobs*3][rows/64]*/);
+
+// ---- sigma (sigma.cu): one sigma_from_H per job, written to row out_row[job] (1 KiB rows) of `out`
+struct SigmaJobs {
+    uint64_t n = 0;
+    const uint64_t* ztag = nullptr;     // layer seed tables, indexed by seed_idx[job] (or by job if seed_idx == nullptr)
+    const uint64_t* nlo = nullptr;
+    const uint64_t* nhi = nullptr;
+    const uint32_t* seed_idx = nullptr;
+    const uint16_t* idx = nullptr;      // [n]
+    const uint8_t* ch = nullptr;        // [n]
+    const uint64_t* salt = nullptr;     // [n]
+    const uint32_t* out_row = nullptr;  // [n] or nullptr (row = job)
+    uint64_t* out = nullptr;            // rows [0, out_split)
+    uint64_t out_split = ~0ull;         // rows >= out_split live in out2 (scratch rows of merged enc_value edges)
+    uint64_t* out2 = nullptr;
+};
+int sigma_run(Ctx* ctx, const SigmaJobs& jobs);
+// out[dst] ^= row src for every pair (dst_row, src_row); rows >= split are taken from out2
+int sigma_xor_rows(Ctx* ctx, uint64_t npairs, const uint2* d_pairs, uint64_t* out, uint64_t split, const uint64_t* out2);
+// exclusive scan of n u32 counts into n+1 offsets (arith.cu)
+int scan_u32(Ctx* ctx, uint64_t n, const uint32_t* in, uint32_t* out);
+
+// ---- ops
+int op_enc_value(Ctx* ctx, const uint64_t* h_or_d_values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out);
+int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode /*0 add, 1 sub*/, Batch** out);
+int op_ct_scale(Ctx* ctx, const Batch* A, Fp s, Batch** out);
+int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, const uint64_t* h_states, Batch** out);
+int op_dec_value(Ctx* ctx, const Batch* C, uint64_t* h_out /*n x 2*/);
+
+// compact_layers (ops/encrypt.hpp:73-104) of every ciphertext of b, in place (layer arrays shrink, edges stay).
+int compact_layers_batch(Ctx* ctx, Batch* b);
+
+}  // namespace pvacb

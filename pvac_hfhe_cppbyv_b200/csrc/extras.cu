@@ -1,0 +1,210 @@
+// Entry points around the hot path: batch slicing, synthetic benchmark batches, and the device building blocks exposed
+// for parity tests (pvacb_prf, pvacb_sigma_from_H, pvacb_fp_op). All of them run CUDA kernels; none has a CPU path.
+#include "engine.h"
+#include "../../include/pvacb.h"
+
+#include <vector>
+
+using namespace pvacb;
+
+namespace pvacb {
+
+__global__ void fp_op_kernel(int op, uint64_t n, const Fp* __restrict__ a, const Fp* __restrict__ b, Fp* __restrict__ o) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x = a[i], y = b ? b[i] : fp_zero(), r;
+    switch (op) {
+        case 0: r = fp_add(x, y); break;
+        case 1: r = fp_sub(x, y); break;
+        case 2: r = fp_mul(x, y); break;
+        case 3: r = fp_neg(x); break;
+        default: r = fp_inv(x); break;
+    }
+    o[i] = r;
+}
+
+__global__ void fill_flags_kernel(uint64_t n, uint8_t v, uint8_t* f) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f[i] = v;
+}
+
+// synthetic fresh-shaped ciphertexts: L = 2 BASE layers, epl edges per layer, uniform fields
+__global__ void synth_meta_kernel(uint64_t n, int epl, uint64_t seed, uint32_t* loff, uint32_t* eoff, uint8_t* rule, uint64_t* ztag, uint64_t* nlo,
+                                  uint64_t* nhi, uint32_t* pa, uint32_t* pb, uint32_t* lid, uint16_t* idx, uint8_t* ch, Fp* w) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    loff[i] = (uint32_t)(2 * i);
+    eoff[i] = (uint32_t)(2 * epl * i);
+    if (i == n) return;
+    Tape t{item_stream_state(seed, i), 0};
+    for (int l = 0; l < 2; l++) {
+        uint64_t L = 2 * i + l;
+        rule[L] = 0; nlo[L] = t.next(); nhi[L] = t.next(); ztag[L] = t.next(); pa[L] = 0; pb[L] = 0;
+        for (int k = 0; k < epl; k++) {
+            uint64_t e = (2 * i + l) * (uint64_t)epl + k;
+            lid[e] = l;
+            idx[e] = (uint16_t)(t.next() % kB);
+            ch[e] = (uint8_t)(t.next() & 1);
+            w[e] = fp_from_words(t.next(), t.next() & kMask63);
+        }
+    }
+}
+__global__ void synth_sigma_kernel(uint64_t nwords, uint64_t seed, uint64_t* sigma) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < nwords; i += stride) sigma[i] = mix64(seed ^ (i * 0x9E3779B97F4A7C15ull));
+}
+
+__global__ void slice_fix_offsets_kernel(uint64_t cnt, const uint32_t* src_l, const uint32_t* src_e, uint32_t* dst_l, uint32_t* dst_e) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > cnt) return;
+    dst_l[i] = src_l[i] - src_l[0];
+    dst_e[i] = src_e[i] - src_e[0];
+}
+
+}  // namespace pvacb
+
+static inline Ctx* C(pvacb_ctx* x) { return reinterpret_cast<Ctx*>(x); }
+static inline const Batch* Bt(const pvacb_batch* x) { return reinterpret_cast<const Batch*>(x); }
+
+extern "C" {
+
+int pvacb_fp_op(pvacb_ctx* x, int op, size_t n, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    Ctx* ctx = C(x);
+    if (!a || !out || op < 0 || op > 4) return PV_E_ARG;
+    if (n == 0) return PV_OK;
+    cudaSetDevice(ctx->device);
+    Fp *da = nullptr, *db = nullptr, *dout = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, (void**)&da, n * 16))) return rc;
+    if ((rc = dev_alloc(ctx, (void**)&dout, n * 16))) return rc;
+    PV_CUDA(cudaMemcpyAsync(da, a, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) {
+        if ((rc = dev_alloc(ctx, (void**)&db, n * 16))) return rc;
+        PV_CUDA(cudaMemcpyAsync(db, b, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    fp_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(op, n, da, db, dout);
+    PV_CUDA(cudaGetLastError());
+    ctx->stat_kernel_launches += 1;
+    PV_CUDA(cudaMemcpyAsync(out, dout, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, da); dev_free(ctx, db); dev_free(ctx, dout);
+    return PV_OK;
+}
+
+int pvacb_prf(pvacb_ctx* x, size_t n, const uint64_t* ztag, const uint64_t* nlo, const uint64_t* nhi, int family, uint64_t* out, uint64_t* ybits) {
+    Ctx* ctx = C(x);
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    if (!ztag || !nlo || !nhi || !out) return PV_E_ARG;
+    if (n == 0) return PV_OK;
+    cudaSetDevice(ctx->device);
+    uint64_t *dz, *dl, *dh, *dy = nullptr;
+    uint8_t* fl;
+    Fp* dout;
+    int rc;
+    const size_t wpc = ctx->prf_mode == PRF_LIVE ? 2 : kLpnT / 64;
+    if ((rc = dev_alloc(ctx, (void**)&dz, n * 8)) || (rc = dev_alloc(ctx, (void**)&dl, n * 8)) || (rc = dev_alloc(ctx, (void**)&dh, n * 8)) ||
+        (rc = dev_alloc(ctx, (void**)&fl, n)) || (rc = dev_alloc(ctx, (void**)&dout, n * 16)))
+        return rc;
+    if (ybits && (rc = dev_alloc(ctx, (void**)&dy, n * 3 * wpc * 8))) return rc;
+    PV_CUDA(cudaMemcpyAsync(dz, ztag, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(dl, nlo, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(dh, nhi, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    fill_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, (uint8_t)(2 | (family & 1)), fl);
+    ctx->stat_kernel_launches += 1;
+    rc = prf_run(ctx, n, dz, dl, dh, fl, dout, dy);
+    if (!rc) {
+        PV_CUDA(cudaMemcpyAsync(out, dout, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ybits) PV_CUDA(cudaMemcpyAsync(ybits, dy, n * 3 * wpc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    dev_free(ctx, dz); dev_free(ctx, dl); dev_free(ctx, dh); dev_free(ctx, fl); dev_free(ctx, dout); dev_free(ctx, dy);
+    return rc;
+}
+
+int pvacb_sigma_from_H(pvacb_ctx* x, size_t n, const uint64_t* ztag, const uint64_t* nlo, const uint64_t* nhi, const uint16_t* idx, const uint8_t* ch,
+                       const uint64_t* salt, uint64_t* out) {
+    Ctx* ctx = C(x);
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    if (!ztag || !nlo || !nhi || !idx || !ch || !salt || !out) return PV_E_ARG;
+    if (n == 0) return PV_OK;
+    cudaSetDevice(ctx->device);
+    uint64_t *dz, *dl, *dh, *ds, *dout;
+    uint16_t* di;
+    uint8_t* dc;
+    int rc;
+    if ((rc = dev_alloc(ctx, (void**)&dz, n * 8)) || (rc = dev_alloc(ctx, (void**)&dl, n * 8)) || (rc = dev_alloc(ctx, (void**)&dh, n * 8)) ||
+        (rc = dev_alloc(ctx, (void**)&ds, n * 8)) || (rc = dev_alloc(ctx, (void**)&di, n * 2)) || (rc = dev_alloc(ctx, (void**)&dc, n)) ||
+        (rc = dev_alloc(ctx, (void**)&dout, n * (size_t)kMWords * 8)))
+        return rc;
+    PV_CUDA(cudaMemcpyAsync(dz, ztag, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(dl, nlo, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(dh, nhi, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(ds, salt, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(di, idx, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(dc, ch, n, cudaMemcpyHostToDevice, ctx->stream));
+    SigmaJobs J;
+    J.n = n; J.ztag = dz; J.nlo = dl; J.nhi = dh; J.idx = di; J.ch = dc; J.salt = ds; J.out = dout;
+    rc = sigma_run(ctx, J);
+    if (!rc) {
+        PV_CUDA(cudaMemcpyAsync(out, dout, n * (size_t)kMWords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    dev_free(ctx, dz); dev_free(ctx, dl); dev_free(ctx, dh); dev_free(ctx, ds); dev_free(ctx, di); dev_free(ctx, dc); dev_free(ctx, dout);
+    return rc;
+}
+
+int pvacb_batch_synthetic(pvacb_ctx* x, size_t n, int epl, uint64_t seed, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    if (!out || epl < 0 || epl > 4096) return PV_E_ARG;
+    cudaSetDevice(ctx->device);
+    if ((uint64_t)n * 2 * epl >= (1ull << 32)) return PV_E_SHAPE;
+    Batch* b = nullptr;
+    int rc = batch_alloc(ctx, n, 2 * n, (uint64_t)n * 2 * epl, &b);
+    if (rc) return rc;
+    synth_meta_kernel<<<(unsigned)((n + 1 + 127) / 128), 128, 0, ctx->stream>>>(n, epl, seed, b->loff, b->eoff, b->rule, b->ztag, b->nlo, b->nhi, b->pa, b->pb,
+                                                                                 b->lid, b->idx, b->ch, b->w);
+    uint64_t nwords = b->nE * (uint64_t)kMWords;
+    if (nwords) synth_sigma_kernel<<<(unsigned)ctx->sm_count * 16, 256, 0, ctx->stream>>>(nwords, seed, b->sigma);
+    PV_CUDA(cudaGetLastError());
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stat_kernel_launches += 2;
+    *out = reinterpret_cast<pvacb_batch*>(b);
+    return PV_OK;
+}
+
+int pvacb_batch_slice(pvacb_ctx* x, const pvacb_batch* pb, size_t first, size_t count, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    const Batch* s = Bt(pb);
+    if (!out || first + count > s->n) return PV_E_ARG;
+    cudaSetDevice(ctx->device);
+    uint32_t h[4];
+    PV_CUDA(cudaMemcpyAsync(&h[0], s->loff + first, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(&h[1], s->loff + first + count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(&h[2], s->eoff + first, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(&h[3], s->eoff + first + count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t l0 = h[0], nL = h[1] - h[0], e0 = h[2], nE = h[3] - h[2];
+    Batch* b = nullptr;
+    int rc = batch_alloc(ctx, count, nL, nE, &b);
+    if (rc) return rc;
+    slice_fix_offsets_kernel<<<(unsigned)((count + 1 + 255) / 256), 256, 0, ctx->stream>>>(count, s->loff + first, s->eoff + first, b->loff, b->eoff);
+    auto cp = [&](void* d, const void* sp, size_t bytes) { return bytes ? cudaMemcpyAsync(d, sp, bytes, cudaMemcpyDeviceToDevice, ctx->stream) : cudaSuccess; };
+    PV_CUDA(cp(b->rule, s->rule + l0, nL));
+    PV_CUDA(cp(b->ztag, s->ztag + l0, nL * 8));
+    PV_CUDA(cp(b->nlo, s->nlo + l0, nL * 8));
+    PV_CUDA(cp(b->nhi, s->nhi + l0, nL * 8));
+    PV_CUDA(cp(b->pa, s->pa + l0, nL * 4));
+    PV_CUDA(cp(b->pb, s->pb + l0, nL * 4));
+    PV_CUDA(cp(b->lid, s->lid + e0, nE * 4));
+    PV_CUDA(cp(b->idx, s->idx + e0, nE * 2));
+    PV_CUDA(cp(b->ch, s->ch + e0, nE));
+    PV_CUDA(cp(b->w, s->w + e0, nE * 16));
+    PV_CUDA(cp(b->sigma, s->sigma + e0 * kMWords, nE * (size_t)kMWords * 8));
+    PV_CUDA(cudaGetLastError());
+    ctx->stat_kernel_launches += 1;
+    *out = reinterpret_cast<pvacb_batch*>(b);
+    return PV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+// ct_mul (ops/arithmetic.hpp:47-106) for a batch of ciphertext pairs.
+//
+// Reference per pair: new PROD layers (nonce from the tape + ztag hash) for every (la, lb); all |A.E|*|B.E| weight products
+// accumulated in a std::unordered_map keyed by (layer pair, (idxa+idxb) mod B) with separate sums for equal / unequal
+// signs; one output edge per non-zero sum IN THE MAP'S ITERATION ORDER, each drawing a salt and a fresh sigma_from_H;
+// compact_layers. Batched restatement:
+//   mul_count_kernel    per pair: layer / key counts, libstdc++ bucket count for reserve(|A.E|*|B.E|)
+//   mul_layers_kernel   pre-compaction layer table (A, B shifted, PROD with tape nonces and SHA-256 ztag)
+//   mul_bylayer_kernel  edges of A and B grouped by layer (counting sort per ciphertext)
+//   mul_pairs_kernel    one CTA per (pair, la, lb): B's layer as a dense (idx, sign) table in shared memory, one thread per
+//                       output residue s accumulates sum_{ea} w_a * w_b[(s - idx_a) mod B] and the first insertion time
+//   mul_bucket_*        first-occupation time of every hash bucket (open-addressing table, atomicMin)
+//   radix sort          keys of each pair ordered by (bucket time desc, insertion time desc) = libstdc++ iteration order
+//   mul_emit_*          P / M edges, salts from the tape in emission order
+//   sigma_run           one sigma_from_H per output edge (sigma.cu) -- > 99% of the time
+//   compact_layers_batch
+#include "engine.h"
+#include "sha256.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+namespace pvacb {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+struct MulCounts {          // per pair
+    uint32_t nLpre;         // LA + LB + LA*LB
+    uint32_t nLP;           // LA*LB
+    uint32_t nKeys;         // LA*LB*B
+    uint32_t tblSize;       // bucket-time table slots (power of two)
+};
+
+__device__ __forceinline__ uint64_t next_bkt(const uint64_t* __restrict__ primes, int np, uint64_t n) {
+    int lo = 0, hi = np - 1;            // smallest table entry >= n (std::lower_bound, as _Prime_rehash_policy::_M_next_bkt)
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (primes[mid] < n) lo = mid + 1; else hi = mid;
+    }
+    return primes[lo];
+}
+
+__global__ void mul_count_kernel(uint64_t n, const uint32_t* __restrict__ la, const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ea,
+                                 const uint32_t* __restrict__ eb, const uint64_t* __restrict__ primes, int np, uint32_t* __restrict__ c_lpre,
+                                 uint32_t* __restrict__ c_lp, uint32_t* __restrict__ c_keys, uint32_t* __restrict__ c_tbl, uint64_t* __restrict__ nb,
+                                 unsigned long long* __restrict__ max_pairs /*[0] max pairs, [1] sum keys, [2] sum table slots*/,
+                                 unsigned int* __restrict__ err) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t LA = la[i + 1] - la[i], LB = lb[i + 1] - lb[i], EA = ea[i + 1] - ea[i], EB = eb[i + 1] - eb[i];
+    uint64_t lp = LA * LB, keys = lp * kB, pairs = EA * EB;
+    if (lp > 0xFFFFFFull || keys >= (1ull << 31) || pairs >= (1ull << 31)) { atomicOr(err, 1u); lp = keys = pairs = 0; }
+    c_lpre[i] = (uint32_t)(LA + LB + lp);
+    c_lp[i] = (uint32_t)lp;
+    c_keys[i] = (uint32_t)keys;
+    uint64_t present_max = keys < pairs ? keys : pairs;
+    uint32_t t = 2;
+    while (t < 2 * present_max) t <<= 1;
+    c_tbl[i] = present_max ? t : 0;
+    nb[i] = pairs ? next_bkt(primes, np, pairs) : 1;
+    atomicMax(max_pairs, (unsigned long long)pairs);
+    atomicAdd(max_pairs + 1, (unsigned long long)keys);
+    atomicAdd(max_pairs + 2, (unsigned long long)c_tbl[i]);
+}
+
+// one CTA per pair
+__global__ void __launch_bounds__(128)
+mul_layers_kernel(uint64_t n, uint64_t batch_seed, const uint64_t* __restrict__ states, uint64_t canon_tag, const uint32_t* __restrict__ loA, const uint32_t* __restrict__ loB,
+                  const uint8_t* __restrict__ ruleA, const uint64_t* __restrict__ ztA, const uint64_t* __restrict__ nlA, const uint64_t* __restrict__ nhA,
+                  const uint32_t* __restrict__ paA, const uint32_t* __restrict__ pbA, const uint8_t* __restrict__ ruleB, const uint64_t* __restrict__ ztB,
+                  const uint64_t* __restrict__ nlB, const uint64_t* __restrict__ nhB, const uint32_t* __restrict__ paB, const uint32_t* __restrict__ pbB,
+                  const uint32_t* __restrict__ loP, const uint32_t* __restrict__ lpoff, uint8_t* __restrict__ rule, uint64_t* __restrict__ zt,
+                  uint64_t* __restrict__ nl, uint64_t* __restrict__ nh, uint32_t* __restrict__ pa, uint32_t* __restrict__ pb,
+                  uint32_t* __restrict__ lp_item) {
+    const uint64_t i = blockIdx.x;
+    const uint32_t a0 = loA[i], LA = loA[i + 1] - a0, b0 = loB[i], LB = loB[i + 1] - b0, o0 = loP[i];
+    for (uint32_t k = threadIdx.x; k < LA; k += blockDim.x) {
+        rule[o0 + k] = ruleA[a0 + k]; zt[o0 + k] = ztA[a0 + k]; nl[o0 + k] = nlA[a0 + k]; nh[o0 + k] = nhA[a0 + k];
+        pa[o0 + k] = paA[a0 + k]; pb[o0 + k] = pbA[a0 + k];
+    }
+    for (uint32_t k = threadIdx.x; k < LB; k += blockDim.x) {
+        uint8_t r = ruleB[b0 + k];
+        uint32_t off = r == 1 ? LA : 0;
+        rule[o0 + LA + k] = r; zt[o0 + LA + k] = ztB[b0 + k]; nl[o0 + LA + k] = nlB[b0 + k]; nh[o0 + LA + k] = nhB[b0 + k];
+        pa[o0 + LA + k] = paB[b0 + k] + off; pb[o0 + LA + k] = pbB[b0 + k] + off;
+    }
+    if (o0 + LA + LB + LA * LB != loP[i + 1]) return;   // shape overflow was flagged by mul_count_kernel
+    const uint64_t s0 = states ? states[i] : item_stream_state(batch_seed, i);
+    const uint32_t base = o0 + LA + LB, lp0 = lpoff[i];
+    for (uint32_t lp = threadIdx.x; lp < LA * LB; lp += blockDim.x) {   // ops/arithmetic.hpp:59-70, row-major (la, lb)
+        uint64_t nlo = tape_word(s0, 2ull * lp), nhi = tape_word(s0, 2ull * lp + 1);
+        rule[base + lp] = 1;
+        nl[base + lp] = nlo; nh[base + lp] = nhi;
+        zt[base + lp] = prg_layer_ztag(canon_tag, nlo, nhi);
+        pa[base + lp] = lp / LB;
+        pb[base + lp] = LA + lp % LB;
+        lp_item[lp0 + lp] = (uint32_t)i;
+    }
+}
+
+// edges of one batch grouped by layer: order[eoff[i] + k] = local edge ids sorted by layer; lstart[loff[i] + l] = first k
+__global__ void __launch_bounds__(128)
+mul_bylayer_kernel(const uint32_t* __restrict__ loff, const uint32_t* __restrict__ eoff, const uint32_t* __restrict__ lid, uint32_t* __restrict__ lstart,
+                   uint32_t* __restrict__ lcount, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order, unsigned int* __restrict__ err) {
+    const uint64_t i = blockIdx.x;
+    const uint32_t l0 = loff[i], L = loff[i + 1] - l0, e0 = eoff[i], E = eoff[i + 1] - e0;
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) lcount[l0 + l] = 0;
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < E; e += blockDim.x) {
+        uint32_t l = lid[e0 + e];
+        if (l >= L) { atomicOr(err, 2u); continue; }
+        atomicAdd(&lcount[l0 + l], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t l = 0; l < L; l++) { lstart[l0 + l] = run; cursor[l0 + l] = run; run += lcount[l0 + l]; }
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < E; e += blockDim.x) {
+        uint32_t l = lid[e0 + e];
+        if (l >= L) continue;
+        uint32_t k = atomicAdd(&cursor[l0 + l], 1u);
+        order[e0 + k] = e;
+    }
+}
+
+struct EdgeView {
+    const uint32_t *loff, *eoff;
+    const uint16_t* idx;
+    const uint8_t* ch;
+    const Fp* w;
+    const uint32_t *lstart, *lcount, *order;
+};
+
+constexpr int kPairThreads = 352;   // >= B = 337 residues
+
+// one CTA per (pair, la, lb)
+__global__ void __launch_bounds__(kPairThreads)
+mul_pairs_kernel(EdgeView A, EdgeView Bv, const uint32_t* __restrict__ lp_item, const uint32_t* __restrict__ lpoff, const uint32_t* __restrict__ koff,
+                 Fp* __restrict__ k_wp, Fp* __restrict__ k_wm, uint8_t* __restrict__ k_flags, uint32_t* __restrict__ k_tins,
+                 unsigned int* __restrict__ err) {
+    __shared__ Fp s_w[kB * 2];
+    __shared__ uint32_t s_ib[kB * 2];
+    const uint32_t g = blockIdx.x;
+    const uint32_t i = lp_item[g];
+    const uint32_t lp = g - lpoff[i];
+    const uint32_t LB = Bv.loff[i + 1] - Bv.loff[i];
+    const uint32_t la = lp / LB, lb = lp % LB;
+    const uint32_t EB = Bv.eoff[i + 1] - Bv.eoff[i];
+    const uint32_t a_l = A.loff[i] + la, b_l = Bv.loff[i] + lb;
+    const uint32_t nA = A.lcount[a_l], nB = Bv.lcount[b_l];
+    const uint32_t kbase = koff[i] + lp * kB;
+    const int s = threadIdx.x;
+    if (nA == 0 || nB == 0) {
+        if (s < kB) { k_tins[kbase + s] = kNone; k_flags[kbase + s] = 0; }
+        return;
+    }
+    for (int k = s; k < kB * 2; k += kPairThreads) s_ib[k] = kNone;
+    __syncthreads();
+    const uint32_t ea0 = A.eoff[i], eb0 = Bv.eoff[i];
+    for (uint32_t k = s; k < nB; k += kPairThreads) {
+        uint32_t ib = Bv.order[eb0 + Bv.lstart[b_l] + k];
+        uint32_t slot = (uint32_t)Bv.idx[eb0 + ib] * 2 + Bv.ch[eb0 + ib];
+        uint32_t old = atomicCAS(&s_ib[slot], kNone, ib);
+        if (old != kNone) atomicOr(err, 4u);          // two edges with equal (layer, idx, sign)
+        else s_w[slot] = Bv.w[eb0 + ib];
+    }
+    __syncthreads();
+    if (s >= kB) return;
+    Fp wp = fp_zero(), wm = fp_zero();
+    uint32_t tmin = kNone;
+    uint8_t fl = 0;
+    for (uint32_t k = 0; k < nA; k++) {
+        uint32_t ia = A.order[ea0 + A.lstart[a_l] + k];   // same address for the whole CTA: broadcast
+        uint32_t ida = A.idx[ea0 + ia];
+        uint32_t cha = A.ch[ea0 + ia];
+        int j = s - (int)ida;
+        if (j < 0) j += kB;
+#pragma unroll
+        for (uint32_t sb = 0; sb < 2; sb++) {
+            uint32_t ib = s_ib[j * 2 + sb];
+            if (ib == kNone) continue;
+            Fp ww = fp_mul(A.w[ea0 + ia], s_w[j * 2 + sb]);
+            uint32_t t = ia * EB + ib;                   // position of the pair in the reference's double loop
+            tmin = min(tmin, t);
+            if (cha == sb) { wp = fp_add(wp, ww); fl |= 1; }
+            else { wm = fp_add(wm, ww); fl |= 2; }
+        }
+    }
+    k_wp[kbase + s] = wp;
+    k_wm[kbase + s] = wm;
+    k_flags[kbase + s] = fl;
+    k_tins[kbase + s] = tmin;
+}
+
+__device__ __forceinline__ uint32_t find_item(const uint32_t* __restrict__ off, uint32_t n, uint32_t x) {   // off[i] <= x < off[i+1]
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// thread per key: bucket = (k * phi mod 2^64) % nb  (struct H, ops/arithmetic.hpp:73); table: bucket -> min insertion time
+__global__ void mul_bucket_insert_kernel(uint32_t nkeys, uint32_t n, const uint32_t* __restrict__ koff, const uint32_t* __restrict__ toff,
+                                         const uint64_t* __restrict__ nb, const uint32_t* __restrict__ k_tins, uint32_t* __restrict__ k_item,
+                                         unsigned long long* __restrict__ t_key, uint32_t* __restrict__ t_val) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    uint32_t i = find_item(koff, n, k);
+    k_item[k] = i;
+    uint32_t t = k_tins[k];
+    if (t == kNone) return;
+    uint32_t rel = k - koff[i];
+    uint64_t key = ((uint64_t)(rel / kB) << 32) | (rel % kB);
+    uint64_t bkt = (key * 0x9E3779B97F4A7C15ull) % nb[i];
+    uint32_t size = toff[i + 1] - toff[i];
+    uint32_t h = (uint32_t)(mix64(bkt) & (size - 1));
+    for (;;) {
+        unsigned long long cur = atomicCAS(&t_key[toff[i] + h], ~0ull, (unsigned long long)bkt);
+        if (cur == ~0ull || cur == bkt) break;
+        h = (h + 1) & (size - 1);
+    }
+    atomicMin(&t_val[toff[i] + h], t);
+}
+
+// sort key: (item, PMAX - (t_bkt+1), PMAX - (t_ins+1)) ascending = (bucket time desc, insertion time desc); absent keys last
+__global__ void mul_sortkey_kernel(uint32_t nkeys, const uint32_t* __restrict__ koff, const uint32_t* __restrict__ toff, const uint64_t* __restrict__ nb,
+                                   const uint32_t* __restrict__ k_tins, const uint32_t* __restrict__ k_item, const unsigned long long* __restrict__ t_key,
+                                   const uint32_t* __restrict__ t_val, int pbits, uint64_t* __restrict__ skey, uint32_t* __restrict__ sval) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    uint32_t i = k_item[k];
+    uint32_t t = k_tins[k];
+    const uint64_t pmax = (1ull << pbits) - 1;
+    uint64_t lowpart;
+    if (t == kNone) lowpart = (pmax << pbits) | pmax;
+    else {
+        uint32_t rel = k - koff[i];
+        uint64_t key = ((uint64_t)(rel / kB) << 32) | (rel % kB);
+        uint64_t bkt = (key * 0x9E3779B97F4A7C15ull) % nb[i];
+        uint32_t size = toff[i + 1] - toff[i];
+        uint32_t h = (uint32_t)(mix64(bkt) & (size - 1));
+        while (t_key[toff[i] + h] != bkt) h = (h + 1) & (size - 1);
+        uint64_t tb = t_val[toff[i] + h];
+        lowpart = ((pmax - (tb + 1)) << pbits) | (pmax - ((uint64_t)t + 1));
+    }
+    skey[k] = ((uint64_t)i << (2 * pbits)) | lowpart;
+    sval[k] = k;
+}
+
+// per sorted position: number of edges emitted (P if ip && wp != 0, M if im && wm != 0; ops/arithmetic.hpp:96-101)
+__global__ void mul_emit_count_kernel(uint32_t nkeys, const uint32_t* __restrict__ sval, const uint8_t* __restrict__ k_flags, const Fp* __restrict__ k_wp,
+                                      const Fp* __restrict__ k_wm, const uint32_t* __restrict__ k_tins, uint32_t* __restrict__ cnt) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nkeys) return;
+    uint32_t k = sval[q];
+    uint32_t c = 0;
+    if (k_tins[k] != kNone) {
+        uint8_t fl = k_flags[k];
+        if ((fl & 1) && !fp_is_zero(k_wp[k])) c++;
+        if ((fl & 2) && !fp_is_zero(k_wm[k])) c++;
+    }
+    cnt[q] = c;
+}
+
+__global__ void mul_eoff_kernel(uint64_t n, const uint32_t* __restrict__ koff, const uint32_t* __restrict__ epos, uint32_t nkeys, uint32_t total,
+                                uint32_t* __restrict__ eoff, unsigned int* __restrict__ err) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t k = koff[i];
+    eoff[i] = (i == n || k >= nkeys) ? total : epos[k];
+    if (i < n) {
+        uint32_t k1 = koff[i + 1];
+        uint32_t e1 = (k1 >= nkeys) ? total : epos[k1];
+        if (e1 - eoff[i] > kEdgeBudget) atomicOr(err, 8u);
+    }
+}
+
+__global__ void mul_emit_kernel(uint32_t nkeys, uint64_t batch_seed, const uint64_t* __restrict__ states, const uint32_t* __restrict__ sval, const uint32_t* __restrict__ epos,
+                                const uint32_t* __restrict__ k_item, const uint32_t* __restrict__ koff, const uint32_t* __restrict__ eoff,
+                                const uint32_t* __restrict__ loA, const uint32_t* __restrict__ loB, const uint32_t* __restrict__ loP,
+                                const uint8_t* __restrict__ k_flags, const Fp* __restrict__ k_wp, const Fp* __restrict__ k_wm,
+                                const uint32_t* __restrict__ k_tins, uint32_t* __restrict__ o_lid, uint16_t* __restrict__ o_idx, uint8_t* __restrict__ o_ch,
+                                Fp* __restrict__ o_w, uint64_t* __restrict__ salt, uint32_t* __restrict__ seed_idx) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nkeys) return;
+    uint32_t k = sval[q];
+    if (k_tins[k] == kNone) return;
+    uint32_t i = k_item[k];
+    uint32_t rel = k - koff[i];
+    uint32_t lp = rel / kB, s = rel % kB;
+    uint32_t LA = loA[i + 1] - loA[i], LB = loB[i + 1] - loB[i];
+    uint32_t lid = LA + LB + lp;
+    uint64_t s0 = states ? states[i] : item_stream_state(batch_seed, i);
+    uint32_t e = epos[q];
+    uint8_t fl = k_flags[k];
+    for (int sg = 0; sg < 2; sg++) {
+        Fp w = sg ? k_wm[k] : k_wp[k];
+        if (!(fl & (1 << sg)) || fp_is_zero(w)) continue;
+        o_lid[e] = lid; o_idx[e] = (uint16_t)s; o_ch[e] = (uint8_t)sg; o_w[e] = w;
+        salt[e] = tape_word(s0, 2ull * LA * LB + (e - eoff[i]));      // salts follow the 2*LA*LB nonce words, in emission order
+        seed_idx[e] = loP[i] + lid;
+        e++;
+    }
+}
+
+#define MUL_ALLOC(ptr, bytes)                                   \
+    do {                                                        \
+        if ((rc = dev_alloc(ctx, (void**)&(ptr), (bytes)))) {   \
+            for (void* _p : scratch) dev_free(ctx, _p);         \
+            return rc;                                          \
+        }                                                       \
+        scratch.push_back((void*)(ptr));                        \
+    } while (0)
+
+int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, const uint64_t* h_states, Batch** out) {
+    const uint64_t n = A->n;
+    int rc;
+    if (n == 0) return batch_alloc(ctx, 0, 0, 0, out);
+    std::vector<void*> scratch;
+    auto cleanup = [&]() { for (void* p : scratch) dev_free(ctx, p); scratch.clear(); };
+
+    uint32_t *c_lpre, *c_lp, *c_keys, *c_tbl, *loP, *lpoff, *koff, *toff;
+    uint64_t* nb;
+    unsigned long long* max_pairs;
+    unsigned int* err;
+    MUL_ALLOC(c_lpre, n * 4); MUL_ALLOC(c_lp, n * 4); MUL_ALLOC(c_keys, n * 4); MUL_ALLOC(c_tbl, n * 4);
+    MUL_ALLOC(loP, (n + 1) * 4); MUL_ALLOC(lpoff, (n + 1) * 4); MUL_ALLOC(koff, (n + 1) * 4); MUL_ALLOC(toff, (n + 1) * 4);
+    MUL_ALLOC(nb, n * 8); MUL_ALLOC(max_pairs, 24); MUL_ALLOC(err, 4);
+    uint64_t* d_states = nullptr;
+    if (h_states) {
+        MUL_ALLOC(d_states, n * 8);
+        PV_CUDA(cudaMemcpyAsync(d_states, h_states, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PV_CUDA(cudaMemsetAsync(max_pairs, 0, 24, ctx->stream));
+    PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
+    mul_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, A->loff, B->loff, A->eoff, B->eoff, ctx->d_primes, ctx->n_primes, c_lpre, c_lp,
+                                                                           c_keys, c_tbl, nb, max_pairs, err);
+    ctx->stat_kernel_launches += 1;
+    if ((rc = scan_u32(ctx, n, c_lpre, loP)) || (rc = scan_u32(ctx, n, c_lp, lpoff)) || (rc = scan_u32(ctx, n, c_keys, koff)) ||
+        (rc = scan_u32(ctx, n, c_tbl, toff))) { cleanup(); return rc; }
+    uint32_t tot[4];
+    unsigned long long h_stats[3] = {0, 0, 0};
+    unsigned int h_err = 0;
+    PV_CUDA(cudaMemcpyAsync(&tot[0], loP + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(&tot[1], lpoff + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(&tot[2], koff + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(&tot[3], toff + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(h_stats, max_pairs, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_err) { cleanup(); ctx->last_error = "ct_mul: operand too large for the batched path (layer pairs / keys / edge pairs overflow)"; return PV_E_SHAPE; }
+    const uint32_t nLpre = tot[0], nLP = tot[1], nKeys = tot[2], nTbl = tot[3];
+    const unsigned long long h_maxpairs = h_stats[0];
+    if (h_stats[1] >= (1ull << 31) || h_stats[2] >= (1ull << 32)) {   // 32-bit offsets index the key space
+        cleanup();
+        ctx->last_error = "ct_mul: batch too large (key space needs more than 2^31 slots); split it into smaller tiles";
+        return PV_E_SHAPE;
+    }
+
+    // ---- pre-compaction layers
+    uint8_t* p_rule; uint64_t *p_zt, *p_nl, *p_nh; uint32_t *p_pa, *p_pb, *lp_item;
+    MUL_ALLOC(p_rule, nLpre); MUL_ALLOC(p_zt, (size_t)nLpre * 8); MUL_ALLOC(p_nl, (size_t)nLpre * 8); MUL_ALLOC(p_nh, (size_t)nLpre * 8);
+    MUL_ALLOC(p_pa, (size_t)nLpre * 4); MUL_ALLOC(p_pb, (size_t)nLpre * 4); MUL_ALLOC(lp_item, (size_t)(nLP ? nLP : 1) * 4);
+    mul_layers_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>(n, batch_seed, d_states, ctx->kv.canon_tag, A->loff, B->loff, A->rule, A->ztag, A->nlo, A->nhi, A->pa, A->pb,
+                                                            B->rule, B->ztag, B->nlo, B->nhi, B->pa, B->pb, loP, lpoff, p_rule, p_zt, p_nl, p_nh, p_pa, p_pb, lp_item);
+    // ---- edges by layer
+    uint32_t *lsA, *lcA, *curA, *ordA, *lsB, *lcB, *curB, *ordB;
+    MUL_ALLOC(lsA, (A->nL + 1) * 4); MUL_ALLOC(lcA, (A->nL + 1) * 4); MUL_ALLOC(curA, (A->nL + 1) * 4); MUL_ALLOC(ordA, (A->nE + 1) * 4);
+    MUL_ALLOC(lsB, (B->nL + 1) * 4); MUL_ALLOC(lcB, (B->nL + 1) * 4); MUL_ALLOC(curB, (B->nL + 1) * 4); MUL_ALLOC(ordB, (B->nE + 1) * 4);
+    mul_bylayer_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>(A->loff, A->eoff, A->lid, lsA, lcA, curA, ordA, err);
+    mul_bylayer_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>(B->loff, B->eoff, B->lid, lsB, lcB, curB, ordB, err);
+    ctx->stat_kernel_launches += 3;
+
+    Batch* o = nullptr;
+    uint32_t nEout = 0;
+    uint64_t* salt = nullptr;
+    uint32_t* seed_idx = nullptr;
+    if (nKeys) {
+        // ---- pair products per key
+        Fp *k_wp, *k_wm; uint8_t* k_flags; uint32_t *k_tins, *k_item, *t_val; unsigned long long* t_key;
+        MUL_ALLOC(k_wp, (size_t)nKeys * 16); MUL_ALLOC(k_wm, (size_t)nKeys * 16); MUL_ALLOC(k_flags, nKeys); MUL_ALLOC(k_tins, (size_t)nKeys * 4);
+        MUL_ALLOC(k_item, (size_t)nKeys * 4); MUL_ALLOC(t_key, (size_t)(nTbl ? nTbl : 1) * 8); MUL_ALLOC(t_val, (size_t)(nTbl ? nTbl : 1) * 4);
+        EdgeView VA{A->loff, A->eoff, A->idx, A->ch, A->w, lsA, lcA, ordA};
+        EdgeView VB{B->loff, B->eoff, B->idx, B->ch, B->w, lsB, lcB, ordB};
+        mul_pairs_kernel<<<nLP, kPairThreads, 0, ctx->stream>>>(VA, VB, lp_item, lpoff, koff, k_wp, k_wm, k_flags, k_tins, err);
+        PV_CUDA(cudaMemsetAsync(t_key, 0xFF, (size_t)(nTbl ? nTbl : 1) * 8, ctx->stream));
+        PV_CUDA(cudaMemsetAsync(t_val, 0xFF, (size_t)(nTbl ? nTbl : 1) * 4, ctx->stream));
+        const unsigned kb = (nKeys + 255) / 256;
+        mul_bucket_insert_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, (uint32_t)n, koff, toff, nb, k_tins, k_item, t_key, t_val);
+        // ---- libstdc++ iteration order by radix sort
+        int pbits = 1;
+        while ((1ull << pbits) - 1 < h_maxpairs + 1) pbits++;
+        int ibits = 1;
+        while ((1ull << ibits) < n) ibits++;
+        if (2 * pbits + ibits > 64) { cleanup(); ctx->last_error = "ct_mul: sort key does not fit 64 bits (batch too large for these operand sizes)"; return PV_E_SHAPE; }
+        uint64_t *skey, *skey2; uint32_t *sval, *sval2, *ecnt, *epos;
+        MUL_ALLOC(skey, (size_t)nKeys * 8); MUL_ALLOC(skey2, (size_t)nKeys * 8); MUL_ALLOC(sval, (size_t)nKeys * 4); MUL_ALLOC(sval2, (size_t)nKeys * 4);
+        MUL_ALLOC(ecnt, (size_t)nKeys * 4); MUL_ALLOC(epos, (size_t)nKeys * 4);
+        mul_sortkey_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, koff, toff, nb, k_tins, k_item, t_key, t_val, pbits, skey, sval);
+        size_t tmp_bytes = 0, tmp2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, skey, skey2, sval, sval2, (int)nKeys, 0, 2 * pbits + ibits, ctx->stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ecnt, epos, (int)nKeys, ctx->stream);
+        if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+        void* tmp;
+        MUL_ALLOC(tmp, tmp_bytes);
+        PV_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, skey, skey2, sval, sval2, (int)nKeys, 0, 2 * pbits + ibits, ctx->stream));
+        mul_emit_count_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, sval2, k_flags, k_wp, k_wm, k_tins, ecnt);
+        PV_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ecnt, epos, (int)nKeys, ctx->stream));
+        uint32_t last[2] = {0, 0};
+        PV_CUDA(cudaMemcpyAsync(&last[0], epos + (nKeys - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA(cudaMemcpyAsync(&last[1], ecnt + (nKeys - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PV_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->stat_kernel_launches += 7;
+        if (h_err) {
+            cleanup();
+            if (h_err & 2) { ctx->last_error = "ct_mul: edge layer id out of range"; return PV_E_FORMAT; }
+            ctx->last_error = "ct_mul: operand holds two edges with equal (layer, idx, sign); the batched path needs compacted operands";
+            return PV_E_DUP_EDGE;
+        }
+        nEout = last[0] + last[1];
+        if ((rc = batch_alloc(ctx, n, nLpre, nEout, &o))) { cleanup(); return rc; }
+        MUL_ALLOC(salt, (size_t)(nEout ? nEout : 1) * 8);
+        MUL_ALLOC(seed_idx, (size_t)(nEout ? nEout : 1) * 4);
+        mul_eoff_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, koff, epos, nKeys, nEout, o->eoff, err);
+        mul_emit_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, batch_seed, d_states, sval2, epos, k_item, koff, o->eoff, A->loff, B->loff, loP, k_flags, k_wp, k_wm, k_tins,
+                                                     o->lid, o->idx, o->ch, o->w, salt, seed_idx);
+        ctx->stat_kernel_launches += 2;
+    } else {
+        if ((rc = batch_alloc(ctx, n, nLpre, 0, &o))) { cleanup(); return rc; }
+        PV_CUDA(cudaMemsetAsync(o->eoff, 0, (n + 1) * 4, ctx->stream));
+    }
+    // layers of the result (pre-compaction)
+    PV_CUDA(cudaMemcpyAsync(o->loff, loP, (n + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(o->rule, p_rule, nLpre, cudaMemcpyDeviceToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(o->ztag, p_zt, (size_t)nLpre * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(o->nlo, p_nl, (size_t)nLpre * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(o->nhi, p_nh, (size_t)nLpre * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(o->pa, p_pa, (size_t)nLpre * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    PV_CUDA(cudaMemcpyAsync(o->pb, p_pb, (size_t)nLpre * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    // ---- sigma of every output edge, seeded by its PROD layer (pre-compaction tables)
+    if (nEout) {
+        SigmaJobs J;
+        J.n = nEout; J.ztag = p_zt; J.nlo = p_nl; J.nhi = p_nh; J.seed_idx = seed_idx; J.idx = o->idx; J.ch = o->ch; J.salt = salt; J.out = o->sigma;
+        if ((rc = sigma_run(ctx, J))) { cleanup(); batch_free(o); return rc; }
+    }
+    PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+    if (h_err & 8) { batch_free(o); ctx->last_error = "ct_mul: a result exceeds edge_budget (the reference would run compact_edges here)"; return PV_E_EDGE_BUDGET; }
+    if ((rc = compact_layers_batch(ctx, o))) { batch_free(o); return rc; }
+    *out = o;
+    return PV_OK;
+}
+
+}  // namespace pvacb

@@ -1,0 +1,141 @@
+// PRF path: prf_R / prf_R_noise of the reference (crypto/lpn.hpp:194-275, crypto/toeplitz.hpp:121-162).
+//
+//   prf_setup_kernel    one thread per PRF core: SHA-256 key derivation (midstate reuse), AES-256 key schedule,
+//                       first block of the Toeplitz key stream ("top")
+//   prf_lpn_kernel      THE HOT KERNEL of enc_value / dec_value: AES-256-CTR keystream fused with the LPN parity.
+//                       One thread per ROW PAIR (rows 2p, 2p+1 = 130 stream words = exactly 65 AES blocks), so no
+//                       cross-lane reduction is needed; T-tables replicated per lane in 128 KiB of shared memory
+//                       (bank-conflict free); the secret s sits in the kernel parameter bank; a warp's 64 y-bits are
+//                       assembled with two __ballot_sync and one 64-bit store. The keystream is never stored.
+//   prf_finalize_kernel one thread per job: 127-bit truncated carry-less product, hash_to_fp_nonzero, r1*r2*r3
+//
+// Row layout (crypto/lpn.hpp:219-232, word FIFO of :108-139): stream word w = half (w&1) of block (w>>1); row r uses
+// words 65r..65r+63 for the dot product with s and word 65r+64 for the Bernoulli(1/8) noise bit.
+#include "engine.h"
+#include "prf_core.cuh"
+
+namespace pvacb {
+
+// ------------------------------------------------------------------ setup
+__global__ void prf_setup_kernel(KeyView kv, uint64_t ncores, const uint64_t* __restrict__ ztag, const uint64_t* __restrict__ nlo,
+                                 const uint64_t* __restrict__ nhi, const uint8_t* __restrict__ flags, uint32_t* __restrict__ rk_out,
+                                 uint64_t* __restrict__ ctr0_out, uint64_t* __restrict__ top_out) {
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncores) return;
+    uint64_t job = c / 3;
+    int t = (int)(c % 3);
+    uint8_t fl = flags[job];
+    if (!(fl & 2)) return;
+    uint32_t rk[60];
+    uint64_t ctr0, top0, top1;
+    prf_core_setup(kv.kd_mid, kv.digest3, kv.T0, kv.sbox, ztag[job], nlo[job], nhi[job], fnv_prf_dom(fl & 1, t), rk, ctr0, top0, top1);
+    for (int i = 0; i < 60; i++) rk_out[c * 60 + i] = rk[i];
+    ctr0_out[c] = ctr0;
+    top_out[2 * c] = top0;
+    top_out[2 * c + 1] = top1;
+}
+
+// ------------------------------------------------------------------ LPN rows
+constexpr int kLpnThreads = 512;
+
+// rpc_log2: log2(row pairs evaluated per core): 13 (all 16384 rows, as the reference) or 6 (rows 0..127, the only ones
+// toep_127 can see). Persistent grid: one CTA per SM, static round-robin over units of kLpnThreads row pairs.
+__global__ void __launch_bounds__(kLpnThreads, 1)
+prf_lpn_kernel(const uint32_t* __restrict__ gT0, const __grid_constant__ LpnSecret sec, uint64_t ncores, int rpc_log2,
+               const uint32_t* __restrict__ rk_all, const uint64_t* __restrict__ ctr0_all, const uint8_t* __restrict__ flags,
+               uint64_t* __restrict__ ybits, unsigned int* __restrict__ rare_flag) {
+    extern __shared__ uint32_t sT[];
+    aes_fill_rep_tables(sT, gT0);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t* Tl = sT + lane;
+    const uint64_t slots = ncores << rpc_log2;
+    const uint64_t units = (slots + kLpnThreads - 1) / kLpnThreads;
+    const uint32_t rp_mask = (1u << rpc_log2) - 1;
+
+    for (uint64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        uint64_t slot = u * kLpnThreads + threadIdx.x;
+        bool active = slot < slots;
+        uint64_t core = active ? (slot >> rpc_log2) : 0;
+        uint32_t rp = (uint32_t)slot & rp_mask;
+        if (active && !(flags[core / 3] & 2)) active = false;   // warp-uniform: a core spans whole warps
+        uint32_t ye = 0, yo = 0;
+        if (active) {
+            uint32_t rk[60];
+            const uint4* rkp = reinterpret_cast<const uint4*>(rk_all + core * 60);
+#pragma unroll
+            for (int i = 0; i < 15; i++) {
+                uint4 v = __ldg(rkp + i);
+                rk[4 * i] = v.x; rk[4 * i + 1] = v.y; rk[4 * i + 2] = v.z; rk[4 * i + 3] = v.w;
+            }
+            uint64_t ctr = __ldg(ctr0_all + core) + 65ull * rp;
+            bool rare = false;
+            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) { aes_block_rep(Tl, rk, c, w0, w1); }, ctr, sec.w, ye, yo, rare);
+            if (rare) atomicOr(rare_flag, 1u);
+        }
+        uint32_t be = __ballot_sync(0xffffffffu, ye);
+        uint32_t bo = __ballot_sync(0xffffffffu, yo);
+        if (lane == 0 && active) ybits[slot >> 5] = spread_bits32(be) | (spread_bits32(bo) << 1);
+    }
+}
+
+// ------------------------------------------------------------------ finalize
+__global__ void prf_finalize_kernel(uint64_t njobs, const uint8_t* __restrict__ flags, const uint64_t* __restrict__ ybits,
+                                    int words_per_core, const uint64_t* __restrict__ top, Fp* __restrict__ out) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    if (!(flags[j] & 2)) { out[j] = fp_zero(); return; }
+    Fp r[3];
+    for (int t = 0; t < 3; t++) {
+        uint64_t c = 3 * j + t;
+        const uint64_t* y = ybits + c * (uint64_t)words_per_core;
+        r[t] = toep127_to_fp(y[0], y[1], top[2 * c], top[2 * c + 1]);
+    }
+    out[j] = fp_mul(fp_mul(r[0], r[1]), r[2]);   // crypto/lpn.hpp:263-275
+}
+
+// ------------------------------------------------------------------ host launcher
+int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_nlo, const uint64_t* d_nhi, const uint8_t* d_flags,
+            Fp* d_out, uint64_t* d_ybits_out) {
+    if (njobs == 0) return PV_OK;
+    const uint64_t ncores = njobs * 3;
+    const int rpc_log2 = ctx->prf_mode == PRF_LIVE ? 6 : 13;
+    const int wpc = (1 << rpc_log2) / 32;  // ybits words per core
+    uint32_t* rk = nullptr;
+    uint64_t *ctr0 = nullptr, *top = nullptr, *ybits = nullptr;
+    unsigned int* rare = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, (void**)&rk, ncores * 60 * 4))) return rc;
+    if ((rc = dev_alloc(ctx, (void**)&ctr0, ncores * 8))) return rc;
+    if ((rc = dev_alloc(ctx, (void**)&top, ncores * 16))) return rc;
+    if (d_ybits_out) ybits = d_ybits_out;
+    else if ((rc = dev_alloc(ctx, (void**)&ybits, ncores * wpc * 8))) return rc;
+    if ((rc = dev_alloc(ctx, (void**)&rare, 4))) return rc;
+    PV_CUDA(cudaMemsetAsync(rare, 0, 4, ctx->stream));
+
+    prf_setup_kernel<<<(unsigned)((ncores + 127) / 128), 128, 0, ctx->stream>>>(ctx->kv, ncores, d_ztag, d_nlo, d_nhi, d_flags, rk, ctr0, top);
+    if (!ctx->lpn_attr_set) {
+        PV_CUDA(cudaFuncSetAttribute(prf_lpn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesRepBytes));
+        ctx->lpn_attr_set = true;
+    }
+    uint64_t units = ((ncores << rpc_log2) + kLpnThreads - 1) / kLpnThreads;
+    unsigned grid = (unsigned)(units < (uint64_t)ctx->sm_count ? units : (uint64_t)ctx->sm_count);
+    prf_lpn_kernel<<<grid, kLpnThreads, kAesRepBytes, ctx->stream>>>(ctx->kv.T0, ctx->lpn_s, ncores, rpc_log2, rk, ctr0, d_flags, ybits, rare);
+    prf_finalize_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, ctx->stream>>>(njobs, d_flags, ybits, wpc, top, d_out);
+    PV_CUDA(cudaGetLastError());
+    ctx->stat_kernel_launches += 3;
+    ctx->stat_aes_blocks += ncores * ((65ull << rpc_log2) + 1);
+
+    unsigned int h_rare = 0;
+    PV_CUDA(cudaMemcpyAsync(&h_rare, rare, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, rk); dev_free(ctx, ctr0); dev_free(ctx, top); dev_free(ctx, rare);
+    if (!d_ybits_out) dev_free(ctx, ybits);
+    if (h_rare) {
+        ctx->last_error = "AesCtr256::bounded rejection branch hit (p = 2^-61 per row); not supported on device";
+        return PV_E_RARE_PATH;
+    }
+    return PV_OK;
+}
+
+}  // namespace pvacb

@@ -1,0 +1,318 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libpvacb.so via pvac_hfhe_cppbyv_b200.api), against
+the CPU oracle on the same seeded inputs, against the committed golden fixtures (generated from the unmodified reference),
+and -- at larger sizes -- through size-independent properties. Bit-exact everywhere: this path is integer-only.
+
+Run on the GPU box:  python -m pytest tests -m gpu -x -q
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ct_digest, ct_equal, hexwords, load_npz
+
+pytestmark = pytest.mark.gpu
+
+P127 = (1 << 127) - 1
+SEED = (0x1111, 0x2222, 0x3333)
+
+
+def fpv(a):
+    return int(a[0]) | (int(a[1]) << 64)
+
+
+def to_fp(x):
+    return [x & (2**64 - 1), x >> 64]
+
+
+@pytest.fixture(scope="module")
+def api():
+    from pvac_hfhe_cppbyv_b200 import api as a
+    return a
+
+
+# ------------------------------------------------------------------ field arithmetic (core/field.hpp)
+def test_fp_ops(engine, kat):
+    rng = np.random.default_rng(3)
+    vals = [int.from_bytes(rng.bytes(16), "little") % P127 for _ in range(4096)]
+    vals[:6] = [0, 1, P127 - 1, P127 - 2, 2**64 - 1, 2**64]
+    a = np.array([to_fp(v) for v in vals], np.uint64)
+    b = np.array([to_fp(v) for v in reversed(vals)], np.uint64)
+    bi = list(reversed(vals))
+    for op, f in [(0, lambda x, y: (x + y) % P127), (1, lambda x, y: (x - y) % P127), (2, lambda x, y: x * y % P127)]:
+        got = engine.fp_op(op, a, b)
+        assert [fpv(g) for g in got] == [f(x, y) for x, y in zip(vals, bi)], op
+    assert [fpv(g) for g in engine.fp_op(3, a)] == [(-x) % P127 for x in vals]
+    inv = engine.fp_op(4, a[1:513])
+    assert [fpv(g) for g in inv] == [pow(x, P127 - 2, P127) for x in vals[1:513]]
+    for c in kat["fp"]:   # golden vectors from the reference
+        A = np.array([[int(x, 16) for x in c["a"]]], np.uint64)
+        Bv = np.array([[int(x, 16) for x in c["b"]]], np.uint64)
+        assert hexwords(engine.fp_op(0, A, Bv)) == c["add"] and hexwords(engine.fp_op(1, A, Bv)) == c["sub"]
+        assert hexwords(engine.fp_op(2, A, Bv)) == c["mul"] and hexwords(engine.fp_op(3, A)) == c["neg"]
+        if c["inv"]:
+            assert hexwords(engine.fp_op(4, A)) == c["inv"]
+
+
+# ------------------------------------------------------------------ keygen (crypto/keygen.hpp:35)
+def test_keygen_matches_reference(engine, kat):
+    g = load_npz("keys_seed1.npz")
+    e = engine.export_keys()
+    assert e["canon_tag"] == int(g["canon_tag"])
+    for k in ("H_digest", "prf_k", "lpn_s", "powg"):
+        assert np.array_equal(e[k], g[k]), k
+    for c, h in kat["keygen1_H_col_sha256"].items():
+        assert hashlib.sha256(e["H"][int(c)].tobytes()).hexdigest() == h
+
+
+# ------------------------------------------------------------------ PRF (crypto/lpn.hpp, crypto/toeplitz.hpp)
+@pytest.fixture(scope="module")
+def synth_engine(api, synth_keys_raw):
+    r = synth_keys_raw
+    eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL)
+    eng.import_keys(r["canon_tag"], r["H_digest"], None, None, r["prf_k"], r["lpn_s"])
+    yield eng
+    eng.close()
+
+
+def test_prf_known_answers_faithful(synth_engine, kat):
+    out, yb = synth_engine.prf([SEED[0]], [SEED[1]], [SEED[2]], family=0, want_ybits=True)
+    assert hexwords(out[0]) == kat["prf_R"]
+    # the full 16384-row LPN sample of the first core, as lpn_make_ybits produces it
+    assert hashlib.sha256(yb[0].tobytes()).hexdigest() == kat["ybits_r1_sha256"]
+    assert int(sum(bin(int(v)).count("1") for v in yb[0])) == kat["ybits_r1_popcount"]
+    out = synth_engine.prf([SEED[0]], [SEED[1]], [SEED[2]], family=1)
+    assert hexwords(out[0]) == kat["prf_R_noise"]
+
+
+def test_prf_live_rows_equal_faithful(api, synth_engine, kat, port, synth_keys_raw):
+    rng = np.random.default_rng(11)
+    n = 24
+    z, lo, hi = (rng.integers(0, 2**64, n, dtype=np.uint64) for _ in range(3))
+    synth_engine.set_prf_mode(api.PRF_FAITHFUL)
+    f0, f1 = synth_engine.prf(z, lo, hi, 0), synth_engine.prf(z, lo, hi, 1)
+    synth_engine.set_prf_mode(api.PRF_LIVE)
+    l0, l1 = synth_engine.prf(z, lo, hi, 0), synth_engine.prf(z, lo, hi, 1)
+    synth_engine.set_prf_mode(api.PRF_FAITHFUL)
+    assert np.array_equal(f0, l0) and np.array_equal(f1, l1)
+    r = synth_keys_raw
+    ko = port.Keys.from_raw(r["canon_tag"], r["H_digest"], None, None, r["prf_k"], r["lpn_s"])
+    ko.set_lpn_t(127)
+    for i in range(n):
+        assert np.array_equal(f0[i], ko.prf_R(int(z[i]), int(lo[i]), int(hi[i]))), i
+        assert np.array_equal(f1[i], ko.prf_R_noise(int(z[i]), int(lo[i]), int(hi[i]))), i
+
+
+# ------------------------------------------------------------------ sigma_from_H (crypto/matrix.hpp:267-303)
+def test_sigma_from_H(engine, port_keys, kat):
+    sg = engine.sigma_from_H([0x1111], [0x2222], [0x3333], [5], [1], [0x4444])
+    assert hashlib.sha256(sg[0].tobytes()).hexdigest() == kat["keygen1_sigma_sha256"]
+    rng = np.random.default_rng(5)
+    n = 300   # not a multiple of the CTA tiling
+    z, lo, hi, salt = (rng.integers(0, 2**64, n, dtype=np.uint64) for _ in range(4))
+    idx = rng.integers(0, 337, n).astype(np.uint16)
+    ch = rng.integers(0, 2, n).astype(np.uint8)
+    got = engine.sigma_from_H(z, lo, hi, idx, ch, salt)
+    for i in range(n):
+        want = port_keys.sigma_from_H(int(z[i]), int(lo[i]), int(hi[i]), int(idx[i]), int(ch[i]), int(salt[i]))
+        assert np.array_equal(got[i], want), i
+
+
+# ------------------------------------------------------------------ enc_value (ops/encrypt.hpp:289)
+def test_enc_value_golden(engine, api):
+    b = engine.enc_value([42, 2**64 - 1], tape_states=[1000, 2000])
+    items = api.split_items(engine.export_soa(b))
+    for it, name in zip(items, ("enc_seed1000.npz", "enc_seed2000.npz")):
+        ok, k = ct_equal(it, load_npz(name))
+        assert ok, (name, k)
+
+
+def test_enc_value_vs_oracle(engine, api, port, port_keys):
+    rng = np.random.default_rng(9)
+    n = 48
+    vals = rng.integers(0, 2**64, n, dtype=np.uint64)
+    vals[:4] = [0, 1, 2**64 - 1, 42]
+    seed = 0xC0FFEE
+    items = api.split_items(engine.export_soa(engine.enc_value(vals, seed)))
+    for i in range(n):
+        want = port.ct_export(port_keys.enc_value(port.item_stream_state(seed, i), int(vals[i])))
+        ok, k = ct_equal(items[i], want)
+        assert ok, (i, k)
+
+
+def test_enc_faithful_mode_identical(engine, api):
+    vals = np.arange(6, dtype=np.uint64) + 100
+    live = engine.export_soa(engine.enc_value(vals, 5))
+    engine.set_prf_mode(api.PRF_FAITHFUL)
+    try:
+        full = engine.export_soa(engine.enc_value(vals, 5))
+    finally:
+        engine.set_prf_mode(api.PRF_LIVE)
+    for k in live:
+        assert np.array_equal(live[k], full[k]), k
+
+
+# ------------------------------------------------------------------ ct_add / ct_sub / ct_scale (ops/arithmetic.hpp:12-45)
+def test_bounty2_golden_add_wire(engine):
+    rd = lambda n: open(os.path.join(GOLDEN, "bounty2", n), "rb").read()
+    a, b = engine.import_wire(rd("a.ct")), engine.import_wire(rd("b.ct"))
+    assert engine.export_wire(a) == rd("a.ct")            # wire round trip
+    assert engine.export_wire(engine.ct_add(a, b)) == rd("sum.ct")   # the reference's own golden vector
+
+
+def test_add_sub_scale_vs_oracle(engine, api, port, port_keys, chain):
+    a = engine.enc_value([42], tape_states=[1000])
+    b = engine.enc_value([2**64 - 1], tape_states=[2000])
+    s, d = engine.ct_add(a, b), engine.ct_sub(a, b)
+    assert ct_digest(api.split_items(engine.export_soa(s))[0]) == chain["add"]
+    assert ct_digest(api.split_items(engine.export_soa(d))[0]) == chain["sub"]
+    assert ct_digest(api.split_items(engine.export_soa(engine.ct_scale(a, [12345, 0])))[0]) == chain["scale"]
+    assert hexwords(engine.dec_value(s)[0]) == chain["dec_add"] and hexwords(engine.dec_value(d)[0]) == chain["dec_sub"]
+    # ragged batch: items with different shapes (fresh, sum, difference) concatenated
+    oa, ob = port_keys.enc_value(1000, 42), port_keys.enc_value(2000, 2**64 - 1)
+    os_, od = port_keys.ct_add(oa, ob), port_keys.ct_sub(oa, ob)
+    left = [port.ct_export(x) for x in (oa, os_, od, ob)]
+    right = [port.ct_export(x) for x in (ob, oa, os_, od)]
+    A, B = engine.import_soa(api.join_items(left)), engine.import_soa(api.join_items(right))
+    got_add = api.split_items(engine.export_soa(engine.ct_add(A, B)))
+    got_sub = api.split_items(engine.export_soa(engine.ct_sub(A, B)))
+    for i, (x, y) in enumerate(zip((oa, os_, od, ob), (ob, oa, os_, od))):
+        ok, k = ct_equal(got_add[i], port.ct_export(port_keys.ct_add(x, y)))
+        assert ok, ("add", i, k)
+        ok, k = ct_equal(got_sub[i], port.ct_export(port_keys.ct_sub(x, y)))
+        assert ok, ("sub", i, k)
+
+
+# ------------------------------------------------------------------ ct_mul (ops/arithmetic.hpp:47-106)
+def test_mul_golden(engine, api, kat):
+    a = engine.enc_value([42], tape_states=[1000])
+    b = engine.enc_value([2**64 - 1], tape_states=[2000])
+    p = engine.ct_mul(a, b, tape_states=[3000])
+    it = api.split_items(engine.export_soa(p))[0]
+    g = load_npz("mul_seed3000.npz")
+    ok, k = ct_equal(it, g, with_sigma=False)     # layers, emission order, weights
+    assert ok, k
+    hashes = np.frombuffer(b"".join(hashlib.sha256(r.tobytes()).digest() for r in it["sigma"]), np.uint8).reshape(-1, 32)
+    assert np.array_equal(hashes, g["sigma_sha256"])
+    assert hexwords(engine.dec_value(p)[0]) == kat["dec_mul3000"]
+
+
+def test_mul_chain_golden(engine, api, chain):
+    a = engine.enc_value([42], tape_states=[1000])
+    b = engine.enc_value([2**64 - 1], tape_states=[2000])
+    p = engine.ct_mul(a, b, tape_states=[3000])
+    s = engine.ct_add(a, b)
+    p2 = engine.ct_mul(p, a, tape_states=[4000])            # (a*b)*a
+    it = api.split_items(engine.export_soa(p2))[0]
+    assert [len(it["rule"]), len(it["lid"])] == chain["mul_pa_counts"] and ct_digest(it) == chain["mul_pa"]
+    p3 = engine.ct_mul(s, p, tape_states=[5000])            # (a+b)*(a*b)
+    assert ct_digest(api.split_items(engine.export_soa(p3))[0]) == chain["mul_sp"]
+    assert hexwords(engine.dec_value(p3)[0]) == chain["dec_mul_sp"]
+    sq = engine.ct_mul(p, p, tape_states=[6000])            # test_depth shape: a product squared (compact_layers drops 48 layers)
+    it = api.split_items(engine.export_soa(sq))[0]
+    assert [len(it["rule"]), len(it["lid"])] == chain["sq_counts"] and ct_digest(it) == chain["sq"]
+    assert hexwords(engine.dec_value(sq)[0]) == chain["dec_sq"]
+
+
+def test_mul_vs_oracle_batch(engine, api, port, port_keys):
+    rng = np.random.default_rng(21)
+    n = 12
+    va, vb = rng.integers(0, 2**64, n, dtype=np.uint64), rng.integers(0, 2**64, n, dtype=np.uint64)
+    A, B = engine.enc_value(va, 101), engine.enc_value(vb, 202)
+    Pm = engine.ct_mul(A, B, 303)
+    items = api.split_items(engine.export_soa(Pm))
+    dec = engine.dec_value(Pm)
+    for i in range(n):
+        oa = port_keys.enc_value(port.item_stream_state(101, i), int(va[i]))
+        ob = port_keys.enc_value(port.item_stream_state(202, i), int(vb[i]))
+        op = port_keys.ct_mul(port.item_stream_state(303, i), oa, ob)
+        ok, k = ct_equal(items[i], port.ct_export(op))
+        assert ok, (i, k)
+        assert fpv(dec[i]) == int(va[i]) * int(vb[i]) % P127
+
+
+# ------------------------------------------------------------------ dec_value (ops/decrypt.hpp:62)
+def test_dec_edge_cases(engine, api, port, port_keys):
+    from pvac_hfhe_cppbyv_b200.api import PvacbError
+    a = port.ct_export(port_keys.enc_value(1000, 42))
+    bad = dict(a)
+    bad["rule"] = a["rule"].copy(); bad["pa"] = a["pa"].copy(); bad["pb"] = a["pb"].copy()
+    bad["rule"][1] = 1; bad["pa"][1] = 1; bad["pb"][1] = 0          # a layer that is its own parent: cycle
+    with pytest.raises(PvacbError) as ei:
+        engine.dec_value(engine.import_soa(api.join_items([bad])))
+    assert ei.value.code == 6
+    bad["pa"][1] = 7                                                 # parent out of range
+    with pytest.raises(PvacbError) as ei:
+        engine.dec_value(engine.import_soa(api.join_items([bad])))
+    assert ei.value.code == 6
+    with pytest.raises(PvacbError):                                  # lengths differ
+        engine.ct_add(engine.enc_value([1, 2], 1), engine.enc_value([1], 2))
+    empty = engine.enc_value(np.zeros(0, np.uint64), 1)              # empty batch
+    assert len(empty) == 0 and engine.dec_value(empty).shape == (0, 2)
+    assert len(engine.ct_add(empty, empty)) == 0 and len(engine.ct_mul(empty, empty, 3)) == 0
+
+
+def test_mul_rejects_duplicate_edges(engine, api, port, port_keys):
+    from pvac_hfhe_cppbyv_b200.api import PvacbError
+    a = port.ct_export(port_keys.enc_value(1000, 42))
+    dup = {k: v.copy() for k, v in a.items()}
+    dup["idx"][1], dup["ch"][1], dup["lid"][1] = dup["idx"][0], dup["ch"][0], dup["lid"][0]
+    X = engine.import_soa(api.join_items([a]))
+    D = engine.import_soa(api.join_items([dup]))
+    with pytest.raises(PvacbError) as ei:
+        engine.ct_mul(X, D, 1)
+    assert ei.value.code == 8
+
+
+# ------------------------------------------------------------------ size-independent properties at larger sizes
+def test_roundtrip_and_homomorphism_properties(engine):
+    rng = np.random.default_rng(33)
+    n = 2048
+    va, vb = rng.integers(0, 2**64, n, dtype=np.uint64), rng.integers(0, 2**64, n, dtype=np.uint64)
+    A, B = engine.enc_value(va, 7001), engine.enc_value(vb, 7002)
+    da = engine.dec_value(A)
+    assert np.array_equal(da[:, 0], va) and not da[:, 1].any()          # enc -> dec round trip
+    ds, dd = engine.dec_value(engine.ct_add(A, B)), engine.dec_value(engine.ct_sub(A, B))
+    assert [fpv(x) for x in ds] == [(int(x) + int(y)) % P127 for x, y in zip(va, vb)]
+    assert [fpv(x) for x in dd] == [(int(x) - int(y)) % P127 for x, y in zip(va, vb)]
+    m = 256
+    Am, Bm = engine.slice(A, 0, m), engine.slice(B, 0, m)
+    Pm = engine.ct_mul(Am, Bm, 7003)
+    assert [fpv(x) for x in engine.dec_value(Pm)] == [int(x) * int(y) % P127 for x, y in zip(va[:m], vb[:m])]
+    # distributivity on ciphertexts: (a+b)*a decrypts to a^2 + ab
+    Q = engine.ct_mul(engine.ct_add(Am, Bm), Am, 7004)
+    assert [fpv(x) for x in engine.dec_value(Q)] == [(int(x) + int(y)) * int(x) % P127 for x, y in zip(va[:m], vb[:m])]
+
+
+def test_depth_chain(engine):
+    # tests/test_depth.cpp: c <- c*c starting from enc(2); steps 1..2 here (step 3 is 172k edges per ciphertext)
+    n = 4
+    c = engine.enc_value(np.full(n, 2, np.uint64), 42)
+    exp = 2
+    for step in range(1, 3):
+        c = engine.ct_mul(c, c, 1000 + step)
+        exp = exp * exp % P127
+        assert [fpv(x) for x in engine.dec_value(c)] == [exp] * n
+    nL, nE = c.totals()
+    assert nL == 32 * n                 # layers after two squarings (8, 32, 320)
+
+
+def test_add_is_a_pure_concatenation_checksum(engine):
+    # config 2 shape: synthetic fresh-shaped ciphertexts; sum of all words is preserved by ct_add, and ct_sub only
+    # changes B's weights to p - w
+    n = 4096
+    A, B = engine.synthetic(n, 20, 1), engine.synthetic(n, 20, 2)
+    ea, eb = engine.export_soa(A), engine.export_soa(B)
+    es = engine.export_soa(engine.ct_add(A, B))
+    assert es["sigma"].shape[0] == ea["sigma"].shape[0] + eb["sigma"].shape[0]
+    x = np.bitwise_xor.reduce(es["sigma"], axis=0)
+    assert np.array_equal(x, np.bitwise_xor.reduce(ea["sigma"], axis=0) ^ np.bitwise_xor.reduce(eb["sigma"], axis=0))
+    sig = es["sigma"].reshape(n, 80, 128)
+    assert np.array_equal(sig[:, :40], ea["sigma"].reshape(n, 40, 128)) and np.array_equal(sig[:, 40:], eb["sigma"].reshape(n, 40, 128))
+    assert np.array_equal(es["lid"].reshape(n, 80)[:, 40:], eb["lid"].reshape(n, 40) + 2)
+    ed = engine.export_soa(engine.ct_sub(A, B))
+    wb = eb["w"].reshape(n, 40, 2)
+    wd = ed["w"].reshape(n, 80, 2)[:, 40:]
+    neg = [(P127 - fpv(w)) % P127 for w in wb.reshape(-1, 2)[:500]]
+    assert [fpv(w) for w in wd.reshape(-1, 2)[:500]] == neg

@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched pvac-hfhe path on B200.
+
+Headline metric (BASELINE.json: "ct_mul/s and enc_value/s (batched, device-timed)"): ct_mul/s on fresh x fresh ciphertext
+pairs (the first step of the reference's tests/test_depth.cpp chain); enc_value/s, ct_add/s, ct_sub/s and dec_value/s are
+reported in the same JSON line under "ops", each with its own roofline.
+
+  step      = one pass of ct_mul over one tile of `--pairs` synthetic ciphertext pairs (default 4096 per GPU)
+  value     = pairs/s, whole job, inputs resident in HBM, timed with CUDA events on the engine's stream, max over ranks
+  e2e       = the same metric through the C ABI with HOST buffers: pinned host SoA -> H2D import, ct_mul, D2H export
+  roofline  = dominant kernel (sigma_gather_kernel): algorithmic L2 gather bytes / its CUDA-event time vs the measured
+              L2 gather ceiling of this GPU (pvacb_l2_gather_probe); ct_add's HBM roofline is under ops.ct_add
+  cpu_baseline / --impl reference = the unmodified reference (oracle/_ref, built from /root/reference) on the host cores
+
+Launch:  python bench.py [--gpus N --steps K --warmup W]   (N > 1 through torchrun, one rank per GPU, NCCL)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P127 = (1 << 127) - 1
+EDGE_WIRE_BYTES = 1052          # serialised edge (tests/bounty2_test.cpp:98-106): the byte convention of SURVEY 8d
+GATHER_BYTES_PER_EDGE = 128 * 1024
+
+
+def mix64(z):
+    z = np.asarray(z, np.uint64)
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def item_states(seed, first, count):
+    """tape states of global items [first, first+count): identical for any sharding over GPUs"""
+    with np.errstate(over="ignore"):
+        i = np.arange(first, first + count, dtype=np.uint64)
+        return mix64(np.uint64(seed) + np.uint64(0xD1342543DE82EF95) * (i + np.uint64(1)))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in o.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(float(r[2]) for r in self.rows),
+                "samples": len(self.rows), "reasons": reasons}
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_keys():
+    from oracle import ref
+    if not ref.available():
+        return None, None
+    return ref, ref.Keys.keygen(1)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU ct_mul (fresh x fresh) on all host threads, same metric/unit/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref, K = reference_keys()
+    threads = cpu_threads()
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpvac_ref.so missing (the reference tree was not mounted at build time)"}))
+        return
+    iters = max(1, args.ref_iters)
+    for _ in range(args.warmup):
+        K.bench(3, threads, 1)
+    tot_s, tot_ops = 0.0, 0
+    for _ in range(args.steps):
+        s, ops = K.bench(3, threads, iters)
+        tot_s += s
+        tot_ops += ops
+    v = tot_ops / tot_s
+    line = {
+        "impl": "reference", "metric": "ct_mul/s", "value": v, "unit": "ct_mul/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (GF(2^127-1) limbs, bitwise)",
+        "data": "synthetic", "config": {"workload": "ct_mul fresh x fresh (2 layers, 39-40 edges each), default Params, lpn_t=16384", "pairs_per_step": threads * iters},
+        "cpu_baseline": {"value": v, "unit": "ct_mul/s", "cores": threads, "kind": "reference",
+                         "sample": f"{args.steps} steps x {threads} threads x {iters} ct_mul each, unmodified reference headers, g++ -O2 -march=x86-64-v3 -maes -mpclmul"},
+        "e2e": {"value": v, "unit": "ct_mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4096, help="ciphertext pairs per GPU per step (headline ct_mul tile)")
+    ap.add_argument("--e2e-pairs", type=int, default=512, help="pairs per GPU per end-to-end step (host buffers)")
+    ap.add_argument("--ref-iters", type=int, default=4, help="reference arm: ct_mul per thread per step")
+    ap.add_argument("--skip-ops", action="store_true", help="only the headline op")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pvac_hfhe_cppbyv_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    eng = api.Engine(device=local, prf_mode=api.PRF_LIVE)
+    # ---- keys: generated once on rank 0, replicated over NVLink with one NCCL broadcast (16.8 MB), no steady-state collective
+    blob = torch.empty(api.KEY_BLOB_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0:
+        eng.keygen(1)
+        eng.copy_key_blob_to(blob.data_ptr())
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.broadcast(blob, 0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            eng.adopt_key_blob_from(blob.data_ptr())
+    del blob
+
+    stream = torch.cuda.ExternalStream(eng.stream, device=local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        """W warm-up + K timed steps, barrier + sync on both sides, CUDA events on the engine stream; -> seconds (max over ranks)"""
+        for k in range(warmup):
+            fn(k)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(steps):
+            fn(warmup + k)
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    hbm_peak, peak_src = peaks()
+    M = args.pairs
+    g0 = rank * M                                   # global index of this rank's first pair: results do not depend on N
+    rng = np.random.default_rng(1234 + rank)
+    va = rng.integers(0, 2**64, M, dtype=np.uint64)
+    vb = rng.integers(0, 2**64, M, dtype=np.uint64)
+    A = eng.enc_value(va, tape_states=item_states(1001, g0, M))
+    B = eng.enc_value(vb, tape_states=item_states(1002, g0, M))
+    in_bytes = A.device_bytes() + B.device_bytes()
+
+    # ---- headline: ct_mul, inputs resident
+    out_edges = []
+
+    def step_mul(k):
+        P = eng.ct_mul(A, B, tape_states=item_states(2000 + k, g0, M))
+        out_edges.append(P.totals()[1])
+        if k == args.warmup + args.steps - 1:      # spot check inside the run: products decrypt to a*b mod p
+            d = eng.dec_value(eng.slice(P, 0, 8))
+            for i in range(8):
+                assert (int(d[i][0]) | (int(d[i][1]) << 64)) == int(va[i]) * int(vb[i]) % P127, "ct_mul result does not decrypt"
+        P.free()
+
+    eng.stats_reset()
+    l2_peak = eng.l2_gather_probe(5)
+    eng.profile_enable(True)
+    for k in range(args.warmup):
+        step_mul(k)
+    eng.profile_collect()
+    eng.stats_reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    out_edges.clear()
+    secs = timed(step_mul, args.steps, 0)
+    prof = eng.profile_collect()
+    sampler.stop_flag = True
+    st = eng.stats()
+    eng.profile_enable(False)
+    value = world * M * args.steps / secs
+    edges_per_step = float(np.mean(out_edges)) if out_edges else 0.0
+    gather_ms, gather_launches = prof["sigma_gather"]
+    cand_ms, _ = prof["sigma_cand"]
+    gather_bytes = edges_per_step * args.steps * GATHER_BYTES_PER_EDGE
+    achieved = gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
+    roofline = {
+        "kernel": "sigma_gather_kernel", "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
+        "traffic": None,
+        "peak_source": "measured live: pvacb_l2_gather_probe (warp-wide 1 KiB gathers from the L2-resident 16 MiB matrix H)",
+        "algorithmic_bytes_per_launch": gather_bytes / max(gather_launches, 1), "launches": gather_launches,
+        "kernel_ms_per_step": gather_ms / args.steps, "share_of_step": gather_ms * 1e-3 / secs,
+        "hbm_write_gbs": edges_per_step * args.steps * 1024 / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0, "hbm_peak": hbm_peak, "hbm_peak_source": peak_src,
+        "other_kernels_ms_per_step": {"sigma_cand_kernel": cand_ms / args.steps},
+    }
+    ncu_path = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
+    if os.path.exists(ncu_path):
+        with open(ncu_path) as f:
+            ncu = json.load(f)
+        per_edge = ncu.get("sigma_gather_kernel", {}).get("dram_bytes_per_edge")
+        if per_edge is not None and gather_launches:
+            roofline["traffic"] = per_edge * edges_per_step * args.steps / gather_launches
+
+    # ---- end to end through the C ABI with host buffers
+    Me = min(args.e2e_pairs, M)
+    Ae, Be = eng.slice(A, 0, Me), eng.slice(B, 0, Me)
+    ha, hb = eng.export_soa(Ae), eng.export_soa(Be)
+    Ae.free(); Be.free()
+
+    def pin(d):
+        o = {}
+        for k, v in d.items():
+            if v is None:
+                o[k] = None
+                continue
+            t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+            o[k] = t.numpy()
+            o["_t_" + k] = t
+        return o
+    ha, hb = pin(ha), pin(hb)
+    h2d = sum(v.nbytes for k, v in list(ha.items()) + list(hb.items()) if isinstance(v, np.ndarray))
+    cap_edges = int(Me * 1400)
+    out_sigma_t = torch.empty((cap_edges, 128), dtype=torch.int64).pin_memory()
+    out_sigma = out_sigma_t.numpy().view(np.uint64)
+    d2h_list = []
+
+    def step_e2e(k):
+        X = eng.import_soa({kk: vv for kk, vv in ha.items() if not kk.startswith("_t_")})
+        Y = eng.import_soa({kk: vv for kk, vv in hb.items() if not kk.startswith("_t_")})
+        P = eng.ct_mul(X, Y, tape_states=item_states(3000 + k, g0, Me))
+        nE = P.totals()[1]
+        d = eng.export_soa(P, pinned=out_sigma[:nE])
+        d2h_list.append(sum(v.nbytes for v in d.values() if isinstance(v, np.ndarray)))
+        X.free(); Y.free(); P.free()
+
+    for k in range(args.warmup):
+        step_e2e(k)
+    d2h_list.clear()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e(args.warmup + k)
+    torch.cuda.synchronize()
+    e2e_secs = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": world * Me * args.steps / e2e_secs, "unit": "ct_mul/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(np.mean(d2h_list)),
+           "pairs_per_step_per_gpu": Me, "note": "pinned host SoA arrays -> pvacb_batch_import_soa x2 -> pvacb_ct_mul_ex -> pvacb_batch_export_soa (1.3 MB per product over PCIe)"}
+    del out_sigma, out_sigma_t
+
+    # ---- the other ops of the path (short, device-timed), each with the roofline that bounds it
+    ops = {}
+    if not args.skip_ops:
+        def op_rate(fn, n, steps=3, warmup=3):
+            s = timed(fn, steps, warmup)
+            return world * n * steps / s, s / steps
+
+        # ct_add / ct_sub on synthetic fresh-shaped ciphertexts (config 2 shape: 2 layers, 40 edges)
+        n_add = 1 << 15
+        SA, SB = eng.synthetic(n_add, 20, 11 + rank), eng.synthetic(n_add, 20, 22 + rank)
+        add_bytes = n_add * (2 * (40 * EDGE_WIRE_BYTES + 58) + 80 * EDGE_WIRE_BYTES + 108)
+        for name, f in (("ct_add", eng.ct_add), ("ct_sub", eng.ct_sub)):
+            eng.profile_enable(True)
+            eng.profile_collect()
+            rate, spp = op_rate(lambda k, f=f: f(SA, SB).free(), n_add, steps=5)
+            pr = eng.profile_collect()
+            eng.profile_enable(False)
+            kms, kl = pr["concat"]
+            kms_timed = kms * 5 / max(kl, 1)       # 5 timed launches out of kl = warm-up + timed
+            ach = add_bytes * 5 / (kms_timed * 1e-3) / 1e9
+            ops[name] = {"value": rate, "unit": name + "/s", "pairs_per_step_per_gpu": n_add, "ms_per_step": spp * 1e3,
+                         "roofline": {"kernel": "concat_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                      "algorithmic_bytes_per_launch": add_bytes, "peak_source": peak_src}}
+        SA.free(); SB.free()
+
+        # enc_value: faithful PRF (all 16384 LPN rows, like the reference) and live-row PRF (rows 0..127, same bits)
+        for mode, tag, n_enc in ((api.PRF_FAITHFUL, "enc_value_faithful", 512), (api.PRF_LIVE, "enc_value_live", 16384)):
+            eng.set_prf_mode(mode)
+            vals = rng.integers(0, 2**64, n_enc, dtype=np.uint64)
+            eng.stats_reset()
+            eng.profile_enable(True)
+            eng.profile_collect()
+            rate, spp = op_rate(lambda k: eng.enc_value(vals, 5000 + k).free(), n_enc, steps=3, warmup=3)
+            pr = eng.profile_collect()
+            eng.profile_enable(False)
+            stx = eng.stats()
+            lpn_ms, lpn_l = pr["prf_lpn"]
+            blocks_per_launch = stx["aes_blocks"] / max(lpn_l, 1)
+            ops[tag] = {"value": rate, "unit": "enc_value/s", "items_per_step_per_gpu": n_enc, "ms_per_step": spp * 1e3,
+                        "aes_blocks_per_item": stx["aes_blocks"] / (6 * n_enc),
+                        "roofline": {"kernel": "prf_lpn_kernel", "bound": "shared-memory LSU (T-table AES)", "achieved": blocks_per_launch / (lpn_ms / max(lpn_l, 1) * 1e-3) / 1e9,
+                                     "unit": "G AES-256 blocks/s", "peak": 148 * 32 * 1.965 / 224.0, "frac": None,
+                                     "peak_source": "model: 224 conflict-free LDS per block, 32 lanes/clk/SM, 148 SMs at 1965 MHz",
+                                     "share_of_step": (lpn_ms / max(lpn_l, 1)) * 1e-3 / spp}}
+            r = ops[tag]["roofline"]
+            r["frac"] = r["achieved"] / r["peak"]
+        # dec_value of fresh ciphertexts
+        for mode, tag, n_dec in ((api.PRF_FAITHFUL, "dec_value_faithful", 2048), (api.PRF_LIVE, "dec_value_live", M)):
+            eng.set_prf_mode(mode)
+            D = eng.slice(A, 0, min(n_dec, M))
+            nd = len(D)
+            rate, spp = op_rate(lambda k: eng.dec_value(D), nd, steps=3, warmup=3)
+            ops[tag] = {"value": rate, "unit": "dec_value/s", "items_per_step_per_gpu": nd, "ms_per_step": spp * 1e3}
+            D.free()
+        eng.set_prf_mode(api.PRF_LIVE)
+
+    # ---- CPU baseline: the unmodified reference on the host cores (rank 0, bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        ref, K = reference_keys()
+        threads = cpu_threads()
+        if ref is not None:
+            iters = 16
+            s, n_ops = K.bench(3, threads, iters)
+            cpu = {"value": n_ops / s, "unit": "ct_mul/s", "cores": threads, "kind": "reference",
+                   "sample": f"{threads} threads x {iters} ct_mul (fresh x fresh) each, unmodified reference headers behind a deterministic tape, {s:.1f} s"}
+            extra = {}
+            for op, nm, it in ((0, "enc_value/s", 8), (1, "ct_add/s", 20000), (4, "dec_value/s", 32)):
+                s2, n2 = K.bench(op, threads, it)
+                extra[nm] = n2 / s2
+            cpu["other_ops"] = extra
+        else:
+            from oracle import port
+            ko = port.Keys.keygen(1)
+            a, b = ko.enc_value(1, 5), ko.enc_value(2, 7)
+            t0 = time.perf_counter()
+            for i in range(8):
+                ko.ct_mul(3 + i, a, b)
+            cpu = {"value": 8 / (time.perf_counter() - t0), "unit": "ct_mul/s", "cores": 1, "kind": "port", "sample": "8 ct_mul fresh x fresh, oracle C port, 1 thread"}
+
+    if rank == 0:
+        line = {
+            "metric": "ct_mul/s", "value": value, "unit": "ct_mul/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 (GF(2^127-1) limbs, bitwise)", "data": "synthetic",
+            "config": {"workload": "ct_mul fresh x fresh (2 layers, 39-40 edges each -> 8 layers, ~1200 edges), default Params",
+                       "pairs_per_step_per_gpu": M, "out_edges_per_step_per_gpu": edges_per_step, "input_bytes_resident": in_bytes,
+                       "l2": "inputs (%.0f MB) and outputs (%.1f GB per step) exceed the 126 MB L2; the 16 MiB matrix H is meant to be L2 resident" % (in_bytes / 1e6, edges_per_step * 1052 / 1e9),
+                       "sharding": f"batch index, {world} rank(s), keys replicated by one NCCL broadcast, no steady-state collective", "prf_mode_for_inputs": "live"},
+            "e2e": e2e, "gpu_launches": st["kernel_launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(), "ops": ops,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,12 @@ int pvacb_sync(pvacb_ctx* ctx);
 /* counters since the last reset: kernels launched, AES-256 blocks computed, sigma_from_H evaluations */
 void pvacb_stats(const pvacb_ctx* ctx, uint64_t* kernel_launches, uint64_t* aes_blocks, uint64_t* sigma_edges);
 void pvacb_stats_reset(pvacb_ctx* ctx);
+/* optional per-kernel timing with CUDA events on the context's stream. Tags: 0 prf_lpn, 1 sigma_cand, 2 sigma_gather,
+ * 3 concat (ct_add/ct_sub), 4 dec_edges, 5 mul planning. collect() synchronises, sums ms and launch counts per tag. */
+int pvacb_profile_enable(pvacb_ctx* ctx, int on);
+/* microbenchmark: achieved GB/s of warp-wide 1 KiB gathers from the L2-resident matrix H (ceiling of the sigma kernel) */
+int pvacb_l2_gather_probe(pvacb_ctx* ctx, int reps, double* gbps_out);
+int pvacb_profile_collect(pvacb_ctx* ctx, float ms_out[8], uint32_t launches_out[8]);
 
 /* ---- keys: replaces keygen(const Params&, PubKey&, SecKey&), crypto/keygen.hpp:35 ---------------------------------- */
 /* keygen with default Params; consumes the tape stream with initial state `tape_state` exactly like the reference. */
@@ -79,6 +85,9 @@ int pvacb_keys_export_raw(pvacb_ctx* ctx, uint64_t* canon_tag, uint8_t h_digest[
 int pvacb_keys_device_blob(pvacb_ctx* ctx, void** dptr, size_t* bytes);
 int pvacb_keys_alloc_blob(pvacb_ctx* ctx, void** dptr);            /* empty blob on this device to receive a broadcast */
 int pvacb_keys_adopt_blob(pvacb_ctx* ctx);                         /* after the blob has been filled */
+/* copy the blob to / adopt it from an arbitrary device buffer (e.g. a tensor that an NCCL broadcast filled) */
+int pvacb_keys_copy_blob_to(pvacb_ctx* ctx, void* dst_device);
+int pvacb_keys_adopt_blob_from(pvacb_ctx* ctx, const void* src_device);
 
 /* ---- the hot path ------------------------------------------------------------------------------------------------ */
 /* Cipher enc_value(pk, sk, uint64_t)                      ops/encrypt.hpp:289 */

@@ -14,6 +14,7 @@ importing this module loads the CUDA library, and Engine() raises if no sm_100 d
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -38,6 +39,7 @@ SYMBOLS = [
     "pvacb_dec_value", "pvacb_batch_free", "pvacb_batch_count", "pvacb_batch_totals", "pvacb_batch_device_bytes", "pvacb_batch_offsets",
     "pvacb_batch_slice", "pvacb_batch_export_soa", "pvacb_batch_import_soa", "pvacb_batch_wire_size", "pvacb_batch_export_wire",
     "pvacb_batch_import_wire", "pvacb_batch_synthetic", "pvacb_prf", "pvacb_sigma_from_H", "pvacb_fp_op",
+    "pvacb_profile_enable", "pvacb_profile_collect", "pvacb_keys_copy_blob_to", "pvacb_keys_adopt_blob_from", "pvacb_l2_gather_probe",
 ]
 
 
@@ -99,6 +101,11 @@ def load_library():
         "pvacb_prf": (i32, [vp, sz, P(u64), P(u64), P(u64), i32, P(u64), P(u64)]),
         "pvacb_sigma_from_H": (i32, [vp, sz, P(u64), P(u64), P(u64), P(u16), P(u8), P(u64), P(u64)]),
         "pvacb_fp_op": (i32, [vp, i32, sz, P(u64), P(u64), P(u64)]),
+        "pvacb_profile_enable": (i32, [vp, i32]),
+        "pvacb_profile_collect": (i32, [vp, P(C.c_float), P(u32)]),
+        "pvacb_keys_copy_blob_to": (i32, [vp, vp]),
+        "pvacb_keys_adopt_blob_from": (i32, [vp, vp]),
+        "pvacb_l2_gather_probe": (i32, [vp, i32, P(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -122,6 +129,7 @@ class Batch:
     def __init__(self, eng, handle):
         self.eng = eng
         self.h = handle
+        eng._batches.add(self)
 
     def __len__(self):
         return int(load_library().pvacb_batch_count(self.h))
@@ -136,7 +144,8 @@ class Batch:
 
     def free(self):
         if self.h:
-            load_library().pvacb_batch_free(self.h)
+            if self.eng.h:          # the context owns the memory pool: never touch a batch after its engine was closed
+                load_library().pvacb_batch_free(self.h)
             self.h = None
 
     def __del__(self):
@@ -156,12 +165,21 @@ class Engine:
         if rc:
             raise PvacbError(rc, f"cannot create a context on CUDA device {device} (an sm_100-class GPU is required; there is no CPU fallback)")
         self.L, self.h, self.device = L, h, device
+        self._batches = weakref.WeakSet()
         self.set_prf_mode(prf_mode)
 
     def close(self):
         if self.h:
+            for b in list(self._batches):
+                b.free()
             self.L.pvacb_ctx_destroy(self.h)
             self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _ck(self, rc):
         if rc:
@@ -219,6 +237,29 @@ class Engine:
 
     def adopt_key_blob(self):
         self._ck(self.L.pvacb_keys_adopt_blob(self.h))
+
+    def copy_key_blob_to(self, device_ptr):
+        self._ck(self.L.pvacb_keys_copy_blob_to(self.h, device_ptr))
+
+    def adopt_key_blob_from(self, device_ptr):
+        self._ck(self.L.pvacb_keys_adopt_blob_from(self.h, device_ptr))
+
+    PROF_TAGS = ("prf_lpn", "sigma_cand", "sigma_gather", "concat", "dec_edges", "mul_plan", "t6", "t7")
+
+    def l2_gather_probe(self, reps=5):
+        g = C.c_double()
+        self._ck(self.L.pvacb_l2_gather_probe(self.h, reps, C.byref(g)))
+        return float(g.value)
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.pvacb_profile_enable(self.h, int(on)))
+
+    def profile_collect(self):
+        """-> {tag: (total ms, launches)} of the bracketed kernels since the last collect (CUDA events on the engine stream)."""
+        ms = (C.c_float * 8)()
+        cnt = (C.c_uint32 * 8)()
+        self._ck(self.L.pvacb_profile_collect(self.h, ms, cnt))
+        return {t: (float(ms[i]), int(cnt[i])) for i, t in enumerate(self.PROF_TAGS)}
 
     # ---- hot path
     def enc_value(self, values, batch_seed=0, tape_states=None):

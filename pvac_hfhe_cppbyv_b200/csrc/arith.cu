@@ -115,6 +115,7 @@ int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode, Batch** out) {
         unsigned ych = (unsigned)std::min<uint64_t>(std::max<uint64_t>((avg + kConcatChunk - 1) / kConcatChunk, 1), 4096);
         // CUDA grids allow 2^31-1 blocks in x and 65535 in y
         dim3 grid((unsigned)n, ych);
+        ProfScope ps(ctx, PROF_CONCAT);
         concat_kernel<<<grid, kConcatThreads, 0, ctx->stream>>>(view_of(A), view_of(B), mode, o->loff, o->eoff, o->rule, o->ztag, o->nlo, o->nhi, o->pa,
                                                                  o->pb, o->lid, o->idx, o->ch, o->w, o->sigma);
     }

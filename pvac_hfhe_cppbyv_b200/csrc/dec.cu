@@ -113,10 +113,13 @@ int op_dec_value(Ctx* ctx, const Batch* Cb, uint64_t* h_out) {
         ctx->stat_kernel_launches += 2;
     }
     bool block_per_item = Cb->nE / Cb->n > 256;
+    {
+    ProfScope ps(ctx, PROF_DEC_EDGES);
     if (block_per_item)
         dec_edges_kernel<true><<<(unsigned)Cb->n, 256, 0, ctx->stream>>>(Cb->n, Cb->loff, Cb->eoff, Cb->lid, Cb->idx, Cb->ch, Cb->w, ctx->kv.powg, Rinv, res);
     else
         dec_edges_kernel<false><<<(unsigned)((Cb->n + 7) / 8), 256, 0, ctx->stream>>>(Cb->n, Cb->loff, Cb->eoff, Cb->lid, Cb->idx, Cb->ch, Cb->w, ctx->kv.powg, Rinv, res);
+    }
     ctx->stat_kernel_launches += 1;
     PV_CUDA(cudaGetLastError());
     unsigned int h_err = 0;

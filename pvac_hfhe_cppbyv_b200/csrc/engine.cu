@@ -188,6 +188,43 @@ void pvacb_stats(const pvacb_ctx* x, uint64_t* k, uint64_t* a, uint64_t* s) {
 }
 void pvacb_stats_reset(pvacb_ctx* x) { C(x)->stat_kernel_launches = C(x)->stat_aes_blocks = C(x)->stat_sigma_edges = 0; }
 
+int pvacb_profile_enable(pvacb_ctx* x, int on) {
+    Ctx* ctx = C(x);
+    ctx->profile = on ? 1 : 0;
+    return PV_OK;
+}
+// sums the CUDA-event time (ms) of every bracketed kernel launch since the last collect, per tag; clears the spans
+int pvacb_profile_collect(pvacb_ctx* x, float* ms_out /*8*/, uint32_t* launches_out /*8*/) {
+    Ctx* ctx = C(x);
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < PROF_NTAGS; i++) { ms_out[i] = 0.f; if (launches_out) launches_out[i] = 0; }
+    for (auto& s : ctx->prof_spans) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        ms_out[s.tag] += ms;
+        if (launches_out) launches_out[s.tag]++;
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    ctx->prof_spans.clear();
+    return PV_OK;
+}
+int pvacb_keys_copy_blob_to(pvacb_ctx* x, void* dst_device) {
+    Ctx* ctx = C(x);
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    PV_CUDA(cudaMemcpyAsync(dst_device, ctx->d_blob, kBlobBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+int pvacb_keys_adopt_blob_from(pvacb_ctx* x, const void* src_device) {
+    Ctx* ctx = C(x);
+    int rc = ensure_blob(ctx);
+    if (rc) return rc;
+    PV_CUDA(cudaMemcpyAsync(ctx->d_blob, src_device, kBlobBytes, cudaMemcpyDefault, ctx->stream));
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return pvacb_keys_adopt_blob(x);
+}
+
 // ---- keys
 int pvacb_keygen(pvacb_ctx* x, uint64_t tape_state) {
     Ctx* ctx = C(x);
@@ -245,6 +282,7 @@ int pvacb_keys_alloc_blob(pvacb_ctx* x, void** dptr) {
     *dptr = ctx->d_blob;
     return PV_OK;
 }
+int pvacb_keys_adopt_blob(pvacb_ctx* x);
 int pvacb_keys_adopt_blob(pvacb_ctx* x) {
     Ctx* ctx = C(x);
     if (!ctx->d_blob) return PV_E_NOKEYS;

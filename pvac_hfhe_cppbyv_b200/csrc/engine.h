@@ -61,9 +61,22 @@ struct Ctx {
     uint64_t stat_kernel_launches = 0;
     uint64_t stat_aes_blocks = 0;
     uint64_t stat_sigma_edges = 0;
-    float stat_ms[8] = {0};          // per-stage CUDA-event timings of the last op when profiling is on
-    int profile = 0;
+    int profile = 0;                 // when set, the dominant kernels are bracketed by CUDA events on ctx->stream
+    struct ProfSpan { int tag; cudaEvent_t a, b; };
+    std::vector<ProfSpan> prof_spans;
     bool lpn_attr_set = false;
+};
+
+// profiling tags (pvacb_profile_collect)
+enum : int { PROF_PRF_LPN = 0, PROF_SIGMA_CAND = 1, PROF_SIGMA_GATHER = 2, PROF_CONCAT = 3, PROF_DEC_EDGES = 4, PROF_MUL_PLAN = 5, PROF_NTAGS = 8 };
+struct ProfScope {
+    Ctx* ctx; cudaEvent_t a = nullptr, b = nullptr; int tag;
+    ProfScope(Ctx* c, int t) : ctx(c), tag(t) {
+        if (ctx->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEventRecord(b, ctx->stream); ctx->prof_spans.push_back({tag, a, b}); }
+    }
 };
 
 // device ciphertext batch, structure-of-arrays

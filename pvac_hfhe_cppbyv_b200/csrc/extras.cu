@@ -55,6 +55,35 @@ __global__ void synth_sigma_kernel(uint64_t nwords, uint64_t seed, uint64_t* sig
     for (; i < nwords; i += stride) sigma[i] = mix64(seed ^ (i * 0x9E3779B97F4A7C15ull));
 }
 
+// L2 gather probe: the access pattern of sigma_gather_kernel (a warp XOR-reads pseudo-random 1 KiB columns of the 16 MiB
+// matrix H with 128-bit loads) with nothing else around it. U = columns in flight per warp. The best bandwidth over a
+// few (U, CTAs/SM) shapes is used as the practical ceiling of the sigma kernel.
+template <int U>
+__global__ void __launch_bounds__(256) l2_gather_probe_kernel(const uint4* __restrict__ H4, uint32_t cols_per_warp, uint4* __restrict__ sink) {
+    const int lane = threadIdx.x & 31;
+    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t state = w * 2654435761u + 12345u;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    for (uint32_t i = 0; i < cols_per_warp; i += U) {
+        uint4 v[2 * U];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            state = state * 1664525u + 1013904223u;
+            uint32_t col = (state >> 10) & (kNBits - 1);
+            const uint4* p = H4 + (size_t)col * 64 + lane;
+            v[2 * k] = __ldcg(p);
+            v[2 * k + 1] = __ldcg(p + 32);
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
+            a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
+        }
+    }
+    a0.x ^= a1.x; a0.y ^= a1.y; a0.z ^= a1.z; a0.w ^= a1.w;
+    if ((a0.x ^ a0.y ^ a0.z ^ a0.w) == 0x9E3779B9u && cols_per_warp == 0xFFFFFFFFu) sink[w] = a0;   // keeps the loads alive
+}
+
 __global__ void slice_fix_offsets_kernel(uint64_t cnt, const uint32_t* src_l, const uint32_t* src_e, uint32_t* dst_l, uint32_t* dst_e) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > cnt) return;
@@ -170,6 +199,42 @@ int pvacb_batch_synthetic(pvacb_ctx* x, size_t n, int epl, uint64_t seed, pvacb_
     PV_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stat_kernel_launches += 2;
     *out = reinterpret_cast<pvacb_batch*>(b);
+    return PV_OK;
+}
+
+// measured L2 gather bandwidth (GB/s) of this device for the H matrix access pattern; best over shapes and `reps`
+int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
+    Ctx* ctx = C(x);
+    if (!ctx->have_keys || !gbps_out) return PV_E_NOKEYS;
+    cudaSetDevice(ctx->device);
+    const uint32_t cols_per_warp = 4096;
+    uint4* sink = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, (void**)&sink, (size_t)ctx->sm_count * 16 * 8 * 16))) return rc;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0;
+    const uint4* H4 = reinterpret_cast<const uint4*>(ctx->kv.H);
+    for (int shape = 0; shape < 6; shape++) {
+        const int ctas_per_sm = (shape & 1) ? 8 : 4;
+        const unsigned grid = (unsigned)ctx->sm_count * ctas_per_sm;
+        for (int r = 0; r < reps + 2; r++) {
+            cudaEventRecord(a, ctx->stream);
+            if (shape / 2 == 0) l2_gather_probe_kernel<4><<<grid, 256, 0, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (shape / 2 == 1) l2_gather_probe_kernel<8><<<grid, 256, 0, ctx->stream>>>(H4, cols_per_warp, sink);
+            else l2_gather_probe_kernel<16><<<grid, 256, 0, ctx->stream>>>(H4, cols_per_warp, sink);
+            cudaEventRecord(b, ctx->stream);
+            PV_CUDA(cudaEventSynchronize(b));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, a, b);
+            double bytes = (double)grid * 8 * cols_per_warp * 1024.0;
+            double g = bytes / (ms * 1e-3) / 1e9;
+            if (r > 1 && g > best) best = g;
+        }
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    dev_free(ctx, sink);
+    *gbps_out = best;
     return PV_OK;
 }
 

@@ -120,7 +120,10 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     }
     uint64_t units = ((ncores << rpc_log2) + kLpnThreads - 1) / kLpnThreads;
     unsigned grid = (unsigned)(units < (uint64_t)ctx->sm_count ? units : (uint64_t)ctx->sm_count);
-    prf_lpn_kernel<<<grid, kLpnThreads, kAesRepBytes, ctx->stream>>>(ctx->kv.T0, ctx->lpn_s, ncores, rpc_log2, rk, ctr0, d_flags, ybits, rare);
+    {
+        ProfScope ps(ctx, PROF_PRF_LPN);
+        prf_lpn_kernel<<<grid, kLpnThreads, kAesRepBytes, ctx->stream>>>(ctx->kv.T0, ctx->lpn_s, ncores, rpc_log2, rk, ctr0, d_flags, ybits, rare);
+    }
     prf_finalize_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, ctx->stream>>>(njobs, d_flags, ybits, wpc, top, d_out);
     PV_CUDA(cudaGetLastError());
     ctx->stat_kernel_launches += 3;

@@ -252,11 +252,17 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
         if (S.seed_idx) S.seed_idx += s0; else { S.ztag += s0; S.nlo += s0; S.nhi += s0; }
         S.idx += s0; S.ch += s0; S.salt += s0;
         if (S.out_row) S.out_row += s0; else S.out += s0 * kMWords;
-        sigma_cand_kernel<<<(unsigned)((ns + kCandSrcPerCta - 1) / kCandSrcPerCta), kCandThreads, 0, ctx->stream>>>(S, ctx->kv.canon_tag, cand);
+        {
+            ProfScope ps(ctx, PROF_SIGMA_CAND);
+            sigma_cand_kernel<<<(unsigned)((ns + kCandSrcPerCta - 1) / kCandSrcPerCta), kCandThreads, 0, ctx->stream>>>(S, ctx->kv.canon_tag, cand);
+        }
         unsigned grid = (unsigned)((ns + kGatherWarps - 1) / kGatherWarps);
         unsigned cap = (unsigned)ctx->sm_count * 8;
         if (grid > cap) grid = cap;
-        sigma_gather_kernel<<<grid, kGatherWarps * 32, 0, ctx->stream>>>(S, ctx->kv.canon_tag, cand, reinterpret_cast<const uint4*>(ctx->kv.H));
+        {
+            ProfScope ps(ctx, PROF_SIGMA_GATHER);
+            sigma_gather_kernel<<<grid, kGatherWarps * 32, 0, ctx->stream>>>(S, ctx->kv.canon_tag, cand, reinterpret_cast<const uint4*>(ctx->kv.H));
+        }
         PV_CUDA(cudaGetLastError());
         ctx->stat_kernel_launches += 2;
     }

@@ -84,40 +84,97 @@ PV_HD void aes256_ctr_block(const uint32_t* T0, const uint8_t* sbox, const uint3
 }
 
 #if defined(__CUDACC__)
-// ---- hot path: lane-private-bank replicated tables in shared memory.
-// Layout: word index ((t*256 + a) * 32 + lane), t = 0..3 (T_t = T0 rotated left by 8t bits): 128 KiB.
-constexpr int kAesRepWords = 4 * 256 * 32;
-constexpr int kAesRepBytes = kAesRepWords * 4;
+// ---- hot path: lane-private-bank replicated tables in shared memory (128 KiB).
+// Byte offset of (table t, entry a, lane L) = (t >> 1) * 65536 + a * 256 + (t & 1) * 128 + L * 4   (T_t = T0 rotated left 8t bits).
+// Lane L only ever touches bank L, so every lookup is one conflict-free wavefront whatever the data. The 256-byte entry
+// stride lets ONE PRMT build the whole shared-memory offset of a lookup: bytes (lane*4, state byte k, 0, 0); the table
+// select rides in the LDS immediate. (ncu r01: the first version spent 48 ALU ops per round on shift/mask/add address
+// arithmetic and was ALU-pipe bound at 88%; this form needs 16 PRMT + 8 LOP3.)
+// The tables sit at ABSOLUTE shared-window addresses 0x10000 (T0/T1) and 0x20000 (T2/T3), so the PRMT result is the
+// complete address and the table select is an LDS immediate -- no per-lookup add of the dynamic-smem base. The kernel
+// therefore asks for 0x30000 bytes of dynamic shared memory (the first 64 KiB minus the base stay unused).
+constexpr int kAesRepBytes = 0x30000;
+constexpr uint32_t kAesTabAbs = 0x10000;
 
-__device__ __forceinline__ void aes_fill_rep_tables(uint32_t* sT, const uint32_t* __restrict__ gT0) {
-    for (int i = threadIdx.x; i < kAesRepWords; i += blockDim.x) {
-        int a = (i >> 5) & 255, t = i >> 13;
+__device__ __forceinline__ void aes_fill_rep_tables(uint8_t* sT, const uint32_t* __restrict__ gT0) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(sT);
+    for (int i = threadIdx.x; i < 4 * 256 * 32; i += blockDim.x) {
+        int odd = (i >> 5) & 1, a = (i >> 6) & 255, tp = i >> 14;
         uint32_t v = __ldg(gT0 + a);
-        sT[i] = __funnelshift_l(v, v, 8 * t);
+        uint32_t abs_addr = kAesTabAbs + (uint32_t)i * 4;       // = 0x10000*(1+tp) + a*256 + odd*128 + lane*4
+        *reinterpret_cast<uint32_t*>(sT + (abs_addr - base)) = __funnelshift_l(v, v, 8 * (2 * tp + odd));
     }
 }
 
-// Tl = sT + lane. One AES-256 block of the counter stream; rk[60] in registers.
-#define PVACB_TL(t, a) Tl[(((t) << 8) + (a)) << 5]
-__device__ __forceinline__ void aes_block_rep(const uint32_t* __restrict__ Tl, const uint32_t (&rk)[60], uint64_t ctr, uint64_t& w0, uint64_t& w1) {
-    uint32_t s0 = (uint32_t)ctr ^ rk[0], s1 = (uint32_t)(ctr >> 32) ^ rk[1], s2 = rk[2], s3 = rk[3];
-#pragma unroll
-    for (int r = 1; r < 14; r++) {
-        uint32_t t0 = PVACB_TL(0, s0 & 0xff) ^ PVACB_TL(1, (s1 >> 8) & 0xff) ^ PVACB_TL(2, (s2 >> 16) & 0xff) ^ PVACB_TL(3, s3 >> 24) ^ rk[4 * r + 0];
-        uint32_t t1 = PVACB_TL(0, s1 & 0xff) ^ PVACB_TL(1, (s2 >> 8) & 0xff) ^ PVACB_TL(2, (s3 >> 16) & 0xff) ^ PVACB_TL(3, s0 >> 24) ^ rk[4 * r + 1];
-        uint32_t t2 = PVACB_TL(0, s2 & 0xff) ^ PVACB_TL(1, (s3 >> 8) & 0xff) ^ PVACB_TL(2, (s0 >> 16) & 0xff) ^ PVACB_TL(3, s1 >> 24) ^ rk[4 * r + 2];
-        uint32_t t3 = PVACB_TL(0, s3 & 0xff) ^ PVACB_TL(1, (s0 >> 8) & 0xff) ^ PVACB_TL(2, (s1 >> 16) & 0xff) ^ PVACB_TL(3, s2 >> 24) ^ rk[4 * r + 3];
-        s0 = t0; s1 = t1; s2 = t2; s3 = t3;
-    }
-    // last round: S-box bytes picked out of the T-tables (T2 has S in byte 0, T3 in byte 1, T0 in byte 2, T1 in byte 3)
-    uint32_t o0 = (PVACB_TL(2, s0 & 0xff) & 0x000000ffu) | (PVACB_TL(3, (s1 >> 8) & 0xff) & 0x0000ff00u) | (PVACB_TL(0, (s2 >> 16) & 0xff) & 0x00ff0000u) | (PVACB_TL(1, s3 >> 24) & 0xff000000u);
-    uint32_t o1 = (PVACB_TL(2, s1 & 0xff) & 0x000000ffu) | (PVACB_TL(3, (s2 >> 8) & 0xff) & 0x0000ff00u) | (PVACB_TL(0, (s3 >> 16) & 0xff) & 0x00ff0000u) | (PVACB_TL(1, s0 >> 24) & 0xff000000u);
-    uint32_t o2 = (PVACB_TL(2, s2 & 0xff) & 0x000000ffu) | (PVACB_TL(3, (s3 >> 8) & 0xff) & 0x0000ff00u) | (PVACB_TL(0, (s0 >> 16) & 0xff) & 0x00ff0000u) | (PVACB_TL(1, s1 >> 24) & 0xff000000u);
-    uint32_t o3 = (PVACB_TL(2, s3 & 0xff) & 0x000000ffu) | (PVACB_TL(3, (s0 >> 8) & 0xff) & 0x0000ff00u) | (PVACB_TL(0, (s1 >> 16) & 0xff) & 0x00ff0000u) | (PVACB_TL(1, s2 >> 24) & 0xff000000u);
-    o0 ^= rk[56]; o1 ^= rk[57]; o2 ^= rk[58]; o3 ^= rk[59];
-    w0 = (uint64_t)o0 | ((uint64_t)o1 << 32);
-    w1 = (uint64_t)o2 | ((uint64_t)o3 << 32);
+template <int kOff>
+__device__ __forceinline__ uint32_t aes_lds_abs(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(kOff));
+    return v;
 }
+// address of the lookup indexed by byte k of s: (lane4 | byte_k << 8); table t selected by the immediate
+#define PVACB_IDX(s, k) __byte_perm((s), lane4, 0x5504 | ((k) << 4))
+#define PVACB_LD(t, idx) aes_lds_abs<(int)kAesTabAbs + ((t) >> 1) * 65536 + ((t) & 1) * 128>(idx)
+
+// AES-256 counter-mode block generator for one thread: round keys in registers, and the part of round 1 that only depends
+// on the high 96 bits of the input block (the counter's high word and the zero half, crypto/lpn.hpp:84,104) hoisted out of
+// the per-block work: 4 lookups instead of 16 in round 1.
+struct AesCtrThread {
+    uint32_t rk0;          // rk[0]
+    uint32_t c0, c1, c2, c3;   // round-1 partial columns (everything except the terms of state word 0)
+    uint32_t hi;           // counter high word the partials were computed for
+    uint32_t rk1;          // rk[1], needed again if the low word wraps
+    uint32_t rk2, rk3, rk4, rk5, rk6, rk7;
+    uint32_t rk[52];       // rk[8..59]
+
+    __device__ __forceinline__ void prime(const uint8_t* __restrict__ sT, uint32_t lane4, uint32_t hi_word) {
+        hi = hi_word;
+        uint32_t s1 = hi_word ^ rk1, s2 = rk2, s3 = rk3;
+        c0 = PVACB_LD(1, PVACB_IDX(s1, 1)) ^ PVACB_LD(2, PVACB_IDX(s2, 2)) ^ PVACB_LD(3, PVACB_IDX(s3, 3)) ^ rk4;
+        c1 = PVACB_LD(0, PVACB_IDX(s1, 0)) ^ PVACB_LD(1, PVACB_IDX(s2, 1)) ^ PVACB_LD(2, PVACB_IDX(s3, 2)) ^ rk5;
+        c2 = PVACB_LD(0, PVACB_IDX(s2, 0)) ^ PVACB_LD(1, PVACB_IDX(s3, 1)) ^ PVACB_LD(3, PVACB_IDX(s1, 3)) ^ rk6;
+        c3 = PVACB_LD(0, PVACB_IDX(s3, 0)) ^ PVACB_LD(2, PVACB_IDX(s1, 2)) ^ PVACB_LD(3, PVACB_IDX(s2, 3)) ^ rk7;
+    }
+
+    __device__ __forceinline__ void load_keys(const uint32_t* __restrict__ rk_core) {
+        const uint4* p = reinterpret_cast<const uint4*>(rk_core);
+        uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        rk0 = v0.x; rk1 = v0.y; rk2 = v0.z; rk3 = v0.w;
+        rk4 = v1.x; rk5 = v1.y; rk6 = v1.z; rk7 = v1.w;
+#pragma unroll
+        for (int i = 0; i < 13; i++) {
+            uint4 v = __ldg(p + 2 + i);
+            rk[4 * i] = v.x; rk[4 * i + 1] = v.y; rk[4 * i + 2] = v.z; rk[4 * i + 3] = v.w;
+        }
+    }
+
+    __device__ __forceinline__ void block(const uint8_t* __restrict__ sT, uint32_t lane4, uint64_t ctr, uint64_t& w0, uint64_t& w1) {
+        uint32_t hw = (uint32_t)(ctr >> 32);
+        if (hw != hi) prime(sT, lane4, hw);          // the low word wrapped: at most once per thread
+        uint32_t x = (uint32_t)ctr ^ rk0;
+        uint32_t s0 = c0 ^ PVACB_LD(0, PVACB_IDX(x, 0));
+        uint32_t s1 = c1 ^ PVACB_LD(3, PVACB_IDX(x, 3));
+        uint32_t s2 = c2 ^ PVACB_LD(2, PVACB_IDX(x, 2));
+        uint32_t s3 = c3 ^ PVACB_LD(1, PVACB_IDX(x, 1));
+#pragma unroll
+        for (int r = 2; r < 14; r++) {
+            const int kb = 4 * r - 8;
+            uint32_t t0 = PVACB_LD(0, PVACB_IDX(s0, 0)) ^ PVACB_LD(1, PVACB_IDX(s1, 1)) ^ PVACB_LD(2, PVACB_IDX(s2, 2)) ^ PVACB_LD(3, PVACB_IDX(s3, 3)) ^ rk[kb + 0];
+            uint32_t t1 = PVACB_LD(0, PVACB_IDX(s1, 0)) ^ PVACB_LD(1, PVACB_IDX(s2, 1)) ^ PVACB_LD(2, PVACB_IDX(s3, 2)) ^ PVACB_LD(3, PVACB_IDX(s0, 3)) ^ rk[kb + 1];
+            uint32_t t2 = PVACB_LD(0, PVACB_IDX(s2, 0)) ^ PVACB_LD(1, PVACB_IDX(s3, 1)) ^ PVACB_LD(2, PVACB_IDX(s0, 2)) ^ PVACB_LD(3, PVACB_IDX(s1, 3)) ^ rk[kb + 2];
+            uint32_t t3 = PVACB_LD(0, PVACB_IDX(s3, 0)) ^ PVACB_LD(1, PVACB_IDX(s0, 1)) ^ PVACB_LD(2, PVACB_IDX(s1, 2)) ^ PVACB_LD(3, PVACB_IDX(s2, 3)) ^ rk[kb + 3];
+            s0 = t0; s1 = t1; s2 = t2; s3 = t3;
+        }
+        // last round: S-box bytes picked out of the T-tables (T2 has S in byte 0, T3 in byte 1, T0 in byte 2, T1 in byte 3)
+        uint32_t o0 = (PVACB_LD(2, PVACB_IDX(s0, 0)) & 0x000000ffu) | (PVACB_LD(3, PVACB_IDX(s1, 1)) & 0x0000ff00u) | (PVACB_LD(0, PVACB_IDX(s2, 2)) & 0x00ff0000u) | (PVACB_LD(1, PVACB_IDX(s3, 3)) & 0xff000000u);
+        uint32_t o1 = (PVACB_LD(2, PVACB_IDX(s1, 0)) & 0x000000ffu) | (PVACB_LD(3, PVACB_IDX(s2, 1)) & 0x0000ff00u) | (PVACB_LD(0, PVACB_IDX(s3, 2)) & 0x00ff0000u) | (PVACB_LD(1, PVACB_IDX(s0, 3)) & 0xff000000u);
+        uint32_t o2 = (PVACB_LD(2, PVACB_IDX(s2, 0)) & 0x000000ffu) | (PVACB_LD(3, PVACB_IDX(s3, 1)) & 0x0000ff00u) | (PVACB_LD(0, PVACB_IDX(s0, 2)) & 0x00ff0000u) | (PVACB_LD(1, PVACB_IDX(s1, 3)) & 0xff000000u);
+        uint32_t o3 = (PVACB_LD(2, PVACB_IDX(s3, 0)) & 0x000000ffu) | (PVACB_LD(3, PVACB_IDX(s0, 1)) & 0x0000ff00u) | (PVACB_LD(0, PVACB_IDX(s1, 2)) & 0x00ff0000u) | (PVACB_LD(1, PVACB_IDX(s2, 3)) & 0xff000000u);
+        o0 ^= rk[48]; o1 ^= rk[49]; o2 ^= rk[50]; o3 ^= rk[51];
+        w0 = (uint64_t)o0 | ((uint64_t)o1 << 32);
+        w1 = (uint64_t)o2 | ((uint64_t)o3 << 32);
+    }
+};
 #endif
 
 }  // namespace pvacb

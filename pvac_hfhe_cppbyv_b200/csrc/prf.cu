@@ -44,11 +44,11 @@ __global__ void __launch_bounds__(kLpnThreads, 1)
 prf_lpn_kernel(const uint32_t* __restrict__ gT0, const __grid_constant__ LpnSecret sec, uint64_t ncores, int rpc_log2,
                const uint32_t* __restrict__ rk_all, const uint64_t* __restrict__ ctr0_all, const uint8_t* __restrict__ flags,
                uint64_t* __restrict__ ybits, unsigned int* __restrict__ rare_flag) {
-    extern __shared__ uint32_t sT[];
+    extern __shared__ __align__(16) uint8_t sT[];
     aes_fill_rep_tables(sT, gT0);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const uint32_t* Tl = sT + lane;
+    const uint32_t lane4 = (uint32_t)lane * 4;
     const uint64_t slots = ncores << rpc_log2;
     const uint64_t units = (slots + kLpnThreads - 1) / kLpnThreads;
     const uint32_t rp_mask = (1u << rpc_log2) - 1;
@@ -61,16 +61,12 @@ prf_lpn_kernel(const uint32_t* __restrict__ gT0, const __grid_constant__ LpnSecr
         if (active && !(flags[core / 3] & 2)) active = false;   // warp-uniform: a core spans whole warps
         uint32_t ye = 0, yo = 0;
         if (active) {
-            uint32_t rk[60];
-            const uint4* rkp = reinterpret_cast<const uint4*>(rk_all + core * 60);
-#pragma unroll
-            for (int i = 0; i < 15; i++) {
-                uint4 v = __ldg(rkp + i);
-                rk[4 * i] = v.x; rk[4 * i + 1] = v.y; rk[4 * i + 2] = v.z; rk[4 * i + 3] = v.w;
-            }
+            AesCtrThread aes;
+            aes.load_keys(rk_all + core * 60);
             uint64_t ctr = __ldg(ctr0_all + core) + 65ull * rp;
+            aes.prime(sT, lane4, (uint32_t)(ctr >> 32));
             bool rare = false;
-            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) { aes_block_rep(Tl, rk, c, w0, w1); }, ctr, sec.w, ye, yo, rare);
+            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) { aes.block(sT, lane4, c, w0, w1); }, ctr, sec.w, ye, yo, rare);
             if (rare) atomicOr(rare_flag, 1u);
         }
         uint32_t be = __ballot_sync(0xffffffffu, ye);

@@ -8,7 +8,7 @@ reported in the same JSON line under "ops", each with its own roofline.
   step      = one pass of ct_mul over one tile of `--pairs` synthetic ciphertext pairs (default 4096 per GPU)
   value     = pairs/s, whole job, inputs resident in HBM, timed with CUDA events on the engine's stream, max over ranks
   e2e       = the same metric through the C ABI with HOST buffers: pinned host SoA -> H2D import, ct_mul, D2H export
-  roofline  = dominant kernel (sigma_gather_kernel): algorithmic L2 gather bytes / its CUDA-event time vs the measured
+  roofline  = dominant kernel (sigma_fused_kernel): algorithmic L2 gather bytes / its CUDA-event time vs the measured
               L2 gather ceiling of this GPU (pvacb_l2_gather_probe); ct_add's HBM roofline is under ops.ct_add
   cpu_baseline / --impl reference = the unmodified reference (oracle/_ref, built from /root/reference) on the host cores
 
@@ -31,6 +31,8 @@ if ROOT not in sys.path:
 P127 = (1 << 127) - 1
 EDGE_WIRE_BYTES = 1052          # serialised edge (tests/bounty2_test.cpp:98-106): the byte convention of SURVEY 8d
 GATHER_BYTES_PER_EDGE = 128 * 1024
+SHA_PER_EDGE = 70               # 2 midstates + 2 x 34 counter hashes (csrc/sigma.cu)
+SHA_ALU_INSTR = 1240            # SHF + LOP3 + IADD3 of one unrolled compression
 
 
 def mix64(z):
@@ -239,24 +241,28 @@ def main():
     eng.profile_enable(False)
     value = world * M * args.steps / secs
     edges_per_step = float(np.mean(out_edges)) if out_edges else 0.0
-    gather_ms, gather_launches = prof["sigma_gather"]
-    cand_ms, _ = prof["sigma_cand"]
+    gather_ms, gather_launches = prof["sigma"]
     gather_bytes = edges_per_step * args.steps * GATHER_BYTES_PER_EDGE
     achieved = gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
+    sha_rate = edges_per_step * args.steps * SHA_PER_EDGE / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
+    # second ceiling of the same kernel: the SHA-256 counter PRG on the ALU pipe (SHF/LOP3/IADD3: 64 lanes/clk/SM)
+    alu_peak = 148 * 64 * 1.965 / SHA_ALU_INSTR
     roofline = {
-        "kernel": "sigma_gather_kernel", "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
+        "kernel": "sigma_fused_kernel", "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
         "traffic": None,
-        "peak_source": "measured live: pvacb_l2_gather_probe (warp-wide 1 KiB gathers from the L2-resident 16 MiB matrix H)",
+        "peak_source": "measured live: pvacb_l2_gather_probe (warp-wide 1 KiB gathers from the L2-resident 16 MiB matrix H, nothing else running)",
         "algorithmic_bytes_per_launch": gather_bytes / max(gather_launches, 1), "launches": gather_launches,
         "kernel_ms_per_step": gather_ms / args.steps, "share_of_step": gather_ms * 1e-3 / secs,
         "hbm_write_gbs": edges_per_step * args.steps * 1024 / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0, "hbm_peak": hbm_peak, "hbm_peak_source": peak_src,
-        "other_kernels_ms_per_step": {"sigma_cand_kernel": cand_ms / args.steps},
+        "alu": {"achieved": sha_rate, "unit": "G SHA-256 compressions/s", "peak": alu_peak, "frac": sha_rate / alu_peak,
+                "peak_source": f"model: {SHA_ALU_INSTR} ALU-pipe instructions per compression (cuobjdump), 64 lanes/clk/SM, 148 SMs at 1965 MHz",
+                "compressions_per_edge": SHA_PER_EDGE},
     }
     ncu_path = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
     if os.path.exists(ncu_path):
         with open(ncu_path) as f:
             ncu = json.load(f)
-        per_edge = ncu.get("sigma_gather_kernel", {}).get("dram_bytes_per_edge")
+        per_edge = ncu.get("sigma_fused_kernel", {}).get("dram_bytes_per_edge")
         if per_edge is not None and gather_launches:
             roofline["traffic"] = per_edge * edges_per_step * args.steps / gather_launches
 

@@ -65,7 +65,7 @@ int pvacb_sync(pvacb_ctx* ctx);
 /* counters since the last reset: kernels launched, AES-256 blocks computed, sigma_from_H evaluations */
 void pvacb_stats(const pvacb_ctx* ctx, uint64_t* kernel_launches, uint64_t* aes_blocks, uint64_t* sigma_edges);
 void pvacb_stats_reset(pvacb_ctx* ctx);
-/* optional per-kernel timing with CUDA events on the context's stream. Tags: 0 prf_lpn, 1 sigma_cand, 2 sigma_gather,
+/* optional per-kernel timing with CUDA events on the context's stream. Tags: 0 prf_lpn, 1 unused, 2 sigma (fused sigma_from_H kernel),
  * 3 concat (ct_add/ct_sub), 4 dec_edges, 5 mul planning. collect() synchronises, sums ms and launch counts per tag. */
 int pvacb_profile_enable(pvacb_ctx* ctx, int on);
 /* microbenchmark: achieved GB/s of warp-wide 1 KiB gathers from the L2-resident matrix H (ceiling of the sigma kernel) */

@@ -14,7 +14,7 @@ n = 1024
 va, vb = rng.integers(0, 2**64, n, dtype=np.uint64), rng.integers(0, 2**64, n, dtype=np.uint64)
 X, Y = eng.enc_value(va, 2), eng.enc_value(vb, 3)
 for k in range(2):
-    P = eng.ct_mul(X, Y, 10 + k)        # sigma_cand_kernel + sigma_gather_kernel over ~1.2M edges
+    P = eng.ct_mul(X, Y, 10 + k)        # sigma_fused_kernel over ~1.2M edges
 d = eng.dec_value(P)
 assert all((int(d[i][0]) | (int(d[i][1]) << 64)) == int(va[i]) * int(vb[i]) % ((1 << 127) - 1) for i in range(n))
 SA, SB = eng.synthetic(1 << 14, 20, 5), eng.synthetic(1 << 14, 20, 6)

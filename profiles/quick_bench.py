@@ -44,8 +44,9 @@ if "sigma" in what:
         out = eng.sigma_from_H(z, lo, hi, idx, ch, salt)
         wall = time.perf_counter() - t0
         pr = eng.profile_collect()
-    print(f"sigma n={n}: cand {pr['sigma_cand'][0]:.2f} ms ({pr['sigma_cand'][0]*1e6/n:.2f} ns/edge), gather {pr['sigma_gather'][0]:.2f} ms "
-          f"({pr['sigma_gather'][0]*1e6/n:.2f} ns/edge, {n*131072/pr['sigma_gather'][0]/1e9:.2f} TB/s L2), wall {wall*1e3:.0f} ms", flush=True)
+    ms = pr['sigma'][0]
+    print(f"sigma cfg={os.environ.get('PVACB_SIGMA_CFG', '0')} n={n}: fused {ms:.2f} ms ({ms*1e6/n:.2f} ns/edge, {n*131072/ms/1e9:.2f} TB/s L2 gather, "
+          f"{n*68/ms/1e6:.2f} G SHA-256 compressions/s), wall {wall*1e3:.0f} ms", flush=True)
     print("l2 probe GB/s", eng.l2_gather_probe(3), flush=True)
 
 if "add" in what:

@@ -244,7 +244,7 @@ class Engine:
     def adopt_key_blob_from(self, device_ptr):
         self._ck(self.L.pvacb_keys_adopt_blob_from(self.h, device_ptr))
 
-    PROF_TAGS = ("prf_lpn", "sigma_cand", "sigma_gather", "concat", "dec_edges", "mul_plan", "t6", "t7")
+    PROF_TAGS = ("prf_lpn", "t1", "sigma", "concat", "dec_edges", "mul_plan", "t6", "t7")
 
     def l2_gather_probe(self, reps=5):
         g = C.c_double()

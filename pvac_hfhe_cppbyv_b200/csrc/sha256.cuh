@@ -18,15 +18,10 @@ namespace pvacb {
     0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, \
     0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, \
     0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2
-static const uint32_t h_shaK[64] = {PVACB_SHA_K_LIST};
-#if defined(__CUDACC__)
-static __device__ __constant__ uint32_t c_shaK[64] = {PVACB_SHA_K_LIST};
-#endif
-#if defined(__CUDA_ARCH__)
-#define PVACB_SHA_K(i) c_shaK[i]
-#else
-#define PVACB_SHA_K(i) h_shaK[i]
-#endif
+// round constants as compile-time immediates: the 64 rounds are fully unrolled, so K[i] folds into the IADD3 operand
+// (a __constant__ table made ptxas hoist 64 LDCs out of the hashing loop and spill them to local memory)
+#define PVACB_SHA_K_DECL constexpr uint32_t kShaK[64] = {PVACB_SHA_K_LIST}
+#define PVACB_SHA_K(i) kShaK[i]
 
 struct ShaState {
     uint32_t h[8];
@@ -54,6 +49,7 @@ PV_HD uint32_t sha_bswap(uint32_t x) {
 
 // one compression; w[16] = big-endian schedule words of the block (destroyed)
 PV_HD void sha_compress(ShaState& s, uint32_t w[16]) {
+    PVACB_SHA_K_DECL;
     uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
@@ -69,6 +65,29 @@ PV_HD void sha_compress(ShaState& s, uint32_t w[16]) {
     }
     s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
+
+// one compression starting from a parked state (e.g. a midstate in shared memory): out = compress(from, w). `from` is read
+// again for the final addition instead of being kept in registers across the 64 rounds.
+PV_HD void sha_compress_from(const uint32_t* from, uint32_t w[16], uint32_t out[8]) {
+    PVACB_SHA_K_DECL;
+    uint32_t a = from[0], b = from[1], c = from[2], d = from[3], e = from[4], f = from[5], g = from[6], h = from[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+            uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+            w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+        }
+        uint32_t t1 = h + (sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25)) + ((e & f) ^ (~e & g)) + PVACB_SHA_K(i) + w[i & 15];
+        uint32_t t2 = (sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    out[0] = from[0] + a; out[1] = from[1] + b; out[2] = from[2] + c; out[3] = from[3] + d;
+    out[4] = from[4] + e; out[5] = from[5] + f; out[6] = from[6] + g; out[7] = from[7] + h;
+}
+// LE64 of 8 big-endian digest bytes held as two state words (what load_le64(digest + 8k) returns)
+PV_HD uint64_t sha_le64_of(uint32_t h_even, uint32_t h_odd) { return (uint64_t)sha_bswap(h_even) | ((uint64_t)sha_bswap(h_odd) << 32); }
 
 // 8 little-endian stream words -> 16 big-endian schedule words
 PV_HD void sha_block_from_le64(const uint64_t q[8], uint32_t w[16]) {

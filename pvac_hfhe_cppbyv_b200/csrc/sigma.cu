@@ -1,22 +1,27 @@
 // sigma_from_H (crypto/matrix.hpp:267-303) for arrays of edges: the hot kernel of ct_mul and 40 calls per enc_value.
 //
-//   sigma_cand_kernel    SHA-256 counter PRG of prg_choose_k (matrix.hpp:15-92): one thread per (source, label, ctr),
-//                        block 0 of the 78/79-byte message is constant per (source, label) -> midstate in shared memory,
-//                        one compression per thread, 4 candidates per hash. 34 hashes (136 candidates) per label cover
-//                        the 128 picks plus up to 8 duplicates; the gather kernel continues the stream if that is short.
-//   sigma_gather_kernel  one warp per destination edge: ordered de-duplication with a bitmap in shared memory
-//                        (first 128 distinct values in stream order = what the unordered_set loop accepts), XOR-gather of
-//                        the 128 chosen 1 KiB columns of H (16 MiB, L2 resident) with 128-bit loads, noise flips taken
-//                        straight from the noise bitmap, 1 KiB coalesced store.
+// ONE fused kernel, one warp per group of G edges, no CTA-wide barrier. Each warp runs three phases per group:
+//   A  midstates   prg_choose_k (matrix.hpp:15-92) hashes  label || 7 words || LE64(ctr): block 0 of that 78/79-byte message is
+//                  constant per (edge, label), so 2G lanes compress it once and park the SHA-256 midstate in shared memory;
+//   B  candidates  the G*68 counter hashes (34 per label = 136 candidates: the 128 picks plus up to 8 duplicates) are dealt
+//                  round-robin to the 32 lanes, one compression each (block 1 = tail of the salt, ctr, padding); the accepted
+//                  16-bit candidates go to shared memory. G = 8 makes that exactly 17 full rounds;
+//   C  gather      per edge: ordered de-duplication with a bitmap in shared memory (first 128 distinct values in stream order
+//                  = what the reference's unordered_set loop accepts, continuing the stream in the rare short case), XOR-
+//                  gather of the 128 chosen 1 KiB columns of H (16 MiB, L2 resident) with 128-bit loads, noise flips taken
+//                  straight from the noise bitmap, one coalesced 1 KiB store.
+// Phases A/B are ALU-pipe work (SHF/LOP3/IADD3), phase C is L2->SM bandwidth; warps of one SM drift apart, so the hashing
+// of some warps hides under the gathers of the others. (r01: as two kernels, candidates through HBM, the same work took
+// 47.7 ms + 31.9 ms per 4.96 M edges; half of the first was a one-lane-per-warp midstate phase.)
 #include "engine.h"
 #include "sha256.cuh"
+
+#include <cstdlib>
 
 namespace pvacb {
 
 constexpr int kCandHashes = 34;
 constexpr int kCandPerLabel = kCandHashes * 4;  // 136
-constexpr int kCandSrcPerCta = 4;
-constexpr int kCandThreads = kCandSrcPerCta * 2 * kCandHashes;  // 272
 
 // candidate value of one PRG word: accept iff x <= 2^64-1 - ((2^64-1) % N) (matrix.hpp:64-75; N is a power of two here)
 PV_HD uint16_t cand_from_word(uint64_t x, uint32_t N) {
@@ -37,59 +42,6 @@ __device__ __forceinline__ void load_words(const SigmaJobs& J, uint64_t canon, u
     x[7] = 0;
 }
 
-__global__ void __launch_bounds__(kCandThreads)
-sigma_cand_kernel(SigmaJobs J, uint64_t canon, uint16_t* __restrict__ cand) {
-    __shared__ uint32_t mid[kCandSrcPerCta * 2][8];
-    __shared__ uint64_t tailw[kCandSrcPerCta * 2];   // x[6] (salt), needed for block 1
-    const int tid = threadIdx.x;
-    const int sl = tid / kCandHashes;        // 0..7 : (source local, label)
-    const int ctr = tid % kCandHashes;
-    const int label = sl & 1;
-    const uint64_t src = (uint64_t)blockIdx.x * kCandSrcPerCta + (sl >> 1);
-    const bool valid = src < J.n;
-    const LabelStream ls = label ? label_noise() : label_xseed();
-    if (ctr == 0 && valid) {
-        uint64_t x[8];
-        load_words(J, canon, src, x);
-        uint64_t q[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) q[j] = stream_word(ls, x, 8, j, 0x80ull);
-        uint32_t w[16];
-        sha_block_from_le64(q, w);
-        ShaState st;
-        sha_init(st);
-        sha_compress(st, w);
-#pragma unroll
-        for (int i = 0; i < 8; i++) mid[sl][i] = st.h[i];
-        tailw[sl] = x[6];
-    }
-    __syncthreads();
-    if (!valid) return;
-    // block 1: remaining bytes of the salt, LE64(ctr), 0x80, zeros, bit length
-    const int sh = 8 * ls.r;
-    uint64_t salt = tailw[sl];
-    uint64_t c = (uint64_t)ctr;
-    uint64_t q8 = (salt >> (64 - sh)) | (c << sh);
-    uint64_t q9 = (c >> (64 - sh)) | (0x80ull << sh);
-    uint32_t w[16];
-    w[0] = sha_bswap((uint32_t)q8); w[1] = sha_bswap((uint32_t)(q8 >> 32));
-    w[2] = sha_bswap((uint32_t)q9); w[3] = sha_bswap((uint32_t)(q9 >> 32));
-#pragma unroll
-    for (int i = 4; i < 15; i++) w[i] = 0;
-    w[15] = (uint32_t)(8 + ls.r + 64) * 8;  // message bytes = label + 8 words
-    ShaState st;
-#pragma unroll
-    for (int i = 0; i < 8; i++) st.h[i] = mid[sl][i];
-    sha_compress(st, w);
-    const uint32_t N = label ? (uint32_t)kMBits : (uint32_t)kNBits;
-    uint16_t v0 = cand_from_word(sha_digest_le64(st, 0), N), v1 = cand_from_word(sha_digest_le64(st, 1), N);
-    uint16_t v2 = cand_from_word(sha_digest_le64(st, 2), N), v3 = cand_from_word(sha_digest_le64(st, 3), N);
-    uint2 pk;
-    pk.x = (uint32_t)v0 | ((uint32_t)v1 << 16);
-    pk.y = (uint32_t)v2 | ((uint32_t)v3 << 16);
-    reinterpret_cast<uint2*>(cand + (src * 2 + label) * kCandPerLabel)[ctr] = pk;
-}
-
 // slow path: hash number `ctr` of the stream, both blocks (used only when 136 candidates were not enough)
 __device__ __noinline__ void prg_hash_words(const LabelStream ls, const uint64_t xin[8], uint64_t ctr, uint64_t out[4]) {
     uint64_t x[8];
@@ -100,18 +52,22 @@ __device__ __noinline__ void prg_hash_words(const LabelStream ls, const uint64_t
     for (int k = 0; k < 4; k++) out[k] = sha_digest_le64(st, k);
 }
 
-constexpr int kGatherWarps = 8;
-struct GatherSmem {
-    uint32_t bmX[kNBits / 32];     // 2 KiB: seen columns
-    uint32_t bmN[kMBits / 32];     // 1 KiB: noise bits (doubles as the flip mask)
-    uint16_t cols[kXColWt];        // chosen columns
-    uint16_t more[128];            // continuation candidates
+template <int G>
+struct __align__(16) SigmaWarpSmem {
+    uint32_t bm[kNBits / 32];               // 2 KiB: de-dup bitmap of the columns, then of the noise bits (= the flip mask)
+    uint16_t cols[kXColWt];                 // chosen columns, in draw order
+    uint16_t cand[G * 2 * kCandPerLabel];   // phase B output: [edge][label][136]
+    union {
+        uint32_t mid[G * 2][8];             // phase A output: SHA-256 state after block 0, per (edge, label)
+        uint16_t more[128];                 // phase C, rare: continuation candidates
+    };
+    uint64_t salt[G < 4 ? 4 : G];           // word 6 of the hashed words: its tail opens block 1
 };
 
-// ordered de-duplication of one label. Lanes hold candidates 4*lane..4*lane+3 (c[]), positions 128..135 are in gc[128..].
-// Returns with exactly `want` distinct values marked in bm; winners are appended to cols (if cols != nullptr).
-__device__ __forceinline__ void dedupe_label(uint32_t* bm, uint16_t* cols, uint16_t* more, const uint16_t* __restrict__ gc, const LabelStream ls,
-                                             const uint64_t x[8], uint32_t N, int lane) {
+// ordered de-duplication of one label. Lanes hold candidates 4*lane..4*lane+3, positions 128..135 follow in gc[128..].
+// Returns with exactly 128 distinct values marked in bm (x_col_wt = err_wt = 128); winners are appended to cols if given.
+__device__ __forceinline__ void dedupe_label(uint32_t* bm, uint16_t* cols, uint16_t* more, const uint16_t* gc, const LabelStream ls,
+                                             const SigmaJobs& J, uint64_t canon, uint64_t job, uint32_t N, int lane) {
     uint2 pk = reinterpret_cast<const uint2*>(gc)[lane];
     uint16_t c[4] = {(uint16_t)(pk.x & 0xffff), (uint16_t)(pk.x >> 16), (uint16_t)(pk.y & 0xffff), (uint16_t)(pk.y >> 16)};
     int have = 0;
@@ -127,14 +83,17 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint16_t* cols, uint1
         if (win && cols) cols[have + __popc(b & ((1u << lane) - 1))] = c[k];
         have += __popc(b);
     }
-    if (have < kXColWt) {   // both labels want 128 picks (x_col_wt = err_wt = 128)
+    if (have < kXColWt) {
         // sequential tail, exactly like the reference's one-word-at-a-time loop
         int pos = 128;
         uint64_t next_ctr = kCandHashes;
         const uint16_t* cur = gc;
         int cur_base = 0, cur_end = kCandPerLabel;
+        uint64_t x[8];
+        bool have_x = false;
         while (have < kXColWt) {
             if (pos >= cur_end) {   // continue the PRG stream: 32 more hashes, one per lane
+                if (!have_x) { load_words(J, canon, job, x); have_x = true; }
                 uint64_t o[4];
                 prg_hash_words(ls, x, next_ctr + lane, o);
                 for (int k = 0; k < 4; k++) more[4 * lane + k] = cand_from_word(o[k], N);
@@ -163,56 +122,105 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint16_t* cols, uint1
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kGatherWarps * 32)
-sigma_gather_kernel(SigmaJobs J, uint64_t canon, const uint16_t* __restrict__ cand, const uint4* __restrict__ H4) {
-    __shared__ GatherSmem sm[kGatherWarps];
+template <int G, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4) {
+    extern __shared__ __align__(16) uint8_t sigma_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    GatherSmem& S = sm[wid];
-    for (int i = lane; i < kNBits / 32; i += 32) S.bmX[i] = 0;
-    for (int i = lane; i < kMBits / 32; i += 32) S.bmN[i] = 0;
+    SigmaWarpSmem<G>& S = reinterpret_cast<SigmaWarpSmem<G>*>(sigma_smem)[wid];
+    for (int i = lane; i < kNBits / 32; i += 32) S.bm[i] = 0;
     __syncwarp();
-    const uint64_t nwarps = (uint64_t)gridDim.x * kGatherWarps;
-    for (uint64_t job = (uint64_t)blockIdx.x * kGatherWarps + wid; job < J.n; job += nwarps) {
-        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
-        uint64_t x[8];
-        load_words(J, canon, job, x);
-        const uint16_t* gc = cand + job * 2 * kCandPerLabel;
-        // ---- columns of H
-        dedupe_label(S.bmX, S.cols, S.more, gc, label_xseed(), x, (uint32_t)kNBits, lane);
-#pragma unroll 1
-        for (int i = 0; i < kXColWt; i += 8) {
-            uint4 cv = *reinterpret_cast<const uint4*>(&S.cols[i]);   // 8 column ids, broadcast
-            uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
-            uint4 v[16];
+    const uint64_t ngroups = (J.n + G - 1) / G;
+    const uint64_t nwarps = (uint64_t)gridDim.x * WARPS;
+    for (uint64_t grp = (uint64_t)blockIdx.x * WARPS + wid; grp < ngroups; grp += nwarps) {
+        const uint64_t job0 = grp * G;
+        const int ng = (int)(J.n - job0 < (uint64_t)G ? J.n - job0 : (uint64_t)G);
+        // ---- phase A: midstate of block 0 for (edge, label) = (lane >> 1, lane & 1)
+        if (lane < 2 * ng) {
+            const LabelStream ls = (lane & 1) ? label_noise() : label_xseed();
+            uint64_t x[8];
+            load_words(J, canon, job0 + (lane >> 1), x);
+            uint64_t q[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                uint32_t col = (cw[k >> 1] >> ((k & 1) * 16)) & 0xffff;
-                const uint4* p = H4 + (size_t)col * 64 + lane;
-                v[2 * k] = __ldcg(p);
-                v[2 * k + 1] = __ldcg(p + 32);
-            }
+            for (int j = 0; j < 8; j++) q[j] = stream_word(ls, x, 8, j, 0x80ull);
+            uint32_t w[16];
+            sha_block_from_le64(q, w);
+            ShaState st;
+            sha_init(st);
+            sha_compress(st, w);
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
-                a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
-            }
+            for (int i = 0; i < 8; i++) S.mid[lane][i] = st.h[i];
+            if (!(lane & 1)) S.salt[lane >> 1] = x[6];
         }
-        // clear the column bitmap again: every word that got a bit belongs to one of the chosen columns
-        for (int i = lane; i < kXColWt; i += 32) S.bmX[S.cols[i] >> 5] = 0;
         __syncwarp();
-        // ---- noise bits: the de-dup bitmap is the flip mask
-        dedupe_label(S.bmN, nullptr, S.more, gc + kCandPerLabel, label_noise(), x, (uint32_t)kMBits, lane);
-        uint4* bn = reinterpret_cast<uint4*>(S.bmN);
-        uint4 n0 = bn[lane], n1 = bn[lane + 32];
-        a0.x ^= n0.x; a0.y ^= n0.y; a0.z ^= n0.z; a0.w ^= n0.w;
-        a1.x ^= n1.x; a1.y ^= n1.y; a1.z ^= n1.z; a1.w ^= n1.w;
-        bn[lane] = make_uint4(0, 0, 0, 0);
-        bn[lane + 32] = make_uint4(0, 0, 0, 0);
+        // ---- phase B: hash h = (edge, label, ctr), one compression: block 1 = tail of the salt, LE64(ctr), 0x80, bit length
+        const int nh = ng * 2 * kCandHashes;
+        for (int h = lane; h < nh; h += 32) {
+            const int sl = h / kCandHashes;          // edge * 2 + label
+            const uint32_t ctr = (uint32_t)(h - sl * kCandHashes);
+            const int label = sl & 1;
+            const int sh = label ? 48 : 56;          // 8 * (label length - 8)
+            const uint64_t q8 = (S.salt[sl >> 1] >> (64 - sh)) | ((uint64_t)ctr << sh);
+            uint32_t w[16];
+            w[0] = sha_bswap((uint32_t)q8);
+            w[1] = sha_bswap((uint32_t)(q8 >> 32));
+            w[2] = 0;                                 // ctr < 2^8: the upper counter bytes are zero
+            w[3] = label ? 0x00008000u : 0x00000080u; // the 0x80 terminator right after the counter
+#pragma unroll
+            for (int i = 4; i < 15; i++) w[i] = 0;
+            w[15] = label ? 78u * 8u : 79u * 8u;
+            uint32_t d[8];
+            sha_compress_from(S.mid[sl], w, d);
+            const uint32_t N = label ? (uint32_t)kMBits : (uint32_t)kNBits;
+            uint2 pk;
+            pk.x = (uint32_t)cand_from_word(sha_le64_of(d[0], d[1]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[2], d[3]), N) << 16);
+            pk.y = (uint32_t)cand_from_word(sha_le64_of(d[4], d[5]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[6], d[7]), N) << 16);
+            reinterpret_cast<uint2*>(S.cand + sl * kCandPerLabel)[ctr] = pk;
+        }
         __syncwarp();
-        uint64_t row = J.out_row ? J.out_row[job] : job;
-        uint4* o = reinterpret_cast<uint4*>(row < J.out_split ? J.out + row * kMWords : J.out2 + (row - J.out_split) * kMWords);
-        o[lane] = a0;
-        o[lane + 32] = a1;
+        // ---- phase C: de-duplicate, gather, flip, store
+#pragma unroll 1
+        for (int e = 0; e < ng; e++) {
+            const uint64_t job = job0 + e;
+            const uint16_t* gc = S.cand + e * 2 * kCandPerLabel;
+            dedupe_label(S.bm, S.cols, S.more, gc, label_xseed(), J, canon, job, (uint32_t)kNBits, lane);
+            // clear the bitmap again: every word that got a bit belongs to one of the chosen columns
+            for (int i = lane; i < kXColWt; i += 32) S.bm[S.cols[i] >> 5] = 0;
+            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+            for (int i = 0; i < kXColWt; i += 8) {
+                uint4 cv = *reinterpret_cast<const uint4*>(&S.cols[i]);   // 8 column ids, broadcast
+                uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+                uint4 v[16];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    uint32_t col = (cw[k >> 1] >> ((k & 1) * 16)) & 0xffff;
+                    const uint4* p = H4 + (size_t)col * 64 + lane;
+                    v[2 * k] = __ldcg(p);
+                    v[2 * k + 1] = __ldcg(p + 32);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
+                    a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
+                }
+            }
+            __syncwarp();
+            // noise bits: the de-dup bitmap is the flip mask (values < 8192: the first KiB of bm)
+            dedupe_label(S.bm, nullptr, S.more, gc + kCandPerLabel, label_noise(), J, canon, job, (uint32_t)kMBits, lane);
+            uint4* bn = reinterpret_cast<uint4*>(S.bm);
+            uint4 n0 = bn[lane], n1 = bn[lane + 32];
+            a0.x ^= n0.x; a0.y ^= n0.y; a0.z ^= n0.z; a0.w ^= n0.w;
+            a1.x ^= n1.x; a1.y ^= n1.y; a1.z ^= n1.z; a1.w ^= n1.w;
+            bn[lane] = make_uint4(0, 0, 0, 0);
+            bn[lane + 32] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            uint64_t row = J.out_row ? J.out_row[job] : job;
+            uint4* o = reinterpret_cast<uint4*>(row < J.out_split ? J.out + row * kMWords : J.out2 + (row - J.out_split) * kMWords);
+            __stcs(o + lane, a0);        // streaming store: the 1 KiB rows are write-once, keep L2 for H
+            __stcs(o + lane + 32, a1);
+        }
+        __syncwarp();
     }
 }
 
@@ -237,37 +245,50 @@ int sigma_xor_rows(Ctx* ctx, uint64_t npairs, const uint2* d_pairs, uint64_t* ou
     return PV_OK;
 }
 
+template <int G, int WARPS, int MINB>
+static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
+    auto kern = sigma_fused_kernel<G, WARPS, MINB>;
+    constexpr int smem = (int)sizeof(SigmaWarpSmem<G>) * WARPS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_done = true;
+    }
+    const uint64_t ngroups = (J.n + G - 1) / G;
+    uint64_t grid = (ngroups + WARPS - 1) / WARPS;
+    const uint64_t cap = (uint64_t)ctx->sm_count * MINB;     // persistent: every resident warp walks groups round-robin
+    if (grid > cap) grid = cap;
+    ProfScope ps(ctx, PROF_SIGMA);
+    kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(J, ctx->kv.canon_tag, reinterpret_cast<const uint4*>(ctx->kv.H));
+    return PV_OK;
+}
+
 int sigma_run(Ctx* ctx, const SigmaJobs& J) {
     if (J.n == 0) return PV_OK;
-    uint16_t* cand = nullptr;
     int rc;
-    // candidates are produced in chunks to bound scratch memory (544 B per job)
-    const uint64_t chunk = 1ull << 22;
-    uint64_t max_n = J.n < chunk ? J.n : chunk;
-    if ((rc = dev_alloc(ctx, (void**)&cand, max_n * 2 * kCandPerLabel * 2))) return rc;
-    for (uint64_t s0 = 0; s0 < J.n; s0 += chunk) {
-        uint64_t ns = J.n - s0 < chunk ? J.n - s0 : chunk;
-        SigmaJobs S = J;
-        S.n = ns;
-        if (S.seed_idx) S.seed_idx += s0; else { S.ztag += s0; S.nlo += s0; S.nhi += s0; }
-        S.idx += s0; S.ch += s0; S.salt += s0;
-        if (S.out_row) S.out_row += s0; else S.out += s0 * kMWords;
-        {
-            ProfScope ps(ctx, PROF_SIGMA_CAND);
-            sigma_cand_kernel<<<(unsigned)((ns + kCandSrcPerCta - 1) / kCandSrcPerCta), kCandThreads, 0, ctx->stream>>>(S, ctx->kv.canon_tag, cand);
-        }
-        unsigned grid = (unsigned)((ns + kGatherWarps - 1) / kGatherWarps);
-        unsigned cap = (unsigned)ctx->sm_count * 8;
-        if (grid > cap) grid = cap;
-        {
-            ProfScope ps(ctx, PROF_SIGMA_GATHER);
-            sigma_gather_kernel<<<grid, kGatherWarps * 32, 0, ctx->stream>>>(S, ctx->kv.canon_tag, cand, reinterpret_cast<const uint4*>(ctx->kv.H));
-        }
-        PV_CUDA(cudaGetLastError());
-        ctx->stat_kernel_launches += 2;
+    // shape (G edges per warp-group, warps per CTA, CTAs per SM). G*68 hashes should fill whole 32-lane rounds (G = 8: 17
+    // rounds exactly); shared memory per warp = 2304 + 616 G bytes bounds the resident warps. PVACB_SIGMA_CFG picks another
+    // compiled shape for tuning runs. Small batches use groups of 2 edges so that more warps (and SMs) take part.
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = getenv("PVACB_SIGMA_CFG");
+        cfg = e ? atoi(e) : 0;
     }
+    if (J.n < (uint64_t)ctx->sm_count * 7 * 4 * 8) rc = sigma_launch<2, 4, 8>(ctx, J);
+    else switch (cfg) {
+        default: rc = sigma_launch<8, 4, 7>(ctx, J); break;
+        case 1: rc = sigma_launch<7, 4, 8>(ctx, J); break;
+        case 2: rc = sigma_launch<8, 8, 3>(ctx, J); break;
+        case 3: rc = sigma_launch<4, 4, 8>(ctx, J); break;
+        case 4: rc = sigma_launch<8, 4, 6>(ctx, J); break;
+        case 5: rc = sigma_launch<8, 4, 5>(ctx, J); break;
+        case 6: rc = sigma_launch<6, 4, 8>(ctx, J); break;
+    }
+    if (rc) return rc;
+    PV_CUDA(cudaGetLastError());
+    ctx->stat_kernel_launches += 1;
     ctx->stat_sigma_edges += J.n;
-    dev_free(ctx, cand);
     return PV_OK;
 }
 

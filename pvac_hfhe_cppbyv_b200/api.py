@@ -40,6 +40,7 @@ SYMBOLS = [
     "pvacb_batch_slice", "pvacb_batch_export_soa", "pvacb_batch_import_soa", "pvacb_batch_wire_size", "pvacb_batch_export_wire",
     "pvacb_batch_import_wire", "pvacb_batch_synthetic", "pvacb_prf", "pvacb_sigma_from_H", "pvacb_fp_op",
     "pvacb_profile_enable", "pvacb_profile_collect", "pvacb_keys_copy_blob_to", "pvacb_keys_adopt_blob_from", "pvacb_l2_gather_probe",
+    "pvacb_batch_export_soa_async", "pvacb_export_wait",
 ]
 
 
@@ -106,6 +107,8 @@ def load_library():
         "pvacb_keys_copy_blob_to": (i32, [vp, vp]),
         "pvacb_keys_adopt_blob_from": (i32, [vp, vp]),
         "pvacb_l2_gather_probe": (i32, [vp, i32, P(C.c_double)]),
+        "pvacb_batch_export_soa_async": (i32, [vp, vp, P(u32), P(u32), P(u8), P(u64), P(u64), P(u64), P(u32), P(u32), P(u32), P(u16), P(u8), P(u64), P(u64)]),
+        "pvacb_export_wait": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -324,6 +327,31 @@ class Engine:
             _p(d["nlo"], C.c_uint64), _p(d["nhi"], C.c_uint64), _p(d["pa"], C.c_uint32), _p(d["pb"], C.c_uint32), _p(d["lid"], C.c_uint32),
             _p(d["idx"], C.c_uint16), _p(d["ch"], C.c_uint8), _p(d["w"], C.c_uint64), _p(d["sigma"], C.c_uint64) if with_sigma else None))
         return d
+
+    def export_soa_async(self, b, bufs):
+        """queue the device->host copies of batch b into the (pinned, large enough) arrays of `bufs` and return at once;
+        call export_wait() before reading them or freeing b. -> dict of views trimmed to the batch's sizes."""
+        n = len(b)
+        nL, nE = b.totals()
+        sizes = dict(loff=n + 1, eoff=n + 1, rule=nL, ztag=nL, nlo=nL, nhi=nL, pa=nL, pb=nL, lid=nE, idx=nE, ch=nE, w=nE, sigma=nE)
+        d = {}
+        for k, cnt in sizes.items():
+            a = bufs.get(k)
+            if a is None:
+                d[k] = None
+                continue
+            if len(a) < cnt:
+                raise PvacbError(1, f"export buffer {k} too small: {len(a)} < {cnt}")
+            d[k] = a[:cnt]
+        ptr = lambda k, t: _p(d[k], t) if d[k] is not None else None
+        self._ck(self.L.pvacb_batch_export_soa_async(
+            self.h, b.h, ptr("loff", C.c_uint32), ptr("eoff", C.c_uint32), ptr("rule", C.c_uint8), ptr("ztag", C.c_uint64), ptr("nlo", C.c_uint64),
+            ptr("nhi", C.c_uint64), ptr("pa", C.c_uint32), ptr("pb", C.c_uint32), ptr("lid", C.c_uint32), ptr("idx", C.c_uint16), ptr("ch", C.c_uint8),
+            ptr("w", C.c_uint64), ptr("sigma", C.c_uint64)))
+        return d
+
+    def export_wait(self):
+        self._ck(self.L.pvacb_export_wait(self.h))
 
     def import_soa(self, d):
         n = len(d["loff"]) - 1

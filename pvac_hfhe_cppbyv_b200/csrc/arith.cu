@@ -122,8 +122,7 @@ int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode, Batch** out) {
     PV_CUDA(cudaGetLastError());
     ctx->stat_kernel_launches += n ? 2 : 1;
     unsigned int h_err = 0;
-    PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
     dev_free(ctx, err);
     if (h_err) {
         batch_free(o);
@@ -266,8 +265,7 @@ int compact_layers_batch(Ctx* ctx, Batch* b) {
     layers_mark_kernel<<<(unsigned)b->n, 128, 0, ctx->stream>>>(b->n, b->loff, b->eoff, b->rule, b->pa, b->pb, b->lid, used, cnt, nullptr);
     if ((rc = scan_u32(ctx, b->n, cnt, noff))) return rc;
     uint32_t total = 0;
-    PV_CUDA(cudaMemcpyAsync(&total, noff + b->n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    { SmallRead sr; sr.add(&total, noff + b->n, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
     ctx->stat_kernel_launches += 1;
     if (total != b->nL) {
         uint32_t* remap = nullptr;

@@ -127,9 +127,7 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     if ((rc = scan_u32(ctx, n, cnt, eoff))) return rc;
     if ((rc = scan_u32(ctx, n, xcnt, xoff))) return rc;
     uint32_t tot[2] = {0, 0};
-    PV_CUDA(cudaMemcpyAsync(&tot[0], eoff + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(&tot[1], xoff + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    { SmallRead sr; sr.add(&tot[0], eoff + n, 4); sr.add(&tot[1], xoff + n, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
     ctx->stat_kernel_launches += 1;
     const uint64_t nE = tot[0], nX = tot[1];
 
@@ -166,8 +164,7 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     if ((rc = sigma_run(ctx, J))) { batch_free(b); return rc; }
     if ((rc = sigma_xor_rows(ctx, nX, fix, b->sigma, nE, tmp_rows))) { batch_free(b); return rc; }
     unsigned int h_err = 0;
-    PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) { batch_free(b); return rc; } }
     dev_free(ctx, d_vals); dev_free(ctx, d_states); dev_free(ctx, plans); dev_free(ctx, cnt); dev_free(ctx, xcnt); dev_free(ctx, eoff); dev_free(ctx, xoff);
     dev_free(ctx, j_ztag); dev_free(ctx, j_nlo); dev_free(ctx, j_nhi); dev_free(ctx, j_flags); dev_free(ctx, prf);
     dev_free(ctx, s_seed); dev_free(ctx, s_row); dev_free(ctx, s_idx); dev_free(ctx, s_ch); dev_free(ctx, s_salt); dev_free(ctx, fix);

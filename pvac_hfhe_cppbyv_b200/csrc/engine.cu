@@ -31,6 +31,27 @@ void dev_free(Ctx* ctx, void* p) {
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+struct SmallReadArgs { const uint32_t* src[SmallRead::kMaxItems]; uint32_t words[SmallRead::kMaxItems]; int n; };
+__global__ void small_read_kernel(SmallReadArgs a, volatile uint32_t* mail) {
+    int o = 0;
+    for (int i = 0; i < a.n; i++)
+        for (uint32_t k = 0; k < a.words[i]; k++) mail[o++] = a.src[i][k];
+    __threadfence_system();
+}
+int read_small_sync(Ctx* ctx, const SmallRead& r) {
+    SmallReadArgs a;
+    a.n = r.n;
+    uint32_t total = 0;
+    for (int i = 0; i < r.n; i++) { a.src[i] = r.src[i]; a.words[i] = r.words[i]; total += r.words[i]; }
+    if (r.n > SmallRead::kMaxItems || total > (uint32_t)SmallRead::kMaxWords) { ctx->last_error = "read_small_sync: too many words"; return PV_E_ARG; }
+    small_read_kernel<<<1, 1, 0, ctx->stream>>>(a, ctx->d_mail);
+    PV_CUDA(cudaGetLastError());
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint32_t o = 0;
+    for (int i = 0; i < r.n; i++) { memcpy(r.dst[i], ctx->h_mail + o, r.words[i] * 4); o += r.words[i]; }
+    return PV_OK;
+}
+
 int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out) {
     Batch* b = new Batch();
     b->ctx = ctx; b->n = n; b->nL = nL; b->nE = nE;
@@ -151,6 +172,9 @@ int pvacb_ctx_create(int device, pvacb_ctx** out) {
     ctx->n_primes = (int)primes.size();
     cudaMalloc((void**)&ctx->d_primes, primes.size() * 8);
     cudaMemcpy(ctx->d_primes, primes.data(), primes.size() * 8, cudaMemcpyHostToDevice);
+    cudaMalloc((void**)&ctx->d_work, 64);
+    if (cudaHostAlloc((void**)&ctx->h_mail, SmallRead::kMaxWords * 4, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->d_mail, ctx->h_mail, 0) != cudaSuccess) { delete ctx; return PV_E_CUDA; }
     *out = reinterpret_cast<pvacb_ctx*>(ctx);
     return PV_OK;
 }
@@ -163,6 +187,8 @@ void pvacb_ctx_destroy(pvacb_ctx* x) {
     cudaFree(ctx->d_blob);
     cudaFree(ctx->d_aes);
     cudaFree(ctx->d_primes);
+    cudaFree(ctx->d_work);
+    if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
@@ -393,6 +419,47 @@ int pvacb_batch_export_soa(pvacb_ctx* x, const pvacb_batch* pb, uint32_t* loff, 
     PV_CUDA(cp(w, b->w, b->nE * 16));
     PV_CUDA(cp(sigma, b->sigma, b->nE * (size_t)kMWords * 8));
     PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PV_OK;
+}
+
+// Same copies on the context's second stream, ordered after everything already queued on the compute stream; returns at
+// once. The caller keeps the batch and the (pinned) destination buffers alive until pvacb_export_wait() returns. This is
+// what lets the 1.3 MB-per-product device->host read of step k overlap the compute of step k+1.
+int pvacb_batch_export_soa_async(pvacb_ctx* x, const pvacb_batch* pb, uint32_t* loff, uint32_t* eoff, uint8_t* rule, uint64_t* ztag,
+                                 uint64_t* nlo, uint64_t* nhi, uint32_t* pa, uint32_t* pbb, uint32_t* lid, uint16_t* idx, uint8_t* ch,
+                                 uint64_t* w, uint64_t* sigma) {
+    Ctx* ctx = C(x);
+    const Batch* b = Bt(pb);
+    cudaSetDevice(ctx->device);
+    cudaEvent_t ready;
+    PV_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    PV_CUDA(cudaEventRecord(ready, ctx->stream));
+    PV_CUDA(cudaStreamWaitEvent(ctx->stream2, ready, 0));
+    cudaEventDestroy(ready);
+    auto cp = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (!dst || !bytes) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream2);
+    };
+    PV_CUDA(cp(loff, b->loff, (b->n + 1) * 4));
+    PV_CUDA(cp(eoff, b->eoff, (b->n + 1) * 4));
+    PV_CUDA(cp(rule, b->rule, b->nL));
+    PV_CUDA(cp(ztag, b->ztag, b->nL * 8));
+    PV_CUDA(cp(nlo, b->nlo, b->nL * 8));
+    PV_CUDA(cp(nhi, b->nhi, b->nL * 8));
+    PV_CUDA(cp(pa, b->pa, b->nL * 4));
+    PV_CUDA(cp(pbb, b->pb, b->nL * 4));
+    PV_CUDA(cp(lid, b->lid, b->nE * 4));
+    PV_CUDA(cp(idx, b->idx, b->nE * 2));
+    PV_CUDA(cp(ch, b->ch, b->nE));
+    PV_CUDA(cp(w, b->w, b->nE * 16));
+    PV_CUDA(cp(sigma, b->sigma, b->nE * (size_t)kMWords * 8));
+    return PV_OK;
+}
+
+int pvacb_export_wait(pvacb_ctx* x) {
+    Ctx* ctx = C(x);
+    cudaSetDevice(ctx->device);
+    PV_CUDA(cudaStreamSynchronize(ctx->stream2));
     return PV_OK;
 }
 

@@ -51,6 +51,9 @@ struct Ctx {
     AesTables* d_aes = nullptr;
     uint64_t* d_primes = nullptr;    // libstdc++ bucket-count table
     int n_primes = 0;
+    unsigned long long* d_work = nullptr;   // work-queue counter of the persistent sigma kernel
+    uint32_t* h_mail = nullptr;             // mapped pinned "mailbox": kernels drop small results here (see SmallRead)
+    uint32_t* d_mail = nullptr;             // device alias of h_mail
     KeyView kv{};
     LpnSecret lpn_s{};
     std::vector<uint64_t> h_hdr;     // host copy of the blob header
@@ -124,6 +127,22 @@ enum : int {
             return (_e == cudaErrorMemoryAllocation) ? PV_E_OOM : PV_E_CUDA;                \
         }                                                                                   \
     } while (0)
+
+// Small device->host reads (counts, totals, error flags) that the host needs before it can size the next allocation.
+// They do NOT use cudaMemcpy: a 4-byte copy shares the device->host copy engine with bulk exports running on the second
+// stream (pvacb_batch_export_soa_async) and would sit behind hundreds of MB. One single-thread kernel writes the words
+// into mapped pinned memory instead, then the compute stream is synchronised.
+struct SmallRead {
+    static constexpr int kMaxItems = 12, kMaxWords = 48;
+    const uint32_t* src[kMaxItems];
+    uint32_t words[kMaxItems];
+    void* dst[kMaxItems];
+    int n = 0;
+    void add(void* host_dst, const void* dev_src, size_t bytes) {
+        src[n] = static_cast<const uint32_t*>(dev_src); words[n] = (uint32_t)(bytes / 4); dst[n] = host_dst; n++;
+    }
+};
+int read_small_sync(Ctx* ctx, const SmallRead& r);   // enqueue + cudaStreamSynchronize(ctx->stream) + scatter to the host dsts
 
 int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out);
 void batch_free(Batch* b);

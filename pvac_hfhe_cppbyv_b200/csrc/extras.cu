@@ -244,11 +244,13 @@ int pvacb_batch_slice(pvacb_ctx* x, const pvacb_batch* pb, size_t first, size_t 
     if (!out || first + count > s->n) return PV_E_ARG;
     cudaSetDevice(ctx->device);
     uint32_t h[4];
-    PV_CUDA(cudaMemcpyAsync(&h[0], s->loff + first, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(&h[1], s->loff + first + count, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(&h[2], s->eoff + first, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(&h[3], s->eoff + first + count, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    {
+        SmallRead sr;
+        sr.add(&h[0], s->loff + first, 4); sr.add(&h[1], s->loff + first + count, 4);
+        sr.add(&h[2], s->eoff + first, 4); sr.add(&h[3], s->eoff + first + count, 4);
+        int rc0 = read_small_sync(ctx, sr);
+        if (rc0) return rc0;
+    }
     uint64_t l0 = h[0], nL = h[1] - h[0], e0 = h[2], nE = h[3] - h[2];
     Batch* b = nullptr;
     int rc = batch_alloc(ctx, count, nL, nE, &b);

@@ -345,13 +345,12 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
     uint32_t tot[4];
     unsigned long long h_stats[3] = {0, 0, 0};
     unsigned int h_err = 0;
-    PV_CUDA(cudaMemcpyAsync(&tot[0], loP + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(&tot[1], lpoff + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(&tot[2], koff + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(&tot[3], toff + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(h_stats, max_pairs, 24, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    {
+        SmallRead sr;
+        sr.add(&tot[0], loP + n, 4); sr.add(&tot[1], lpoff + n, 4); sr.add(&tot[2], koff + n, 4); sr.add(&tot[3], toff + n, 4);
+        sr.add(h_stats, max_pairs, 24); sr.add(&h_err, err, 4);
+        if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
+    }
     if (h_err) { cleanup(); ctx->last_error = "ct_mul: operand too large for the batched path (layer pairs / keys / edge pairs overflow)"; return PV_E_SHAPE; }
     const uint32_t nLpre = tot[0], nLP = tot[1], nKeys = tot[2], nTbl = tot[3];
     const unsigned long long h_maxpairs = h_stats[0];
@@ -411,10 +410,11 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
         mul_emit_count_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, sval2, k_flags, k_wp, k_wm, k_tins, ecnt);
         PV_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ecnt, epos, (int)nKeys, ctx->stream));
         uint32_t last[2] = {0, 0};
-        PV_CUDA(cudaMemcpyAsync(&last[0], epos + (nKeys - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PV_CUDA(cudaMemcpyAsync(&last[1], ecnt + (nKeys - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PV_CUDA(cudaStreamSynchronize(ctx->stream));
+        {
+            SmallRead sr;
+            sr.add(&last[0], epos + (nKeys - 1), 4); sr.add(&last[1], ecnt + (nKeys - 1), 4); sr.add(&h_err, err, 4);
+            if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
+        }
         ctx->stat_kernel_launches += 7;
         if (h_err) {
             cleanup();
@@ -448,8 +448,7 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
         J.n = nEout; J.ztag = p_zt; J.nlo = p_nl; J.nhi = p_nh; J.seed_idx = seed_idx; J.idx = o->idx; J.ch = o->ch; J.salt = salt; J.out = o->sigma;
         if ((rc = sigma_run(ctx, J))) { cleanup(); batch_free(o); return rc; }
     }
-    PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) { cleanup(); batch_free(o); return rc; } }
     cleanup();
     if (h_err & 8) { batch_free(o); ctx->last_error = "ct_mul: a result exceeds edge_budget (the reference would run compact_edges here)"; return PV_E_EDGE_BUDGET; }
     if ((rc = compact_layers_batch(ctx, o))) { batch_free(o); return rc; }

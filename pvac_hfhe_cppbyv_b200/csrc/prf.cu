@@ -126,8 +126,7 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     ctx->stat_aes_blocks += ncores * ((65ull << rpc_log2) + 1);
 
     unsigned int h_rare = 0;
-    PV_CUDA(cudaMemcpyAsync(&h_rare, rare, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    { SmallRead sr; sr.add(&h_rare, rare, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
     dev_free(ctx, rk); dev_free(ctx, ctr0); dev_free(ctx, top); dev_free(ctx, rare);
     if (!d_ybits_out) dev_free(ctx, ybits);
     if (h_rare) {

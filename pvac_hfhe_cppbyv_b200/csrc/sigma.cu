@@ -55,7 +55,7 @@ __device__ __noinline__ void prg_hash_words(const LabelStream ls, const uint64_t
 template <int G>
 struct __align__(16) SigmaWarpSmem {
     uint32_t bm[kNBits / 32];               // 2 KiB: de-dup bitmap of the columns, then of the noise bits (= the flip mask)
-    uint16_t cols[kXColWt];                 // chosen columns, in draw order
+    uint32_t cols[kXColWt];                 // chosen columns in draw order, as offsets into H in 16-byte units (col * 64)
     uint16_t cand[G * 2 * kCandPerLabel];   // phase B output: [edge][label][136]
     union {
         uint32_t mid[G * 2][8];             // phase A output: SHA-256 state after block 0, per (edge, label)
@@ -66,7 +66,7 @@ struct __align__(16) SigmaWarpSmem {
 
 // ordered de-duplication of one label. Lanes hold candidates 4*lane..4*lane+3, positions 128..135 follow in gc[128..].
 // Returns with exactly 128 distinct values marked in bm (x_col_wt = err_wt = 128); winners are appended to cols if given.
-__device__ __forceinline__ void dedupe_label(uint32_t* bm, uint16_t* cols, uint16_t* more, const uint16_t* gc, const LabelStream ls,
+__device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint16_t* more, const uint16_t* gc, const LabelStream ls,
                                              const SigmaJobs& J, uint64_t canon, uint64_t job, uint32_t N, int lane) {
     uint2 pk = reinterpret_cast<const uint2*>(gc)[lane];
     uint16_t c[4] = {(uint16_t)(pk.x & 0xffff), (uint16_t)(pk.x >> 16), (uint16_t)(pk.y & 0xffff), (uint16_t)(pk.y >> 16)};
@@ -80,7 +80,7 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint16_t* cols, uint1
             win = !(old & bit);
         }
         uint32_t b = __ballot_sync(0xffffffffu, win);
-        if (win && cols) cols[have + __popc(b & ((1u << lane) - 1))] = c[k];
+        if (win && cols) cols[have + __popc(b & ((1u << lane) - 1))] = (uint32_t)c[k] * 64u;
         have += __popc(b);
     }
     if (have < kXColWt) {
@@ -109,7 +109,7 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint16_t* cols, uint1
                     uint32_t old = bm[v >> 5];
                     if (!(old & bit)) {
                         bm[v >> 5] = old | bit;
-                        if (cols) cols[have] = v;
+                        if (cols) cols[have] = (uint32_t)v * 64u;
                         have++;
                     }
                 }
@@ -124,15 +124,21 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint16_t* cols, uint1
 
 template <int G, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4) {
+sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, unsigned long long* __restrict__ work) {
     extern __shared__ __align__(16) uint8_t sigma_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     SigmaWarpSmem<G>& S = reinterpret_cast<SigmaWarpSmem<G>*>(sigma_smem)[wid];
     for (int i = lane; i < kNBits / 32; i += 32) S.bm[i] = 0;
     __syncwarp();
     const uint64_t ngroups = (J.n + G - 1) / G;
-    const uint64_t nwarps = (uint64_t)gridDim.x * WARPS;
-    for (uint64_t grp = (uint64_t)blockIdx.x * WARPS + wid; grp < ngroups; grp += nwarps) {
+    const uint4* const Hl = H4 + lane;
+    // persistent warps pull groups from a global counter: gather time varies per SM (L2 distance, neighbours), a static
+    // split left a quarter of the warp-time idle at the tail (ncu r01: sm__warps_active 33% of a possible 44%)
+    for (;;) {
+        unsigned long long grp = 0;
+        if (lane == 0) grp = atomicAdd(work, 1ull);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if (grp >= ngroups) break;
         const uint64_t job0 = grp * G;
         const int ng = (int)(J.n - job0 < (uint64_t)G ? J.n - job0 : (uint64_t)G);
         // ---- phase A: midstate of block 0 for (edge, label) = (lane >> 1, lane & 1)
@@ -185,17 +191,17 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4) {
             const uint16_t* gc = S.cand + e * 2 * kCandPerLabel;
             dedupe_label(S.bm, S.cols, S.more, gc, label_xseed(), J, canon, job, (uint32_t)kNBits, lane);
             // clear the bitmap again: every word that got a bit belongs to one of the chosen columns
-            for (int i = lane; i < kXColWt; i += 32) S.bm[S.cols[i] >> 5] = 0;
+            for (int i = lane; i < kXColWt; i += 32) S.bm[S.cols[i] >> 11] = 0;
             uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
             for (int i = 0; i < kXColWt; i += 8) {
-                uint4 cv = *reinterpret_cast<const uint4*>(&S.cols[i]);   // 8 column ids, broadcast
-                uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+                uint4 c0 = *reinterpret_cast<const uint4*>(&S.cols[i]);       // 8 column offsets, broadcast
+                uint4 c1 = *reinterpret_cast<const uint4*>(&S.cols[i + 4]);
+                uint32_t co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                 uint4 v[16];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    uint32_t col = (cw[k >> 1] >> ((k & 1) * 16)) & 0xffff;
-                    const uint4* p = H4 + (size_t)col * 64 + lane;
+                    const uint4* p = Hl + co[k];
                     v[2 * k] = __ldcg(p);
                     v[2 * k + 1] = __ldcg(p + 32);
                 }
@@ -259,8 +265,9 @@ static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
     uint64_t grid = (ngroups + WARPS - 1) / WARPS;
     const uint64_t cap = (uint64_t)ctx->sm_count * MINB;     // persistent: every resident warp walks groups round-robin
     if (grid > cap) grid = cap;
+    PV_CUDA(cudaMemsetAsync(ctx->d_work, 0, 8, ctx->stream));
     ProfScope ps(ctx, PROF_SIGMA);
-    kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(J, ctx->kv.canon_tag, reinterpret_cast<const uint4*>(ctx->kv.H));
+    kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(J, ctx->kv.canon_tag, reinterpret_cast<const uint4*>(ctx->kv.H), ctx->d_work);
     return PV_OK;
 }
 

@@ -316,3 +316,26 @@ def test_add_is_a_pure_concatenation_checksum(engine):
     wd = ed["w"].reshape(n, 80, 2)[:, 40:]
     neg = [(P127 - fpv(w)) % P127 for w in wb.reshape(-1, 2)[:500]]
     assert [fpv(w) for w in wd.reshape(-1, 2)[:500]] == neg
+
+
+def test_async_export_equals_sync_export(engine):
+    """pvacb_batch_export_soa_async + pvacb_export_wait deliver the same bytes as the blocking export, also when more
+    work is queued on the compute stream in between (the overlap the e2e benchmark relies on)."""
+    va = np.arange(1, 33, dtype=np.uint64)
+    A, B = engine.enc_value(va, 8101), engine.enc_value(va[::-1].copy(), 8102)
+    P1 = engine.ct_mul(A, B, 8103)
+    n = len(P1)
+    nL, nE = P1.totals()
+    bufs = dict(loff=np.zeros(n + 1, np.uint32), eoff=np.zeros(n + 1, np.uint32), rule=np.zeros(nL + 5, np.uint8), ztag=np.zeros(nL + 5, np.uint64),
+                nlo=np.zeros(nL + 5, np.uint64), nhi=np.zeros(nL + 5, np.uint64), pa=np.zeros(nL + 5, np.uint32), pb=np.zeros(nL + 5, np.uint32),
+                lid=np.zeros(nE + 9, np.uint32), idx=np.zeros(nE + 9, np.uint16), ch=np.zeros(nE + 9, np.uint8), w=np.zeros((nE + 9, 2), np.uint64),
+                sigma=np.zeros((nE + 9, 128), np.uint64))
+    d = engine.export_soa_async(P1, bufs)
+    P2 = engine.ct_mul(A, B, 8104)          # queued behind / next to the copies
+    engine.export_wait()
+    ref = engine.export_soa(P1)
+    for k, v in ref.items():
+        assert np.array_equal(d[k], v), k
+    assert not np.array_equal(engine.export_soa(P2)["sigma"], ref["sigma"])      # different salts, different syndromes
+    with pytest.raises(Exception):
+        engine.export_soa_async(P1, dict(bufs, sigma=np.zeros((3, 128), np.uint64)))

@@ -1,0 +1,113 @@
+// pvacb.hpp -- header-only C++17 convenience layer over the C ABI (pvacb.h), shaped like the reference's API so that a
+// program written against include/pvac/pvac.hpp reads the same with batches in place of single ciphertexts:
+//
+//   reference (one ciphertext, CPU)                     batched (arrays of independent ciphertexts, B200)
+//   -----------------------------------------------     ------------------------------------------------------------
+//   Params prm; PubKey pk; SecKey sk;                   pvacb::Engine eng(/*device*/ 0);
+//   keygen(prm, pk, sk);              keygen.hpp:35     eng.keygen(tape_state);
+//   Cipher a = enc_value(pk, sk, 42); encrypt.hpp:289   pvacb::Ciphers a = eng.enc_value({42, 7, ...}, seed);
+//   Cipher s = ct_add(pk, a, b);      arithmetic.hpp:12 pvacb::Ciphers s = eng.ct_add(a, b);
+//   Cipher d = ct_sub(pk, a, b);      arithmetic.hpp:43 pvacb::Ciphers d = eng.ct_sub(a, b);
+//   Cipher p = ct_mul(pk, a, b);      arithmetic.hpp:47 pvacb::Ciphers p = eng.ct_mul(a, b, seed);
+//   Fp v = dec_value(pk, sk, p);      decrypt.hpp:62    std::vector<pvacb::Fp> v = eng.dec_value(p);
+//
+// Where the reference calls std::abort() these throw pvacb::Error carrying the PVACB_E_* status. Nothing here computes on
+// the CPU: every call forwards to libpvacb.so (sm_100a kernels).
+#ifndef PVACB_HPP
+#define PVACB_HPP
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "pvacb.h"
+
+namespace pvacb {
+
+struct Fp {            // core/field.hpp:17-20
+    uint64_t lo, hi;
+    bool operator==(const Fp& o) const { return lo == o.lo && hi == o.hi; }
+};
+
+class Error : public std::runtime_error {
+public:
+    Error(int code, const std::string& what) : std::runtime_error("pvacb status " + std::to_string(code) + ": " + what), code(code) {}
+    int code;
+};
+
+class Engine;
+
+// A device-resident array of ciphertexts (move-only; frees the batch on destruction).
+class Ciphers {
+public:
+    Ciphers() = default;
+    explicit Ciphers(pvacb_batch* h) : h_(h) {}
+    Ciphers(Ciphers&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    Ciphers& operator=(Ciphers&& o) noexcept { if (this != &o) { reset(); h_ = o.h_; o.h_ = nullptr; } return *this; }
+    Ciphers(const Ciphers&) = delete;
+    Ciphers& operator=(const Ciphers&) = delete;
+    ~Ciphers() { reset(); }
+    void reset() { if (h_) pvacb_batch_free(h_); h_ = nullptr; }
+    size_t size() const { return h_ ? pvacb_batch_count(h_) : 0; }
+    size_t device_bytes() const { return h_ ? pvacb_batch_device_bytes(h_) : 0; }
+    std::pair<uint64_t, uint64_t> totals() const { uint64_t l = 0, e = 0; if (h_) pvacb_batch_totals(h_, &l, &e); return {l, e}; }
+    pvacb_batch* handle() const { return h_; }
+private:
+    pvacb_batch* h_ = nullptr;
+};
+
+class Engine {
+public:
+    explicit Engine(int device = 0, int prf_mode = PVACB_PRF_FAITHFUL) {
+        int rc = pvacb_ctx_create(device, &ctx_);
+        if (rc) throw Error(rc, "pvacb_ctx_create failed (no sm_100-class GPU? there is no CPU fallback)");
+        pvacb_set_prf_mode(ctx_, prf_mode);
+    }
+    ~Engine() { if (ctx_) pvacb_ctx_destroy(ctx_); }
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    void keygen(uint64_t tape_state) { ck(pvacb_keygen(ctx_, tape_state)); }
+    void set_prf_mode(int mode) { ck(pvacb_set_prf_mode(ctx_, mode)); }
+
+    Ciphers enc_value(const std::vector<uint64_t>& v, uint64_t batch_seed) {
+        pvacb_batch* o = nullptr;
+        ck(pvacb_enc_value(ctx_, v.data(), v.size(), batch_seed, &o));
+        return Ciphers(o);
+    }
+    Ciphers ct_add(const Ciphers& a, const Ciphers& b) { pvacb_batch* o = nullptr; ck(pvacb_ct_add(ctx_, a.handle(), b.handle(), &o)); return Ciphers(o); }
+    Ciphers ct_sub(const Ciphers& a, const Ciphers& b) { pvacb_batch* o = nullptr; ck(pvacb_ct_sub(ctx_, a.handle(), b.handle(), &o)); return Ciphers(o); }
+    Ciphers ct_scale(const Ciphers& a, Fp s) { pvacb_batch* o = nullptr; uint64_t w[2] = {s.lo, s.hi}; ck(pvacb_ct_scale(ctx_, a.handle(), w, &o)); return Ciphers(o); }
+    Ciphers ct_mul(const Ciphers& a, const Ciphers& b, uint64_t batch_seed) {
+        pvacb_batch* o = nullptr;
+        ck(pvacb_ct_mul(ctx_, a.handle(), b.handle(), batch_seed, &o));
+        return Ciphers(o);
+    }
+    std::vector<Fp> dec_value(const Ciphers& c) {
+        std::vector<Fp> out(c.size());
+        static_assert(sizeof(Fp) == 16, "Fp is two u64 limbs");
+        ck(pvacb_dec_value(ctx_, c.handle(), reinterpret_cast<uint64_t*>(out.data())));
+        return out;
+    }
+    // the reference's on-disk format (tests/bounty2_test.cpp:63-143)
+    std::vector<uint8_t> to_wire(const Ciphers& c) {
+        size_t n = 0, w = 0;
+        ck(pvacb_batch_wire_size(ctx_, c.handle(), &n));
+        std::vector<uint8_t> buf(n);
+        ck(pvacb_batch_export_wire(ctx_, c.handle(), buf.data(), buf.size(), &w));
+        buf.resize(w);
+        return buf;
+    }
+    Ciphers from_wire(const std::vector<uint8_t>& buf) { pvacb_batch* o = nullptr; ck(pvacb_batch_import_wire(ctx_, buf.data(), buf.size(), &o)); return Ciphers(o); }
+
+    pvacb_ctx* handle() const { return ctx_; }
+
+private:
+    void ck(int rc) { if (rc) throw Error(rc, pvacb_last_error(ctx_)); }
+    pvacb_ctx* ctx_ = nullptr;
+};
+
+}  // namespace pvacb
+#endif  // PVACB_HPP

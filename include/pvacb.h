@@ -35,7 +35,7 @@ enum {
     PVACB_E_CUDA = 2,
     PVACB_E_OOM = 3,         /* reference: std::bad_alloc */
     PVACB_E_NOKEYS = 4,
-    PVACB_E_EDGE_BUDGET = 5, /* an output would exceed Params::edge_budget; reference: guard_budget -> compact_edges (ops/encrypt.hpp:106-111) */
+    PVACB_E_EDGE_BUDGET = 5, /* reserved (results over Params::edge_budget are compacted like the reference's guard_budget does) */
     PVACB_E_LAYER_GRAPH = 6, /* reference: std::abort() in layer_R_cached (ops/decrypt.hpp:23,36) */
     PVACB_E_RARE_PATH = 7,   /* AesCtr256::bounded rejected a word (p = 2^-61 per LPN row, crypto/lpn.hpp:141-148) */
     PVACB_E_DUP_EDGE = 8,    /* ct_mul input with two edges of equal (layer, idx, sign) */
@@ -101,6 +101,9 @@ int pvacb_ct_add(pvacb_ctx* ctx, const pvacb_batch* a, const pvacb_batch* b, pva
 int pvacb_ct_sub(pvacb_ctx* ctx, const pvacb_batch* a, const pvacb_batch* b, pvacb_batch** out);
 /* Cipher ct_scale(pk, A, Fp s)                            ops/arithmetic.hpp:33  (s = lo,hi; one scalar for the batch) */
 int pvacb_ct_scale(pvacb_ctx* ctx, const pvacb_batch* a, const uint64_t s[2], pvacb_batch** out);
+/* void compact_edges(pk, Cipher&)                          ops/encrypt.hpp:39  (returns a new batch; also what ct_add / ct_mul
+ * apply to any result with more than Params::edge_budget edges, like the reference's guard_budget, ops/encrypt.hpp:106) */
+int pvacb_compact_edges(pvacb_ctx* ctx, const pvacb_batch* a, pvacb_batch** out);
 /* Cipher ct_mul(pk, A, B)                                 ops/arithmetic.hpp:47  (draws nonces and salts from the tape) */
 int pvacb_ct_mul(pvacb_ctx* ctx, const pvacb_batch* a, const pvacb_batch* b, uint64_t batch_seed, pvacb_batch** out);
 int pvacb_ct_mul_ex(pvacb_ctx* ctx, const pvacb_batch* a, const pvacb_batch* b, uint64_t batch_seed, const uint64_t* tape_states,

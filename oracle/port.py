@@ -72,6 +72,7 @@ def lib():
         "orc_ct_add": (vp, [vp, vp]),
         "orc_ct_sub": (vp, [vp, vp]),
         "orc_ct_scale": (vp, [vp, P(u64)]),
+        "orc_compact_edges": (vp, [vp]),
         "orc_ct_mul": (vp, [vp, u64, vp, vp, P(u64)]),
         "orc_dec_value": (i32, [vp, vp, P(u64)]),
         "orc_ct_free": (None, [vp]),
@@ -254,6 +255,9 @@ class Keys:
     def ct_scale(self, a, s):
         ss = np.asarray(s, np.uint64)
         return lib().orc_ct_scale(a, _p(ss, C.c_uint64))
+
+    def compact_edges(self, a):
+        return lib().orc_compact_edges(a)
 
     def ct_mul(self, tape_state, a, b):
         global _last_draws

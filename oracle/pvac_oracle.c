@@ -693,6 +693,14 @@ orc_ct* orc_ct_scale(const orc_ct* a, const uint64_t* s) {
     for (uint32_t i = 0; i < a->nE; i++) { edge_t* x = ct_push_edge(c); *x = a->E[i]; x->w = fp_mul(x->w, sc); }
     return c;
 }
+/* ops/encrypt.hpp:39-71 on a copy (the reference mutates in place) */
+orc_ct* orc_compact_edges(const orc_ct* a) {
+    orc_ct* c = ct_new();
+    for (uint32_t i = 0; i < a->nL; i++) ct_push_layer(c, a->L[i]);
+    for (uint32_t i = 0; i < a->nE; i++) *ct_push_edge(c) = a->E[i];
+    compact_edges(c);
+    return c;
+}
 /* ops/arithmetic.hpp:39-45 */
 orc_ct* orc_ct_sub(const orc_ct* a, const orc_ct* b) {
     fp_t m1 = fp_neg(fp_from_u64(1));

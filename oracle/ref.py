@@ -76,6 +76,7 @@ def lib():
         "ref_ct_add": (vp, [vp, vp, vp]),
         "ref_ct_sub": (vp, [vp, vp, vp]),
         "ref_ct_scale": (vp, [vp, vp, P(u64)]),
+        "ref_compact_edges": (vp, [vp, vp]),
         "ref_ct_mul": (vp, [vp, u64, vp, vp]),
         "ref_dec_value": (None, [vp, vp, P(u64)]),
         "ref_ct_free": (None, [vp]),
@@ -236,6 +237,9 @@ class Keys:
     def ct_scale(self, a, s):
         ss = np.asarray(s, np.uint64)
         return lib().ref_ct_scale(self.h, a, _p(ss, C.c_uint64))
+
+    def compact_edges(self, a):
+        return lib().ref_compact_edges(self.h, a)
 
     def ct_mul(self, tape_state, a, b):
         return lib().ref_ct_mul(self.h, tape_state, a, b)

@@ -244,6 +244,7 @@ void* ref_enc_fp_depth(void* h, uint64_t tape_state, const uint64_t* v, int dept
 void* ref_ct_add(void* h, void* a, void* b) { return new Cipher(ct_add(((Keys*)h)->pk, *(Cipher*)a, *(Cipher*)b)); }
 void* ref_ct_sub(void* h, void* a, void* b) { return new Cipher(ct_sub(((Keys*)h)->pk, *(Cipher*)a, *(Cipher*)b)); }
 void* ref_ct_scale(void* h, void* a, const uint64_t* s) { return new Cipher(ct_scale(((Keys*)h)->pk, *(Cipher*)a, Fp{s[0], s[1]})); }
+void* ref_compact_edges(void* h, void* a) { Cipher* c = new Cipher(*(Cipher*)a); compact_edges(((Keys*)h)->pk, *c); return c; }
 void* ref_ct_mul(void* h, uint64_t tape_state, void* a, void* b) {
     ref_seed(tape_state);
     return new Cipher(ct_mul(((Keys*)h)->pk, *(Cipher*)a, *(Cipher*)b));

@@ -40,7 +40,7 @@ SYMBOLS = [
     "pvacb_batch_slice", "pvacb_batch_export_soa", "pvacb_batch_import_soa", "pvacb_batch_wire_size", "pvacb_batch_export_wire",
     "pvacb_batch_import_wire", "pvacb_batch_synthetic", "pvacb_prf", "pvacb_sigma_from_H", "pvacb_fp_op",
     "pvacb_profile_enable", "pvacb_profile_collect", "pvacb_keys_copy_blob_to", "pvacb_keys_adopt_blob_from", "pvacb_l2_gather_probe",
-    "pvacb_batch_export_soa_async", "pvacb_export_wait",
+    "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges",
 ]
 
 
@@ -109,6 +109,7 @@ def load_library():
         "pvacb_l2_gather_probe": (i32, [vp, i32, P(C.c_double)]),
         "pvacb_batch_export_soa_async": (i32, [vp, vp, P(u32), P(u32), P(u8), P(u64), P(u64), P(u64), P(u32), P(u32), P(u32), P(u16), P(u8), P(u64), P(u64)]),
         "pvacb_export_wait": (i32, [vp]),
+        "pvacb_compact_edges": (i32, [vp, vp, P(vp)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -286,6 +287,11 @@ class Engine:
         ss = _u64(s)
         out = C.c_void_p()
         self._ck(self.L.pvacb_ct_scale(self.h, a.h, _p(ss, C.c_uint64), C.byref(out)))
+        return Batch(self, out)
+
+    def compact_edges(self, a):
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_compact_edges(self.h, a.h, C.byref(out)))
         return Batch(self, out)
 
     def ct_mul(self, a, b, batch_seed=0, tape_states=None):

@@ -124,10 +124,8 @@ int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode, Batch** out) {
     unsigned int h_err = 0;
     { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
     dev_free(ctx, err);
-    if (h_err) {
-        batch_free(o);
-        ctx->last_error = "ct_add: a result exceeds edge_budget (the reference would run compact_edges here)";
-        return PV_E_EDGE_BUDGET;
+    if (h_err) {       // guard_budget(pk, C, "add") -> compact_edges, ops/arithmetic.hpp:28
+        if ((rc = guard_budget_batch(ctx, &o))) { batch_free(o); return rc; }
     }
     rc = compact_layers_batch(ctx, o);
     if (rc) { batch_free(o); return rc; }

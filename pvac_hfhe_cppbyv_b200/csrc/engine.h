@@ -185,5 +185,7 @@ int op_dec_value(Ctx* ctx, const Batch* C, uint64_t* h_out /*n x 2*/);
 
 // compact_layers (ops/encrypt.hpp:73-104) of every ciphertext of b, in place (layer arrays shrink, edges stay).
 int compact_layers_batch(Ctx* ctx, Batch* b);
+// guard_budget (ops/encrypt.hpp:106-111): compact_edges on every ciphertext of *pb with more than edge_budget edges; may replace *pb
+int guard_budget_batch(Ctx* ctx, Batch** pb, uint32_t budget = kEdgeBudget);
 
 }  // namespace pvacb

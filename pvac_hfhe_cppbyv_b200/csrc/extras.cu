@@ -238,6 +238,22 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
     return PV_OK;
 }
 
+// compact_edges (ops/encrypt.hpp:39-71) of every ciphertext of the batch: merge equal (layer, idx, sign), drop all-zero
+// results, order by (layer, idx, P before M). The input batch is left untouched.
+int pvacb_compact_edges(pvacb_ctx* x, const pvacb_batch* pb, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    const Batch* s = Bt(pb);
+    if (!out) return PV_E_ARG;
+    cudaSetDevice(ctx->device);
+    Batch* cpy = nullptr;
+    int rc = batch_alloc(ctx, s->n, s->nL, s->nE, &cpy);
+    if (rc) return rc;
+    PV_CUDA(cudaMemcpyAsync(cpy->base, s->base, s->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = guard_budget_batch(ctx, &cpy, 0))) { batch_free(cpy); return rc; }
+    *out = reinterpret_cast<pvacb_batch*>(cpy);
+    return PV_OK;
+}
+
 int pvacb_batch_slice(pvacb_ctx* x, const pvacb_batch* pb, size_t first, size_t count, pvacb_batch** out) {
     Ctx* ctx = C(x);
     const Batch* s = Bt(pb);

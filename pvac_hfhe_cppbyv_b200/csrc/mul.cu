@@ -450,7 +450,9 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
     }
     { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) { cleanup(); batch_free(o); return rc; } }
     cleanup();
-    if (h_err & 8) { batch_free(o); ctx->last_error = "ct_mul: a result exceeds edge_budget (the reference would run compact_edges here)"; return PV_E_EDGE_BUDGET; }
+    if (h_err & 8) {   // guard_budget(pk, C, "mul") -> compact_edges, ops/arithmetic.hpp:103
+        if ((rc = guard_budget_batch(ctx, &o))) { batch_free(o); return rc; }
+    }
     if ((rc = compact_layers_batch(ctx, o))) { batch_free(o); return rc; }
     *out = o;
     return PV_OK;

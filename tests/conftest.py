@@ -74,6 +74,24 @@ def ct_digest(d):
     return h.hexdigest()
 
 
+P127 = (1 << 127) - 1
+
+
+def with_duplicates(d):
+    """a ciphertext with runs of equal (layer, idx, sign): every edge twice; in the copies, edge 0 cancels exactly
+    (w -> p - w, same sigma: the merged edge is all-zero and must be dropped), edge 1 cancels in weight only (kept: sigma != 0)"""
+    e = {k: np.concatenate([d[k], d[k]]) for k in ("lid", "idx", "ch", "w", "sigma")}
+    n = len(d["lid"])
+    for j in (0, 1):
+        w = (int(d["w"][j][0]) | (int(d["w"][j][1]) << 64))
+        e["w"][n + j] = [((P127 - w) % P127) & (2**64 - 1), ((P127 - w) % P127) >> 64]
+    e["sigma"][n + 1] ^= np.uint64(0x5555)
+    e["sigma"][n + 2:] ^= np.uint64(0xF0F0)
+    out = {k: d[k] for k in ("rule", "ztag", "nlo", "nhi", "pa", "pb")}
+    out.update(e)
+    return out
+
+
 # ---- GPU engine (only constructed by -m gpu tests)
 @pytest.fixture(scope="session")
 def engine():

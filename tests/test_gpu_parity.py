@@ -339,3 +339,55 @@ def test_async_export_equals_sync_export(engine):
     assert not np.array_equal(engine.export_soa(P2)["sigma"], ref["sigma"])      # different salts, different syndromes
     with pytest.raises(Exception):
         engine.export_soa_async(P1, dict(bufs, sigma=np.zeros((3, 128), np.uint64)))
+
+
+def test_compact_edges_vs_oracle(engine, api, port, port_keys):
+    """pvacb_compact_edges (= what guard_budget applies past edge_budget, ops/encrypt.hpp:39-71,106-111) on a batch whose
+    ciphertexts carry runs of equal (layer, idx, sign), including a run that cancels to all-zero (dropped) and one that
+    cancels in weight only (kept); ragged: one ciphertext is already compact, one is empty."""
+    from conftest import with_duplicates as _with_duplicates
+    K = port_keys
+    items, want = [], []
+    for seed, v, dup in ((901, 5, True), (902, 6, False), (903, 7, True)):
+        base = port.ct_export(K.enc_value(seed, v))
+        d = _with_duplicates(base) if dup else base
+        items.append(d)
+        want.append(port.ct_export(K.compact_edges(port.ct_import(d))))
+    empty = {k: items[0][k][:0] for k in items[0]}
+    items.append(empty)
+    want.append(empty)
+    X = engine.import_soa(api.join_items(items))
+    got = api.split_items(engine.export_soa(engine.compact_edges(X)))
+    for i, (g, w) in enumerate(zip(got, want)):
+        ok, k = ct_equal(g, w)
+        assert ok, (i, k)
+    # the input batch is untouched
+    back = api.split_items(engine.export_soa(X))
+    assert ct_equal(back[0], items[0])[0]
+    # products of compacted operands decrypt the same (compaction only reorders / merges)
+    A = engine.enc_value(np.array([3, 4], np.uint64), 911)
+    B = engine.enc_value(np.array([5, 6], np.uint64), 912)
+    Pm = engine.ct_mul(engine.compact_edges(A), engine.compact_edges(B), 913)
+    assert [fpv(x) for x in engine.dec_value(engine.compact_edges(Pm))] == [15, 24]
+
+
+@pytest.mark.timeout(900)
+def test_cpp_basic_usage_batched(tmp_path):
+    """BASELINE.json config 1: the reference's examples/basic_usage.cpp scenarios through include/pvacb.hpp (C++ over the C ABI),
+    compiled here with g++ and run on the GPU. Includes the x^8 depth chain (172 k edges per ciphertext), 6! and the ten
+    chained multiplications whose last result passes edge_budget and is compacted like the reference's guard_budget."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "pvac_hfhe_cppbyv_b200")
+    exe = str(tmp_path / "basic_usage_batched")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "basic_usage_batched.cpp"),
+                           "-L", pkg, "-lpvacb", f"-Wl,-rpath,{pkg}", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=800)
+    tail = r.stdout[-3000:]
+    assert r.returncode == 0, tail + r.stderr[-2000:]
+    assert "FAIL" not in r.stdout
+    last = r.stdout.strip().splitlines()[-1]
+    assert last.startswith("passed ") and last.split()[1].split("/")[0] == last.split()[1].split("/")[1], last
+    # the reference counts 42 results for its whole run; 37 of them are on the enc/add/sub/mul/dec path (commit_ct and the
+    # text codec, 5 results, are out of scope), one more here for the wire round trip
+    assert int(last.split()[1].split("/")[0]) >= 38

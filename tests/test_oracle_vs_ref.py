@@ -8,7 +8,7 @@ oracle/_ref is absent (a checkout that never saw the reference tree); the golden
 import numpy as np
 import pytest
 
-from conftest import ct_equal
+from conftest import ct_equal, with_duplicates as _with_duplicates
 
 from oracle import ref as _ref
 
@@ -147,3 +147,21 @@ def test_depth_chain_step2(port, ref, both):
         ok, k = ct_equal(port.ct_export(co, with_sigma=False), ref.ct_export(cr, with_sigma=False), with_sigma=False)
         assert ok, (step, k)
     assert _v(ko.dec_value(co)) == 16 == _v(kr.dec_value(cr))
+
+
+def test_compact_edges(port, ref, both):
+    """ops/encrypt.hpp:39-71 on inputs that really merge and drop (the library's own call sites never produce duplicates)"""
+    ko, kr = both
+    base = port.ct_export(ko.enc_value(777, 5))
+    d = _with_duplicates(base)
+    co, cr = ko.compact_edges(port.ct_import(d)), kr.compact_edges(ref.ct_import(d))
+    eo, er = port.ct_export(co), ref.ct_export(cr)
+    ok, k = ct_equal(eo, er)
+    assert ok, k
+    assert len(eo["lid"]) == len(base["lid"]) - 1                     # one merged edge was all-zero
+    key = eo["lid"].astype(np.int64) * 1024 + eo["idx"].astype(np.int64) * 2 + eo["ch"]
+    assert np.all(np.diff(key) > 0)                                     # ordered by (layer, idx, P before M), no duplicates left
+    # already-compact input: only the order changes
+    c2o, c2r = ko.compact_edges(port.ct_import(base)), kr.compact_edges(ref.ct_import(base))
+    assert ct_equal(port.ct_export(c2o), ref.ct_export(c2r))[0]
+    assert np.array_equal(ko.dec_value(c2o), ko.dec_value(port.ct_import(base)))

@@ -121,6 +121,11 @@ int pvacb_batch_offsets(pvacb_ctx* ctx, const pvacb_batch* b, uint32_t* layer_of
 /* slice [first, first+count) of a batch as a new batch (device copy) */
 int pvacb_batch_slice(pvacb_ctx* ctx, const pvacb_batch* b, size_t first, size_t count, pvacb_batch** out);
 
+/* order-independent checksums of a whole batch, computed on the device (for parity checks at sizes that are not exported):
+ * out[0] XOR of all sigma words; out[1], out[2] sums of w.lo, w.hi; out[3..5] sums of layer_id, idx, ch (mod 2^64);
+ * out[6] sum over layers of (ztag ^ nonce_lo ^ nonce_hi) for BASE, pa + (pb << 32) for PROD; out[7] number of edges */
+int pvacb_batch_checksum(pvacb_ctx* ctx, const pvacb_batch* b, uint64_t out[8]);
+
 /* struct-of-arrays host export / import (for parity checks and interop). Any output pointer may be NULL.
  * layers: rule u8 (0 BASE, 1 PROD), ztag, nonce_lo, nonce_hi u64, pa, pb u32 (0 for BASE);
  * edges: layer_id u32 (relative to its ciphertext), idx u16, ch u8, w u64[2] (lo,hi), sigma u64[128]. */

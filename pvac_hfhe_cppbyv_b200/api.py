@@ -40,7 +40,7 @@ SYMBOLS = [
     "pvacb_batch_slice", "pvacb_batch_export_soa", "pvacb_batch_import_soa", "pvacb_batch_wire_size", "pvacb_batch_export_wire",
     "pvacb_batch_import_wire", "pvacb_batch_synthetic", "pvacb_prf", "pvacb_sigma_from_H", "pvacb_fp_op",
     "pvacb_profile_enable", "pvacb_profile_collect", "pvacb_keys_copy_blob_to", "pvacb_keys_adopt_blob_from", "pvacb_l2_gather_probe",
-    "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges",
+    "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges", "pvacb_batch_checksum",
 ]
 
 
@@ -110,6 +110,7 @@ def load_library():
         "pvacb_batch_export_soa_async": (i32, [vp, vp, P(u32), P(u32), P(u8), P(u64), P(u64), P(u64), P(u32), P(u32), P(u32), P(u16), P(u8), P(u64), P(u64)]),
         "pvacb_export_wait": (i32, [vp]),
         "pvacb_compact_edges": (i32, [vp, vp, P(vp)]),
+        "pvacb_batch_checksum": (i32, [vp, vp, P(u64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -334,6 +335,12 @@ class Engine:
             _p(d["idx"], C.c_uint16), _p(d["ch"], C.c_uint8), _p(d["w"], C.c_uint64), _p(d["sigma"], C.c_uint64) if with_sigma else None))
         return d
 
+    def checksum(self, b):
+        """order-independent device checksums of the whole batch -> dict (see pvacb_batch_checksum)"""
+        o = np.zeros(8, np.uint64)
+        self._ck(self.L.pvacb_batch_checksum(self.h, b.h, _p(o, C.c_uint64)))
+        return dict(xor_sigma=int(o[0]), sum_wlo=int(o[1]), sum_whi=int(o[2]), sum_lid=int(o[3]), sum_idx=int(o[4]), sum_ch=int(o[5]), layers=int(o[6]), edges=int(o[7]))
+
     def export_soa_async(self, b, bufs):
         """queue the device->host copies of batch b into the (pinned, large enough) arrays of `bufs` and return at once;
         call export_wait() before reading them or freeing b. -> dict of views trimmed to the batch's sizes."""
@@ -415,6 +422,19 @@ class Engine:
         out = np.zeros_like(aa)
         self._ck(self.L.pvacb_fp_op(self.h, op, len(aa), _p(aa, C.c_uint64), _p(bb, C.c_uint64), _p(out, C.c_uint64)))
         return out
+
+
+def checksum_of_soa(d):
+    """the same checksums as Engine.checksum, from an exported SoA dict (numpy, on the host)"""
+    M = (1 << 64) - 1
+    x = int(np.bitwise_xor.reduce(d["sigma"].reshape(-1))) if d["sigma"].size else 0
+    w = np.asarray(d["w"], np.uint64).reshape(-1, 2)
+    lay = 0
+    for r, z, lo, hi, pa, pb in zip(d["rule"], d["ztag"], d["nlo"], d["nhi"], d["pa"], d["pb"]):
+        lay = (lay + ((int(z) ^ int(lo) ^ int(hi)) if r == 0 else (int(pa) + (int(pb) << 32)))) & M
+    return dict(xor_sigma=x, sum_wlo=int(sum(int(v) for v in w[:, 0]) & M), sum_whi=int(sum(int(v) for v in w[:, 1]) & M),
+                sum_lid=int(np.sum(d["lid"], dtype=np.uint64)), sum_idx=int(np.sum(d["idx"], dtype=np.uint64)), sum_ch=int(np.sum(d["ch"], dtype=np.uint64)),
+                layers=lay, edges=len(d["lid"]))
 
 
 def split_items(d):

@@ -84,6 +84,35 @@ __global__ void __launch_bounds__(256) l2_gather_probe_kernel(const uint4* __res
     if ((a0.x ^ a0.y ^ a0.z ^ a0.w) == 0x9E3779B9u && cols_per_warp == 0xFFFFFFFFu) sink[w] = a0;   // keeps the loads alive
 }
 
+// order-independent checksums of a whole batch (parity checks at sizes that cannot be exported):
+//   out[0] XOR of all sigma words   out[1], out[2] sums of w.lo, w.hi   out[3] sum of layer ids   out[4] sum of idx
+//   out[5] sum of ch   out[6] sum over layers of (ztag ^ nonce.lo ^ nonce.hi) for BASE, pa + (pb << 32) for PROD   (all mod 2^64)
+__global__ void __launch_bounds__(256) checksum_kernel(uint64_t nE, uint64_t nL, const uint64_t* __restrict__ sigma, const Fp* __restrict__ w,
+                                                       const uint32_t* __restrict__ lid, const uint16_t* __restrict__ idx, const uint8_t* __restrict__ ch,
+                                                       const uint8_t* __restrict__ rule, const uint64_t* __restrict__ ztag, const uint64_t* __restrict__ nlo,
+                                                       const uint64_t* __restrict__ nhi, const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pb,
+                                                       unsigned long long* __restrict__ out) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t x = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;
+    const ulonglong2* s2p = reinterpret_cast<const ulonglong2*>(sigma);
+    for (uint64_t i = tid; i < nE * (kMWords / 2); i += nth) { ulonglong2 v = s2p[i]; x ^= v.x ^ v.y; }
+    for (uint64_t e = tid; e < nE; e += nth) { s1 += w[e].lo; s2 += w[e].hi; s3 += lid[e]; s4 += idx[e]; s5 += ch[e]; }
+    for (uint64_t l = tid; l < nL; l += nth) {
+        if (rule[l] == 0) s6 += ztag[l] ^ nlo[l] ^ nhi[l];
+        else s6 += (uint64_t)pa[l] + ((uint64_t)pb[l] << 32);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        x ^= __shfl_xor_sync(0xffffffffu, x, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        s4 += __shfl_xor_sync(0xffffffffu, s4, o); s5 += __shfl_xor_sync(0xffffffffu, s5, o); s6 += __shfl_xor_sync(0xffffffffu, s6, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicXor(out + 0, (unsigned long long)x);
+        atomicAdd(out + 1, (unsigned long long)s1); atomicAdd(out + 2, (unsigned long long)s2); atomicAdd(out + 3, (unsigned long long)s3);
+        atomicAdd(out + 4, (unsigned long long)s4); atomicAdd(out + 5, (unsigned long long)s5); atomicAdd(out + 6, (unsigned long long)s6);
+    }
+}
+
 __global__ void slice_fix_offsets_kernel(uint64_t cnt, const uint32_t* src_l, const uint32_t* src_e, uint32_t* dst_l, uint32_t* dst_e) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > cnt) return;
@@ -252,6 +281,27 @@ int pvacb_compact_edges(pvacb_ctx* x, const pvacb_batch* pb, pvacb_batch** out) 
     if ((rc = guard_budget_batch(ctx, &cpy, 0))) { batch_free(cpy); return rc; }
     *out = reinterpret_cast<pvacb_batch*>(cpy);
     return PV_OK;
+}
+
+int pvacb_batch_checksum(pvacb_ctx* x, const pvacb_batch* pb, uint64_t out[8]) {
+    Ctx* ctx = C(x);
+    const Batch* b = Bt(pb);
+    if (!out) return PV_E_ARG;
+    cudaSetDevice(ctx->device);
+    unsigned long long* d = nullptr;
+    int rc = dev_alloc(ctx, (void**)&d, 64);
+    if (rc) return rc;
+    PV_CUDA(cudaMemsetAsync(d, 0, 64, ctx->stream));
+    checksum_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(b->nE, b->nL, b->sigma, b->w, b->lid, b->idx, b->ch, b->rule, b->ztag, b->nlo, b->nhi,
+                                                                            b->pa, b->pb, d);
+    PV_CUDA(cudaGetLastError());
+    ctx->stat_kernel_launches += 1;
+    SmallRead sr;
+    sr.add(out, d, 56);
+    rc = read_small_sync(ctx, sr);
+    dev_free(ctx, d);
+    out[7] = b->nE;
+    return rc;
 }
 
 int pvacb_batch_slice(pvacb_ctx* x, const pvacb_batch* pb, size_t first, size_t count, pvacb_batch** out) {

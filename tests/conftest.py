@@ -92,6 +92,12 @@ def with_duplicates(d):
     return out
 
 
+@pytest.fixture(scope="session")
+def api():
+    from pvac_hfhe_cppbyv_b200 import api as a
+    return a
+
+
 # ---- GPU engine (only constructed by -m gpu tests)
 @pytest.fixture(scope="session")
 def engine():

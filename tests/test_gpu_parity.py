@@ -26,12 +26,6 @@ def to_fp(x):
     return [x & (2**64 - 1), x >> 64]
 
 
-@pytest.fixture(scope="module")
-def api():
-    from pvac_hfhe_cppbyv_b200 import api as a
-    return a
-
-
 # ------------------------------------------------------------------ field arithmetic (core/field.hpp)
 def test_fp_ops(engine, kat):
     rng = np.random.default_rng(3)
@@ -391,3 +385,24 @@ def test_cpp_basic_usage_batched(tmp_path):
     # the reference counts 42 results for its whole run; 37 of them are on the enc/add/sub/mul/dec path (commit_ct and the
     # text codec, 5 results, are out of scope), one more here for the wire round trip
     assert int(last.split()[1].split("/")[0]) >= 38
+
+
+@pytest.mark.timeout(600)
+def test_chain10_guard_budget_golden(engine, api):
+    """examples/basic_usage.cpp "perf 10 muls" under a fixed tape against digests of the UNMODIFIED reference
+    (tests/golden/chain10.json, made by oracle/make_chain10.py): every byte of every product, including the tenth, whose
+    1 380 352 edges pass Params::edge_budget so the reference's guard_budget rebuilds it with compact_edges."""
+    import json
+    with open(os.path.join(GOLDEN, "chain10.json")) as f:
+        g = json.load(f)
+    prod = engine.enc_value(np.array([1], np.uint64), tape_states=np.array([5000], np.uint64))
+    for k in range(10):
+        two = engine.enc_value(np.array([2], np.uint64), tape_states=np.array([5100 + k], np.uint64))
+        prod = engine.ct_mul(prod, two, tape_states=np.array([5200 + k], np.uint64))
+        nL, nE = prod.totals()
+        assert (nL, nE) == (g["steps"][k]["layers"], g["steps"][k]["edges"]), k
+        if k <= 5 or k == 9:
+            d = engine.export_soa(prod)
+            assert ct_digest(d) == g["steps"][k]["sha256"], k
+            del d
+    assert hexwords(engine.dec_value(prod)[0]) == g["dec"] == ["0000000000000400", "0000000000000000"]

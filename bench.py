@@ -146,6 +146,12 @@ def main():
         run_reference_arm(args)
         return
 
+    # exactly ONE line on stdout: libraries (NCCL with NCCL_DEBUG=VERSION, torchrun banners) write there too, so stdout is
+    # pointed at stderr for the whole run and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from pvac_hfhe_cppbyv_b200 import api
@@ -437,7 +443,8 @@ def main():
                        "sharding": f"batch index, {world} rank(s), keys replicated by one NCCL broadcast, no steady-state collective", "prf_mode_for_inputs": "live"},
             "e2e": e2e, "gpu_launches": st["kernel_launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(), "ops": ops,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     eng.close()

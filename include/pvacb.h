@@ -96,11 +96,21 @@ int pvacb_enc_value(pvacb_ctx* ctx, const uint64_t* values, size_t n, uint64_t b
  * tape_states == NULL falls back to the batch_seed derivation above. */
 int pvacb_enc_value_ex(pvacb_ctx* ctx, const uint64_t* values, size_t n, uint64_t batch_seed, const uint64_t* tape_states,
                        pvacb_batch** out);
+/* Cipher enc_value_depth(pk, sk, v, depth_hint)            ops/encrypt.hpp:281  (plan_noise(depth_hint) noise groups; depth_hint 0..9)
+ * Cipher enc_zero_depth(pk, sk, depth_hint)                ops/encrypt.hpp:293  (identical draws to enc_value_depth(0, depth_hint)) */
+int pvacb_enc_value_depth(pvacb_ctx* ctx, const uint64_t* values, size_t n, int depth_hint, uint64_t batch_seed, const uint64_t* tape_states,
+                          pvacb_batch** out);
+int pvacb_enc_zero_depth(pvacb_ctx* ctx, size_t n, int depth_hint, uint64_t batch_seed, const uint64_t* tape_states, pvacb_batch** out);
+/* std::pair<int,int> plan_noise(pk, depth_hint)            ops/encrypt.hpp:16 */
+int pvacb_plan_noise(int depth_hint, int* z2, int* z3);
 /* Cipher ct_add / ct_sub(pk, A, B)                        ops/arithmetic.hpp:12,43 */
 int pvacb_ct_add(pvacb_ctx* ctx, const pvacb_batch* a, const pvacb_batch* b, pvacb_batch** out);
 int pvacb_ct_sub(pvacb_ctx* ctx, const pvacb_batch* a, const pvacb_batch* b, pvacb_batch** out);
 /* Cipher ct_scale(pk, A, Fp s)                            ops/arithmetic.hpp:33  (s = lo,hi; one scalar for the batch) */
 int pvacb_ct_scale(pvacb_ctx* ctx, const pvacb_batch* a, const uint64_t s[2], pvacb_batch** out);
+/* Cipher ct_neg(pk, A), ct_div_const(pk, A, Fp k)          ops/arithmetic.hpp:39,108 */
+int pvacb_ct_neg(pvacb_ctx* ctx, const pvacb_batch* a, pvacb_batch** out);
+int pvacb_ct_div_const(pvacb_ctx* ctx, const pvacb_batch* a, const uint64_t k[2], pvacb_batch** out);
 /* void compact_edges(pk, Cipher&)                          ops/encrypt.hpp:39  (returns a new batch; also what ct_add / ct_mul
  * apply to any result with more than Params::edge_budget edges, like the reference's guard_budget, ops/encrypt.hpp:106) */
 int pvacb_compact_edges(pvacb_ctx* ctx, const pvacb_batch* a, pvacb_batch** out);
@@ -110,6 +120,9 @@ int pvacb_ct_mul_ex(pvacb_ctx* ctx, const pvacb_batch* a, const pvacb_batch* b, 
                     pvacb_batch** out);
 /* Fp dec_value(pk, sk, C)                                 ops/decrypt.hpp:62   out: n x (lo,hi) host words */
 int pvacb_dec_value(pvacb_ctx* ctx, const pvacb_batch* c, uint64_t* out);
+
+/* std::array<uint8_t,32> commit_ct(pk, C)                  ops/commit.hpp:12   out: n x 32 bytes (SHA-256 over layers, edges and sigma) */
+int pvacb_commit_ct(pvacb_ctx* ctx, const pvacb_batch* c, uint8_t* out);
 
 /* ---- batches --------------------------------------------------------------------------------------------------- */
 void pvacb_batch_free(pvacb_batch* b);

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpvac_oracle.so")
 
 M_WORDS = 128
+P127 = (1 << 127) - 1
 N_COLS = 16384
 B = 337
 LPN_WORDS = 64
@@ -68,10 +69,13 @@ def lib():
         "orc_next_bkt": (u64, [u64]),
         "orc_unordered_buckets_real": (u64, [u64]),
         "orc_enc_value": (vp, [vp, u64, u64, P(u64)]),
+        "orc_enc_value_depth": (vp, [vp, u64, u64, i32, P(u64)]),
+        "orc_enc_zero_depth": (vp, [vp, u64, i32, P(u64)]),
         "orc_enc_fp_depth": (vp, [vp, u64, P(u64), i32, P(u64)]),
         "orc_ct_add": (vp, [vp, vp]),
         "orc_ct_sub": (vp, [vp, vp]),
         "orc_ct_scale": (vp, [vp, P(u64)]),
+        "orc_commit_ct": (None, [vp, vp, P(u8)]),
         "orc_compact_edges": (vp, [vp]),
         "orc_ct_mul": (vp, [vp, u64, vp, vp, P(u64)]),
         "orc_dec_value": (i32, [vp, vp, P(u64)]),
@@ -238,6 +242,28 @@ class Keys:
         _last_draws = int(d.value)
         return h
 
+    def enc_value_depth(self, tape_state, v, depth):
+        global _last_draws
+        d = C.c_uint64()
+        c = lib().orc_enc_value_depth(self.h, tape_state, v, depth, C.byref(d))
+        _last_draws = int(d.value)
+        return c
+
+    def enc_zero_depth(self, tape_state, depth):
+        global _last_draws
+        d = C.c_uint64()
+        c = lib().orc_enc_zero_depth(self.h, tape_state, depth, C.byref(d))
+        _last_draws = int(d.value)
+        return c
+
+    def ct_neg(self, a):
+        return self.ct_scale(a, [P127 - 1 & (2**64 - 1), (P127 - 1) >> 64])
+
+    def ct_div_const(self, a, k):
+        kv = int(k[0]) | (int(k[1]) << 64)
+        inv = pow(kv, P127 - 2, P127)
+        return self.ct_scale(a, [inv & (2**64 - 1), inv >> 64])
+
     def enc_fp_depth(self, tape_state, v, depth=0):
         global _last_draws
         d = C.c_uint64()
@@ -255,6 +281,11 @@ class Keys:
     def ct_scale(self, a, s):
         ss = np.asarray(s, np.uint64)
         return lib().orc_ct_scale(a, _p(ss, C.c_uint64))
+
+    def commit_ct(self, c):
+        o = np.zeros(32, np.uint8)
+        lib().orc_commit_ct(self.h, c, _p(o, C.c_uint8))
+        return o.tobytes()
 
     def compact_edges(self, a):
         return lib().orc_compact_edges(a)

@@ -673,12 +673,24 @@ orc_ct* orc_enc_fp_depth(const orc_keys* k, uint64_t tape_state, const uint64_t*
 }
 /* ops/encrypt.hpp:281-291. enc_value_depth passes two enc_fp_depth calls as arguments of combine_ciphers; with
  * g++ 13.3 the second (-mask) is evaluated first (pinned by tests/test_oracle_vs_ref.py). */
-orc_ct* orc_enc_value(const orc_keys* k, uint64_t tape_state, uint64_t v, uint64_t* draws) {
+orc_ct* orc_enc_value_depth(const orc_keys* k, uint64_t tape_state, uint64_t v, int depth_hint, uint64_t* draws) {
     tape_t t = { tape_state, 0 };
     fp_t val = fp_from_u64(v);
     fp_t mask = rand_fp_nonzero(&t);
-    orc_ct* b = enc_fp_depth(k, &t, fp_neg(mask), 0);
-    orc_ct* a = enc_fp_depth(k, &t, fp_add(val, mask), 0);
+    orc_ct* b = enc_fp_depth(k, &t, fp_neg(mask), depth_hint);
+    orc_ct* a = enc_fp_depth(k, &t, fp_add(val, mask), depth_hint);
+    orc_ct* c = concat_ct(a, b);
+    orc_ct_free(a); orc_ct_free(b);
+    if (draws) *draws = t.draws;
+    return c;
+}
+orc_ct* orc_enc_value(const orc_keys* k, uint64_t tape_state, uint64_t v, uint64_t* draws) { return orc_enc_value_depth(k, tape_state, v, 0, draws); }
+/* ops/encrypt.hpp:293-298: combine(enc_fp_depth(mask), enc_fp_depth(-mask)), second argument first like enc_value_depth */
+orc_ct* orc_enc_zero_depth(const orc_keys* k, uint64_t tape_state, int depth_hint, uint64_t* draws) {
+    tape_t t = { tape_state, 0 };
+    fp_t mask = rand_fp_nonzero(&t);
+    orc_ct* b = enc_fp_depth(k, &t, fp_neg(mask), depth_hint);
+    orc_ct* a = enc_fp_depth(k, &t, mask, depth_hint);
     orc_ct* c = concat_ct(a, b);
     orc_ct_free(a); orc_ct_free(b);
     if (draws) *draws = t.draws;
@@ -800,6 +812,32 @@ orc_ct* orc_ct_mul(const orc_keys* k, uint64_t tape_state, const orc_ct* A, cons
     compact_layers(C);
     if (draws) *draws = t.draws;
     return C;
+}
+
+/* ops/commit.hpp:12-87 -- SHA-256("pvac.dom.commit" || H_digest || canon_tag || layers || edges (lid, idx as u64, ch, w 16 B, sigma)) */
+void orc_commit_ct(const orc_keys* k, const orc_ct* C, uint8_t out[32]) {
+    sha_t s; sha_init(&s);
+    sha_update(&s, "pvac.dom.commit", 15);
+    sha_update(&s, k->h_digest, 32);
+    sha_u64le(&s, k->canon_tag);
+    for (uint32_t i = 0; i < C->nL; i++) {
+        const layer_t* L = &C->L[i];
+        uint8_t r = (uint8_t)L->rule;
+        sha_update(&s, &r, 1);
+        if (L->rule == 0) { sha_u64le(&s, L->ztag); sha_u64le(&s, L->nlo); sha_u64le(&s, L->nhi); }
+        else { sha_u64le(&s, L->pa); sha_u64le(&s, L->pb); }
+    }
+    for (uint32_t i = 0; i < C->nE; i++) {
+        const edge_t* e = &C->E[i];
+        sha_u64le(&s, e->lid);
+        sha_u64le(&s, e->idx);
+        uint8_t ch = e->ch;
+        sha_update(&s, &ch, 1);
+        sha_u64le(&s, e->w.lo);
+        sha_u64le(&s, e->w.hi & MASK63);
+        for (int w = 0; w < ORC_M_WORDS; w++) sha_u64le(&s, e->s[w]);
+    }
+    sha_final(&s, out);
 }
 
 /* ops/decrypt.hpp:12-89. Returns 0, or -1 where the reference aborts (parent out of range / cycle). */

@@ -76,6 +76,11 @@ def lib():
         "ref_ct_add": (vp, [vp, vp, vp]),
         "ref_ct_sub": (vp, [vp, vp, vp]),
         "ref_ct_scale": (vp, [vp, vp, P(u64)]),
+        "ref_enc_value_depth": (vp, [vp, u64, u64, i32]),
+        "ref_enc_zero_depth": (vp, [vp, u64, i32]),
+        "ref_ct_neg": (vp, [vp, vp]),
+        "ref_ct_div_const": (vp, [vp, vp, P(u64)]),
+        "ref_commit_ct": (None, [vp, vp, P(u8)]),
         "ref_compact_edges": (vp, [vp, vp]),
         "ref_ct_mul": (vp, [vp, u64, vp, vp]),
         "ref_dec_value": (None, [vp, vp, P(u64)]),
@@ -224,6 +229,19 @@ class Keys:
     def enc_value_explicit(self, tape_state, v, second_first):
         return lib().ref_enc_value_explicit(self.h, tape_state, v, int(second_first))
 
+    def enc_value_depth(self, tape_state, v, depth):
+        return lib().ref_enc_value_depth(self.h, tape_state, v, depth)
+
+    def enc_zero_depth(self, tape_state, depth):
+        return lib().ref_enc_zero_depth(self.h, tape_state, depth)
+
+    def ct_neg(self, a):
+        return lib().ref_ct_neg(self.h, a)
+
+    def ct_div_const(self, a, k):
+        kk = np.asarray(k, np.uint64)
+        return lib().ref_ct_div_const(self.h, a, _p(kk, C.c_uint64))
+
     def enc_fp_depth(self, tape_state, v, depth=0):
         vv = np.asarray(v, np.uint64)
         return lib().ref_enc_fp_depth(self.h, tape_state, _p(vv, C.c_uint64), depth)
@@ -237,6 +255,11 @@ class Keys:
     def ct_scale(self, a, s):
         ss = np.asarray(s, np.uint64)
         return lib().ref_ct_scale(self.h, a, _p(ss, C.c_uint64))
+
+    def commit_ct(self, c):
+        o = np.zeros(32, np.uint8)
+        lib().ref_commit_ct(self.h, c, _p(o, C.c_uint8))
+        return o.tobytes()
 
     def compact_edges(self, a):
         return lib().ref_compact_edges(self.h, a)

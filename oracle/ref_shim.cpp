@@ -220,6 +220,18 @@ void* ref_enc_value(void* h, uint64_t tape_state, uint64_t v) {
     ref_seed(tape_state);
     return new Cipher(enc_value(k->pk, k->sk, v));
 }
+void* ref_enc_value_depth(void* h, uint64_t tape_state, uint64_t v, int depth) {
+    Keys* k = (Keys*)h;
+    ref_seed(tape_state);
+    return new Cipher(enc_value_depth(k->pk, k->sk, v, depth));
+}
+void* ref_enc_zero_depth(void* h, uint64_t tape_state, int depth) {
+    Keys* k = (Keys*)h;
+    ref_seed(tape_state);
+    return new Cipher(enc_zero_depth(k->pk, k->sk, depth));
+}
+void* ref_ct_neg(void* h, void* a) { return new Cipher(ct_neg(((Keys*)h)->pk, *(Cipher*)a)); }
+void* ref_ct_div_const(void* h, void* a, const uint64_t* kk) { return new Cipher(ct_div_const(((Keys*)h)->pk, *(Cipher*)a, Fp{kk[0], kk[1]})); }
 // explicit order used by g++ 13.3 for enc_value_depth's two argument calls (ops/encrypt.hpp:284-286)
 void* ref_enc_value_explicit(void* h, uint64_t tape_state, uint64_t v, int second_first) {
     Keys* k = (Keys*)h;
@@ -244,6 +256,7 @@ void* ref_enc_fp_depth(void* h, uint64_t tape_state, const uint64_t* v, int dept
 void* ref_ct_add(void* h, void* a, void* b) { return new Cipher(ct_add(((Keys*)h)->pk, *(Cipher*)a, *(Cipher*)b)); }
 void* ref_ct_sub(void* h, void* a, void* b) { return new Cipher(ct_sub(((Keys*)h)->pk, *(Cipher*)a, *(Cipher*)b)); }
 void* ref_ct_scale(void* h, void* a, const uint64_t* s) { return new Cipher(ct_scale(((Keys*)h)->pk, *(Cipher*)a, Fp{s[0], s[1]})); }
+void ref_commit_ct(void* h, void* c, uint8_t* out32) { auto d = commit_ct(((Keys*)h)->pk, *(Cipher*)c); memcpy(out32, d.data(), 32); }
 void* ref_compact_edges(void* h, void* a) { Cipher* c = new Cipher(*(Cipher*)a); compact_edges(((Keys*)h)->pk, *c); return c; }
 void* ref_ct_mul(void* h, uint64_t tape_state, void* a, void* b) {
     ref_seed(tape_state);

@@ -40,7 +40,8 @@ SYMBOLS = [
     "pvacb_batch_slice", "pvacb_batch_export_soa", "pvacb_batch_import_soa", "pvacb_batch_wire_size", "pvacb_batch_export_wire",
     "pvacb_batch_import_wire", "pvacb_batch_synthetic", "pvacb_prf", "pvacb_sigma_from_H", "pvacb_fp_op",
     "pvacb_profile_enable", "pvacb_profile_collect", "pvacb_keys_copy_blob_to", "pvacb_keys_adopt_blob_from", "pvacb_l2_gather_probe",
-    "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges", "pvacb_batch_checksum",
+    "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges", "pvacb_batch_checksum", "pvacb_commit_ct",
+    "pvacb_enc_value_depth", "pvacb_enc_zero_depth", "pvacb_plan_noise", "pvacb_ct_neg", "pvacb_ct_div_const",
 ]
 
 
@@ -111,6 +112,12 @@ def load_library():
         "pvacb_export_wait": (i32, [vp]),
         "pvacb_compact_edges": (i32, [vp, vp, P(vp)]),
         "pvacb_batch_checksum": (i32, [vp, vp, P(u64)]),
+        "pvacb_commit_ct": (i32, [vp, vp, P(u8)]),
+        "pvacb_enc_value_depth": (i32, [vp, P(u64), sz, i32, u64, P(u64), P(vp)]),
+        "pvacb_enc_zero_depth": (i32, [vp, sz, i32, u64, P(u64), P(vp)]),
+        "pvacb_plan_noise": (i32, [i32, P(i32), P(i32)]),
+        "pvacb_ct_neg": (i32, [vp, vp, P(vp)]),
+        "pvacb_ct_div_const": (i32, [vp, vp, P(u64), P(vp)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -290,6 +297,35 @@ class Engine:
         self._ck(self.L.pvacb_ct_scale(self.h, a.h, _p(ss, C.c_uint64), C.byref(out)))
         return Batch(self, out)
 
+    def enc_value_depth(self, values, depth_hint, batch_seed=0, tape_states=None):
+        v = _u64(values)
+        st = _u64(tape_states) if tape_states is not None else None
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_enc_value_depth(self.h, _p(v, C.c_uint64), len(v), depth_hint, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        return Batch(self, out)
+
+    def enc_zero_depth(self, n, depth_hint, batch_seed=0, tape_states=None):
+        st = _u64(tape_states) if tape_states is not None else None
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_enc_zero_depth(self.h, n, depth_hint, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        return Batch(self, out)
+
+    def plan_noise(self, depth_hint):
+        a, b = C.c_int(), C.c_int()
+        self.L.pvacb_plan_noise(depth_hint, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def ct_neg(self, a):
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_ct_neg(self.h, a.h, C.byref(out)))
+        return Batch(self, out)
+
+    def ct_div_const(self, a, k):
+        kk = _u64(k)
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_ct_div_const(self.h, a.h, _p(kk, C.c_uint64), C.byref(out)))
+        return Batch(self, out)
+
     def compact_edges(self, a):
         out = C.c_void_p()
         self._ck(self.L.pvacb_compact_edges(self.h, a.h, C.byref(out)))
@@ -334,6 +370,12 @@ class Engine:
             _p(d["nlo"], C.c_uint64), _p(d["nhi"], C.c_uint64), _p(d["pa"], C.c_uint32), _p(d["pb"], C.c_uint32), _p(d["lid"], C.c_uint32),
             _p(d["idx"], C.c_uint16), _p(d["ch"], C.c_uint8), _p(d["w"], C.c_uint64), _p(d["sigma"], C.c_uint64) if with_sigma else None))
         return d
+
+    def commit_ct(self, c):
+        """-> (n, 32) uint8: commit_ct digest of every ciphertext"""
+        out = np.zeros((len(c), 32), np.uint8)
+        self._ck(self.L.pvacb_commit_ct(self.h, c.h, _p(out, C.c_uint8)))
+        return out
 
     def checksum(self, b):
         """order-independent device checksums of the whole batch -> dict (see pvacb_batch_checksum)"""

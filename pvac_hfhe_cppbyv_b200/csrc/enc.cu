@@ -13,6 +13,9 @@
 #include "engine.h"
 #include "enc_plan.cuh"
 
+#include <algorithm>
+#include <cmath>
+
 namespace pvacb {
 
 // share s = 0 is enc_fp_depth(-mask) (drawn first, becomes layer 1 / the trailing edges), s = 1 is enc_fp_depth(v+mask)
@@ -92,9 +95,21 @@ __global__ void enc_weights_kernel(uint64_t n, const SharePlan* __restrict__ pla
     for (int p = 0; p < P.n_out; p++) b_w[e0 + p] = wsum[p];
 }
 
-int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out) {
-    const int Z2 = ctx->z2, Z3 = ctx->z3, G = Z2 + Z3, RAW = kSignal + 2 * Z2 + 3 * Z3;
-    if (Z2 > kMaxZ2 || Z3 > kMaxZ3 || G < 1) return PV_E_ARG;
+// plan_noise (ops/encrypt.hpp:16-27) for the default Params: the only floating point on the path, evaluated on the host with
+// the same double expressions as the reference (noise_entropy_bits 120, depth_slope_bits 16, tuple2_fraction 0.55, B 337)
+void plan_noise_host(int depth_hint, int& z2, int& z3) {
+    double budget = 120.0 + 16.0 * (double)std::max(0, depth_hint);
+    double per2 = 2.0 * std::log2((double)kB), per3 = 3.0 * std::log2((double)kB);
+    z2 = std::max(0, (int)std::floor((budget * 0.55) / std::max(1e-6, per2)));
+    z3 = std::max(0, (int)std::floor((budget * (1.0 - 0.55)) / std::max(1e-6, per3)));
+    if (z2 + z3 == 1) { z3 > 0 ? ++z3 : ++z2; }
+}
+
+int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint) {
+    int Z2, Z3;
+    plan_noise_host(depth_hint, Z2, Z3);
+    const int G = Z2 + Z3, RAW = kSignal + 2 * Z2 + 3 * Z3;
+    if (Z2 > kMaxZ2 || Z3 > kMaxZ3 || G < 1) { ctx->last_error = "enc_value: depth_hint outside the supported range 0..9"; return PV_E_ARG; }
     int rc;
     if (n == 0) return batch_alloc(ctx, 0, 0, 0, out);
     uint64_t *d_vals = nullptr, *d_states = nullptr;

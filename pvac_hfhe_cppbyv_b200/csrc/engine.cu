@@ -332,6 +332,26 @@ int pvacb_enc_value_ex(pvacb_ctx* x, const uint64_t* values, size_t n, uint64_t 
 int pvacb_enc_value(pvacb_ctx* x, const uint64_t* values, size_t n, uint64_t seed, pvacb_batch** out) {
     return pvacb_enc_value_ex(x, values, n, seed, nullptr, out);
 }
+int pvacb_enc_value_depth(pvacb_ctx* x, const uint64_t* values, size_t n, int depth_hint, uint64_t seed, const uint64_t* tape_states, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    if (!out || (n && !values)) return PV_E_ARG;
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    cudaSetDevice(ctx->device);
+    Batch* b = nullptr;
+    int rc = op_enc_value(ctx, values, false, n, seed, tape_states, &b, depth_hint);
+    *out = reinterpret_cast<pvacb_batch*>(b);
+    return rc;
+}
+// enc_zero_depth draws the mask and both shares exactly like enc_value_depth(0, depth): fp_add(0, mask) == mask
+int pvacb_enc_zero_depth(pvacb_ctx* x, size_t n, int depth_hint, uint64_t seed, const uint64_t* tape_states, pvacb_batch** out) {
+    std::vector<uint64_t> zeros(n ? n : 1, 0);
+    return pvacb_enc_value_depth(x, zeros.data(), n, depth_hint, seed, tape_states, out);
+}
+int pvacb_plan_noise(int depth_hint, int* z2, int* z3) {
+    if (!z2 || !z3) return PV_E_ARG;
+    plan_noise_host(depth_hint, *z2, *z3);
+    return PV_OK;
+}
 static int binop(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, int mode, pvacb_batch** out) {
     Ctx* ctx = C(x);
     if (!a || !b || !out) return PV_E_ARG;
@@ -344,6 +364,17 @@ static int binop(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, int m
 }
 int pvacb_ct_add(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, pvacb_batch** out) { return binop(x, a, b, 0, out); }
 int pvacb_ct_sub(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, pvacb_batch** out) { return binop(x, a, b, 1, out); }
+int pvacb_ct_neg(pvacb_ctx* x, const pvacb_batch* a, pvacb_batch** out) {
+    const Fp m1 = fp_neg(fp_one());
+    const uint64_t s[2] = {m1.lo, m1.hi};
+    return pvacb_ct_scale(x, a, s, out);
+}
+int pvacb_ct_div_const(pvacb_ctx* x, const pvacb_batch* a, const uint64_t k[2], pvacb_batch** out) {
+    if (!k) return PV_E_ARG;
+    const Fp inv = fp_inv(fp_from_words(k[0], k[1]));     // one scalar: the 127-squaring Fermat ladder runs once, on the host
+    const uint64_t s[2] = {inv.lo, inv.hi};
+    return pvacb_ct_scale(x, a, s, out);
+}
 int pvacb_ct_scale(pvacb_ctx* x, const pvacb_batch* a, const uint64_t s[2], pvacb_batch** out) {
     Ctx* ctx = C(x);
     if (!a || !s || !out) return PV_E_ARG;

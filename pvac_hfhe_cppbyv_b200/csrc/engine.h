@@ -58,7 +58,6 @@ struct Ctx {
     LpnSecret lpn_s{};
     std::vector<uint64_t> h_hdr;     // host copy of the blob header
     int prf_mode = PRF_FAITHFUL;
-    int z2 = 3, z3 = 2;              // plan_noise(depth 0)
     std::string last_error;
     // statistics of the last call (for bench.py)
     uint64_t stat_kernel_launches = 0;
@@ -177,11 +176,13 @@ int sigma_xor_rows(Ctx* ctx, uint64_t npairs, const uint2* d_pairs, uint64_t* ou
 int scan_u32(Ctx* ctx, uint64_t n, const uint32_t* in, uint32_t* out);
 
 // ---- ops
-int op_enc_value(Ctx* ctx, const uint64_t* h_or_d_values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out);
+int op_enc_value(Ctx* ctx, const uint64_t* h_or_d_values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint = 0);
+void plan_noise_host(int depth_hint, int& z2, int& z3);
 int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode /*0 add, 1 sub*/, Batch** out);
 int op_ct_scale(Ctx* ctx, const Batch* A, Fp s, Batch** out);
 int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, const uint64_t* h_states, Batch** out);
 int op_dec_value(Ctx* ctx, const Batch* C, uint64_t* h_out /*n x 2*/);
+int op_commit_ct(Ctx* ctx, const Batch* b, uint8_t* h_out /*n x 32*/);
 
 // compact_layers (ops/encrypt.hpp:73-104) of every ciphertext of b, in place (layer arrays shrink, edges stay).
 int compact_layers_batch(Ctx* ctx, Batch* b);

@@ -283,6 +283,14 @@ int pvacb_compact_edges(pvacb_ctx* x, const pvacb_batch* pb, pvacb_batch** out) 
     return PV_OK;
 }
 
+int pvacb_commit_ct(pvacb_ctx* x, const pvacb_batch* pb, uint8_t* out) {
+    Ctx* ctx = C(x);
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    if (!out) return PV_E_ARG;
+    cudaSetDevice(ctx->device);
+    return op_commit_ct(ctx, Bt(pb), out);
+}
+
 int pvacb_batch_checksum(pvacb_ctx* x, const pvacb_batch* pb, uint64_t out[8]) {
     Ctx* ctx = C(x);
     const Batch* b = Bt(pb);

@@ -406,3 +406,53 @@ def test_chain10_guard_budget_golden(engine, api):
             assert ct_digest(d) == g["steps"][k]["sha256"], k
             del d
     assert hexwords(engine.dec_value(prod)[0]) == g["dec"] == ["0000000000000400", "0000000000000000"]
+
+
+def test_commit_ct_vs_oracle(engine, api, port, port_keys):
+    """pvacb_commit_ct (ops/commit.hpp:12-87): digests of fresh, summed, product and empty ciphertexts in one ragged batch"""
+    K = port_keys
+    a, b = K.enc_value(port.item_stream_state(8201, 0), 3), K.enc_value(port.item_stream_state(8202, 0), 4)
+    cts = [a, K.ct_add(a, b), K.ct_mul(77, a, b), K.ct_sub(b, a)]
+    items = [port.ct_export(c) for c in cts]
+    empty = {k: items[0][k][:0] for k in items[0]}
+    X = engine.import_soa(api.join_items(items + [empty]))
+    got = engine.commit_ct(X)
+    for i, c in enumerate(cts):
+        assert got[i].tobytes() == K.commit_ct(c), i
+    assert got[4].tobytes() == K.commit_ct(port.ct_import(empty))
+    # a larger batch: every digest distinct, equal to the digest of the re-imported export
+    A = engine.enc_value(np.arange(100, dtype=np.uint64), 8203)
+    Pm = engine.ct_mul(A, A, 8204)
+    d1 = engine.commit_ct(Pm)
+    assert len({x.tobytes() for x in d1}) == 100
+    d2 = engine.commit_ct(engine.import_soa(engine.export_soa(Pm)))
+    assert np.array_equal(d1, d2)
+
+
+def test_depth_hints_and_riders_vs_oracle(engine, api, port, port_keys):
+    """pvacb_enc_value_depth / enc_zero_depth (plan_noise(depth) noise groups), ct_neg, ct_div_const against the oracle"""
+    K = port_keys
+    assert [engine.plan_noise(d) for d in range(10)] == [K.plan_noise(d) for d in range(10)]
+    vals = np.array([5, 2**64 - 1, 0], np.uint64)
+    for depth in (0, 1, 3, 9):
+        got = api.split_items(engine.export_soa(engine.enc_value_depth(vals, depth, 8300 + depth)))
+        for i in range(3):
+            want = port.ct_export(K.enc_value_depth(port.item_stream_state(8300 + depth, i), int(vals[i]), depth))
+            ok, f = ct_equal(got[i], want)
+            assert ok, (depth, i, f)
+        Z = engine.enc_zero_depth(3, depth, 8400 + depth)
+        gz = api.split_items(engine.export_soa(Z))
+        for i in range(3):
+            ok, f = ct_equal(gz[i], port.ct_export(K.enc_zero_depth(port.item_stream_state(8400 + depth, i), depth)))
+            assert ok, (depth, i, f)
+        assert not engine.dec_value(Z).any()
+    with pytest.raises(api.PvacbError):
+        engine.enc_value_depth(vals, 10, 1)                  # more noise groups than the kernels are built for
+    A = engine.enc_value(np.array([77, 91], np.uint64), 8500)
+    oa = [K.enc_value(port.item_stream_state(8500, i), v) for i, v in enumerate((77, 91))]
+    gn = api.split_items(engine.export_soa(engine.ct_neg(A)))
+    gd = api.split_items(engine.export_soa(engine.ct_div_const(A, [7, 0])))
+    for i in range(2):
+        assert ct_equal(gn[i], port.ct_export(K.ct_neg(oa[i])))[0]
+        assert ct_equal(gd[i], port.ct_export(K.ct_div_const(oa[i], [7, 0])))[0]
+    assert [fpv(x) for x in engine.dec_value(engine.ct_div_const(A, [7, 0]))] == [11, 13]

@@ -165,3 +165,37 @@ def test_compact_edges(port, ref, both):
     c2o, c2r = ko.compact_edges(port.ct_import(base)), kr.compact_edges(ref.ct_import(base))
     assert ct_equal(port.ct_export(c2o), ref.ct_export(c2r))[0]
     assert np.array_equal(ko.dec_value(c2o), ko.dec_value(port.ct_import(base)))
+
+
+def test_commit_ct(port, ref, both):
+    """ops/commit.hpp:12-87 on fresh, summed and product ciphertexts (BASE and PROD layers, 39 .. ~1200 edges)"""
+    ko, kr = both
+    ao, ar = ko.enc_value(31, 9), kr.enc_value(31, 9)
+    bo, br = ko.enc_value(32, 11), kr.enc_value(32, 11)
+    for co, cr in ((ao, ar), (ko.ct_add(ao, bo), kr.ct_add(ar, br)), (ko.ct_mul(33, ao, bo), kr.ct_mul(33, ar, br))):
+        assert ko.commit_ct(co) == kr.commit_ct(cr)
+    assert ko.commit_ct(ao) != ko.commit_ct(bo)
+
+
+def test_depth_hints_and_riders(port, ref, both):
+    """enc_value_depth / enc_zero_depth with depth hints (plan_noise gives (4,2), (5,3), (8,4) groups at depths 1, 3, 9),
+    ct_neg, ct_div_const (ops/encrypt.hpp:281-298, ops/arithmetic.hpp:39-41,108-110)"""
+    ko, kr = both
+    for depth in (1, 3, 9):
+        co, cr = ko.enc_value_depth(600 + depth, 123456789, depth), kr.enc_value_depth(600 + depth, 123456789, depth)
+        ok, k = ct_equal(port.ct_export(co), ref.ct_export(cr))
+        assert ok, (depth, k)
+        assert _v(ko.dec_value(co)) == 123456789
+        zo, zr = ko.enc_zero_depth(700 + depth, depth), kr.enc_zero_depth(700 + depth, depth)
+        ok, k = ct_equal(port.ct_export(zo), ref.ct_export(zr))
+        assert ok, (depth, k)
+        assert _v(ko.dec_value(zo)) == 0
+        # enc_zero_depth(d) and enc_value_depth(0, d) consume the tape identically
+        ok, _ = ct_equal(port.ct_export(zo), port.ct_export(ko.enc_value_depth(700 + depth, 0, depth)))
+        assert ok
+    ao, ar = ko.enc_value(41, 77), kr.enc_value(41, 77)
+    assert ct_equal(port.ct_export(ko.ct_neg(ao)), ref.ct_export(kr.ct_neg(ar)))[0]
+    k7 = _w(7)
+    do, dr = ko.ct_div_const(ao, k7), kr.ct_div_const(ar, k7)
+    assert ct_equal(port.ct_export(do), ref.ct_export(dr))[0]
+    assert _v(ko.dec_value(do)) == 11 and _v(ko.dec_value(ko.ct_neg(ao))) == P - 77

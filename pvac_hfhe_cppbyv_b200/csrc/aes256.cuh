@@ -116,24 +116,31 @@ __device__ __forceinline__ uint32_t aes_lds_abs(uint32_t addr) {
 #define PVACB_IDX(s, k) __byte_perm((s), lane4, 0x5504 | ((k) << 4))
 #define PVACB_LD(t, idx) aes_lds_abs<(int)kAesTabAbs + ((t) >> 1) * 65536 + ((t) & 1) * 128>(idx)
 
-// AES-256 counter-mode block generator for one thread: round keys in registers, and the part of round 1 that only depends
-// on the high 96 bits of the input block (the counter's high word and the zero half, crypto/lpn.hpp:84,104) hoisted out of
-// the per-block work: 4 lookups instead of 16 in round 1.
+// AES-256 counter-mode block generator for one thread: round keys in registers. The input block is LE64(ctr) || 0^8
+// (crypto/lpn.hpp:84,104) and a thread walks 65 CONSECUTIVE counters, so between two blocks only byte 0 of the state
+// changes (until the low byte wraps, once per 256 blocks). Everything of rounds 1 and 2 that does not depend on that byte
+// is hoisted: round 1 keeps one lookup (T0 of the changing byte; the other three columns u1..u3 are constant), round 2
+// keeps the four lookups indexed by the bytes of the one changing column; the constant parts are c0 and d0..d3.
+// 1 + 4 + 11*16 + 16 = 197 lookups per block instead of 224.
 struct AesCtrThread {
-    uint32_t rk0;          // rk[0]
-    uint32_t c0, c1, c2, c3;   // round-1 partial columns (everything except the terms of state word 0)
-    uint32_t hi;           // counter high word the partials were computed for
-    uint32_t rk1;          // rk[1], needed again if the low word wraps
-    uint32_t rk2, rk3, rk4, rk5, rk6, rk7;
-    uint32_t rk[52];       // rk[8..59]
+    uint32_t rk0;              // rk[0]
+    uint32_t c0;               // round 1, column 0 without the T0[x.b0] term
+    uint32_t d0, d1, d2, d3;   // round 2 without the terms of column 0
+    uint64_t tag;              // ctr >> 8 the constants were computed for
+    uint32_t rk1, rk2, rk3, rk4, rk5, rk6, rk7;
+    uint32_t rk[52];           // rk[8..59]
 
-    __device__ __forceinline__ void prime(const uint8_t* __restrict__ sT, uint32_t lane4, uint32_t hi_word) {
-        hi = hi_word;
-        uint32_t s1 = hi_word ^ rk1, s2 = rk2, s3 = rk3;
-        c0 = PVACB_LD(1, PVACB_IDX(s1, 1)) ^ PVACB_LD(2, PVACB_IDX(s2, 2)) ^ PVACB_LD(3, PVACB_IDX(s3, 3)) ^ rk4;
-        c1 = PVACB_LD(0, PVACB_IDX(s1, 0)) ^ PVACB_LD(1, PVACB_IDX(s2, 1)) ^ PVACB_LD(2, PVACB_IDX(s3, 2)) ^ rk5;
-        c2 = PVACB_LD(0, PVACB_IDX(s2, 0)) ^ PVACB_LD(1, PVACB_IDX(s3, 1)) ^ PVACB_LD(3, PVACB_IDX(s1, 3)) ^ rk6;
-        c3 = PVACB_LD(0, PVACB_IDX(s3, 0)) ^ PVACB_LD(2, PVACB_IDX(s1, 2)) ^ PVACB_LD(3, PVACB_IDX(s2, 3)) ^ rk7;
+    __device__ __forceinline__ void prime(const uint8_t* __restrict__ sT, uint32_t lane4, uint64_t ctr) {
+        tag = ctr >> 8;
+        const uint32_t x0 = (uint32_t)ctr ^ rk0, x1 = (uint32_t)(ctr >> 32) ^ rk1, x2 = rk2, x3 = rk3;
+        c0 = PVACB_LD(1, PVACB_IDX(x1, 1)) ^ PVACB_LD(2, PVACB_IDX(x2, 2)) ^ PVACB_LD(3, PVACB_IDX(x3, 3)) ^ rk4;
+        const uint32_t u1 = PVACB_LD(0, PVACB_IDX(x1, 0)) ^ PVACB_LD(1, PVACB_IDX(x2, 1)) ^ PVACB_LD(2, PVACB_IDX(x3, 2)) ^ PVACB_LD(3, PVACB_IDX(x0, 3)) ^ rk5;
+        const uint32_t u2 = PVACB_LD(0, PVACB_IDX(x2, 0)) ^ PVACB_LD(1, PVACB_IDX(x3, 1)) ^ PVACB_LD(2, PVACB_IDX(x0, 2)) ^ PVACB_LD(3, PVACB_IDX(x1, 3)) ^ rk6;
+        const uint32_t u3 = PVACB_LD(0, PVACB_IDX(x3, 0)) ^ PVACB_LD(1, PVACB_IDX(x0, 1)) ^ PVACB_LD(2, PVACB_IDX(x1, 2)) ^ PVACB_LD(3, PVACB_IDX(x2, 3)) ^ rk7;
+        d0 = PVACB_LD(1, PVACB_IDX(u1, 1)) ^ PVACB_LD(2, PVACB_IDX(u2, 2)) ^ PVACB_LD(3, PVACB_IDX(u3, 3)) ^ rk[0];
+        d1 = PVACB_LD(0, PVACB_IDX(u1, 0)) ^ PVACB_LD(1, PVACB_IDX(u2, 1)) ^ PVACB_LD(2, PVACB_IDX(u3, 2)) ^ rk[1];
+        d2 = PVACB_LD(0, PVACB_IDX(u2, 0)) ^ PVACB_LD(1, PVACB_IDX(u3, 1)) ^ PVACB_LD(3, PVACB_IDX(u1, 3)) ^ rk[2];
+        d3 = PVACB_LD(0, PVACB_IDX(u3, 0)) ^ PVACB_LD(2, PVACB_IDX(u1, 2)) ^ PVACB_LD(3, PVACB_IDX(u2, 3)) ^ rk[3];
     }
 
     __device__ __forceinline__ void load_keys(const uint32_t* __restrict__ rk_core) {
@@ -149,15 +156,15 @@ struct AesCtrThread {
     }
 
     __device__ __forceinline__ void block(const uint8_t* __restrict__ sT, uint32_t lane4, uint64_t ctr, uint64_t& w0, uint64_t& w1) {
-        uint32_t hw = (uint32_t)(ctr >> 32);
-        if (hw != hi) prime(sT, lane4, hw);          // the low word wrapped: at most once per thread
-        uint32_t x = (uint32_t)ctr ^ rk0;
-        uint32_t s0 = c0 ^ PVACB_LD(0, PVACB_IDX(x, 0));
-        uint32_t s1 = c1 ^ PVACB_LD(3, PVACB_IDX(x, 3));
-        uint32_t s2 = c2 ^ PVACB_LD(2, PVACB_IDX(x, 2));
-        uint32_t s3 = c3 ^ PVACB_LD(1, PVACB_IDX(x, 1));
+        if ((ctr >> 8) != tag) prime(sT, lane4, ctr);   // the low counter byte wrapped: at most twice per thread
+        const uint32_t x = (uint32_t)ctr ^ rk0;
+        const uint32_t t0 = c0 ^ PVACB_LD(0, PVACB_IDX(x, 0));                 // round 1: the one column that changes
+        uint32_t s0 = d0 ^ PVACB_LD(0, PVACB_IDX(t0, 0));                      // round 2: its four bytes
+        uint32_t s1 = d1 ^ PVACB_LD(3, PVACB_IDX(t0, 3));
+        uint32_t s2 = d2 ^ PVACB_LD(2, PVACB_IDX(t0, 2));
+        uint32_t s3 = d3 ^ PVACB_LD(1, PVACB_IDX(t0, 1));
 #pragma unroll
-        for (int r = 2; r < 14; r++) {
+        for (int r = 3; r < 14; r++) {
             const int kb = 4 * r - 8;
             uint32_t t0 = PVACB_LD(0, PVACB_IDX(s0, 0)) ^ PVACB_LD(1, PVACB_IDX(s1, 1)) ^ PVACB_LD(2, PVACB_IDX(s2, 2)) ^ PVACB_LD(3, PVACB_IDX(s3, 3)) ^ rk[kb + 0];
             uint32_t t1 = PVACB_LD(0, PVACB_IDX(s1, 0)) ^ PVACB_LD(1, PVACB_IDX(s2, 1)) ^ PVACB_LD(2, PVACB_IDX(s3, 2)) ^ PVACB_LD(3, PVACB_IDX(s0, 3)) ^ rk[kb + 1];

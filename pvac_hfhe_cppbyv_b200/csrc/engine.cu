@@ -96,7 +96,7 @@ static void derive_key_view(Ctx* ctx) {
     kv.H = ctx->d_blob + kBlobHdrWords;
     kv.T0 = ctx->d_aes->t0;
     kv.sbox = ctx->d_aes->sbox;
-    for (int i = 0; i < kLpnWords; i++) ctx->lpn_s.w[i] = h[9 + i];
+    lpn_masks_from_secret(&h[9], ctx->lpn_m);
     ctx->have_keys = true;
 }
 

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "fp127.cuh"
 #include "aes256.cuh"
+#include "prf_core.cuh"
 
 namespace pvacb {
 
@@ -25,9 +26,6 @@ constexpr size_t kBlobHdrWords = 748;
 constexpr size_t kBlobWords = kBlobHdrWords + (size_t)kNBits * kMWords;
 constexpr size_t kBlobBytes = kBlobWords * 8;
 
-struct LpnSecret {
-    uint64_t w[kLpnWords];
-};
 
 struct KeyView {             // passed by value to kernels (pointers into the device blob)
     uint64_t canon_tag;
@@ -55,7 +53,7 @@ struct Ctx {
     uint32_t* h_mail = nullptr;             // mapped pinned "mailbox": kernels drop small results here (see SmallRead)
     uint32_t* d_mail = nullptr;             // device alias of h_mail
     KeyView kv{};
-    LpnSecret lpn_s{};
+    LpnMasks lpn_m{};                // the LPN secret as per-stream-word masks (prf_core.cuh)
     std::vector<uint64_t> h_hdr;     // host copy of the blob header
     int prf_mode = PRF_FAITHFUL;
     std::string last_error;

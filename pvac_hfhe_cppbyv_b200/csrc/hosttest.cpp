@@ -92,12 +92,14 @@ void ht_prf_core(const uint64_t* prf_k, uint64_t canon, const uint8_t* digest, c
     prf_core_setup(mid, d3, tab().t0, tab().sbox, ztag, nlo, nhi, fnv_prf_dom(family, t), rk, ctr0, top0, top1);
     std::vector<uint64_t> y(rows / 64, 0);
     bool rare = false;
+    LpnMasks msk;
+    lpn_masks_from_secret(lpn_s, msk);
     for (int base = 0; base < rows / 2; base += 32) {      // one "warp" = 32 row pairs
         uint32_t be = 0, bo = 0;
         for (int lane = 0; lane < 32; lane++) {
             uint32_t ye, yo;
             uint32_t rp = base + lane;
-            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) { aes256_ctr_block(tab().t0, tab().sbox, rk, c, w0, w1); }, ctr0 + 65ull * rp, lpn_s, ye, yo, rare);
+            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) { aes256_ctr_block(tab().t0, tab().sbox, rk, c, w0, w1); }, ctr0 + 65ull * rp, msk, ye, yo, rare);
             be |= ye << lane; bo |= yo << lane;
         }
         y[base / 32] = spread_bits32(be) | (spread_bits32(bo) << 1);

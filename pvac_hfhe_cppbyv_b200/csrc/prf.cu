@@ -41,7 +41,7 @@ constexpr int kLpnThreads = 512;
 // rpc_log2: log2(row pairs evaluated per core): 13 (all 16384 rows, as the reference) or 6 (rows 0..127, the only ones
 // toep_127 can see). Persistent grid: one CTA per SM, static round-robin over units of kLpnThreads row pairs.
 __global__ void __launch_bounds__(kLpnThreads, 1)
-prf_lpn_kernel(const uint32_t* __restrict__ gT0, const __grid_constant__ LpnSecret sec, uint64_t ncores, int rpc_log2,
+prf_lpn_kernel(const uint32_t* __restrict__ gT0, const __grid_constant__ LpnMasks msk, uint64_t ncores, int rpc_log2,
                const uint32_t* __restrict__ rk_all, const uint64_t* __restrict__ ctr0_all, const uint8_t* __restrict__ flags,
                uint64_t* __restrict__ ybits, unsigned int* __restrict__ rare_flag) {
     extern __shared__ __align__(16) uint8_t sT[];
@@ -64,9 +64,9 @@ prf_lpn_kernel(const uint32_t* __restrict__ gT0, const __grid_constant__ LpnSecr
             AesCtrThread aes;
             aes.load_keys(rk_all + core * 60);
             uint64_t ctr = __ldg(ctr0_all + core) + 65ull * rp;
-            aes.prime(sT, lane4, (uint32_t)(ctr >> 32));
+            aes.prime(sT, lane4, ctr);
             bool rare = false;
-            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) { aes.block(sT, lane4, c, w0, w1); }, ctr, sec.w, ye, yo, rare);
+            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) { aes.block(sT, lane4, c, w0, w1); }, ctr, msk, ye, yo, rare);
             if (rare) atomicOr(rare_flag, 1u);
         }
         uint32_t be = __ballot_sync(0xffffffffu, ye);
@@ -118,7 +118,7 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     unsigned grid = (unsigned)(units < (uint64_t)ctx->sm_count ? units : (uint64_t)ctx->sm_count);
     {
         ProfScope ps(ctx, PROF_PRF_LPN);
-        prf_lpn_kernel<<<grid, kLpnThreads, kAesRepBytes, ctx->stream>>>(ctx->kv.T0, ctx->lpn_s, ncores, rpc_log2, rk, ctr0, d_flags, ybits, rare);
+        prf_lpn_kernel<<<grid, kLpnThreads, kAesRepBytes, ctx->stream>>>(ctx->kv.T0, ctx->lpn_m, ncores, rpc_log2, rk, ctr0, d_flags, ybits, rare);
     }
     prf_finalize_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, ctx->stream>>>(njobs, d_flags, ybits, wpc, top, d_out);
     PV_CUDA(cudaGetLastError());

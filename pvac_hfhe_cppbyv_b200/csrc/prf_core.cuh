@@ -38,29 +38,39 @@ PV_HD void prf_core_setup(const uint32_t kd_mid[8], uint64_t digest3, const uint
     ctr0 = domhash ^ nlo;
 }
 
-// LPN rows 2p and 2p+1 (crypto/lpn.hpp:219-232): 130 stream words = AES blocks ctr..ctr+64. blk(counter, w0, w1) yields
-// one keystream block. s = the 64 secret words. Returns the two y bits; `rare` is set if bounded(8) would have rejected.
+// LPN rows 2p and 2p+1 (crypto/lpn.hpp:219-232): 130 stream words = AES blocks ctr..ctr+64. Word w of that span belongs to the
+// even row's dot product (w < 64, with s[w]), is its noise word (w = 64), belongs to the odd row's dot product
+// (65 <= w < 129, with s[w-65]) or is the odd row's noise word (w = 129). The two dot products are written as ONE loop over
+// the 65 blocks with per-word masks (e[w] = s[w] or 0, o[w] = s[w-65] or 0): a single small loop body instead of four
+// specialised ones keeps the kernel inside the instruction cache (ncu r01: 0.59 no_instruction stalls per issue with the
+// unrolled form). The masks sit in the kernel parameter bank and are read with a warp-uniform index.
+struct LpnMasks {
+    uint64_t e[130];
+    uint64_t o[130];
+};
+inline void lpn_masks_from_secret(const uint64_t s[kLpnWords], LpnMasks& m) {
+    for (int w = 0; w < 130; w++) {
+        m.e[w] = w < 64 ? s[w] : 0ull;
+        m.o[w] = (w >= 65 && w < 129) ? s[w - 65] : 0ull;
+    }
+}
+
+// blk(counter, w0, w1) yields one keystream block. Returns the two y bits; `rare` is set if bounded(8) would have rejected.
 template <class BlockFn>
-PV_HD void lpn_row_pair(BlockFn&& blk, uint64_t ctr, const uint64_t* __restrict__ s, uint32_t& ye, uint32_t& yo, bool& rare) {
-    uint64_t accE = 0, accO = 0, w0, w1;
-#pragma unroll 2
-    for (int q = 0; q < 32; q++) {                // even row: its 64 words are blocks 0..31
+PV_HD void lpn_row_pair(BlockFn&& blk, uint64_t ctr, const LpnMasks& m, uint32_t& ye, uint32_t& yo, bool& rare) {
+    uint64_t accE = 0, accO = 0, nwE = 0, nwO = 0;
+#pragma unroll 1
+    for (int q = 0; q < 65; q++) {
+        uint64_t w0, w1;
         blk(ctr + q, w0, w1);
-        accE ^= (w0 & s[2 * q]) ^ (w1 & s[2 * q + 1]);
+        accE ^= (w0 & m.e[2 * q]) ^ (w1 & m.e[2 * q + 1]);
+        accO ^= (w0 & m.o[2 * q]) ^ (w1 & m.o[2 * q + 1]);
+        if (q == 32) nwE = w0;      // stream word 64: noise word of the even row
+        if (q == 64) nwO = w1;      // stream word 129: noise word of the odd row
     }
-    blk(ctr + 32, w0, w1);                         // block 32: noise word of the even row | word 0 of the odd row
-    uint32_t nE = ((uint32_t)w0 & 7u) == 0u;       // bounded(8) < 1  (crypto/lpn.hpp:141-148,228)
-    rare |= w0 >= 0xFFFFFFFFFFFFFFF8ull;            // rejection branch of bounded(): would shift the whole stream
-    accO ^= w1 & s[0];
-#pragma unroll 2
-    for (int j = 0; j < 31; j++) {                 // blocks 33..63: odd-row words 1+2j, 2+2j
-        blk(ctr + 33 + j, w0, w1);
-        accO ^= (w0 & s[1 + 2 * j]) ^ (w1 & s[2 + 2 * j]);
-    }
-    blk(ctr + 64, w0, w1);                         // block 64: odd-row word 63 | noise word of the odd row
-    accO ^= w0 & s[63];
-    uint32_t nO = ((uint32_t)w1 & 7u) == 0u;
-    rare |= w1 >= 0xFFFFFFFFFFFFFFF8ull;
+    const uint32_t nE = ((uint32_t)nwE & 7u) == 0u;        // bounded(8) < 1  (crypto/lpn.hpp:141-148,228)
+    const uint32_t nO = ((uint32_t)nwO & 7u) == 0u;
+    rare |= (nwE >= 0xFFFFFFFFFFFFFFF8ull) | (nwO >= 0xFFFFFFFFFFFFFFF8ull);   // rejection branch of bounded(): would shift the whole stream
 #if defined(__CUDA_ARCH__)
     ye = (__popcll(accE) & 1) ^ nE;
     yo = (__popcll(accO) & 1) ^ nO;

@@ -61,30 +61,49 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """nvidia-smi in loop mode (one process, a sample every 50 ms), time-stamped; summary() over a window of the run."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.proc = gpu, [], None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in o.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for ln in self.proc.stdout:
+                parts = [x.strip() for x in ln.strip().split(",")]
                 if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.2)
+                    self.rows.append((time.perf_counter(), parts))
+        except Exception:
+            pass
 
-    def summary(self):
-        if not self.rows:
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0=None, t1=None):
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(float(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(float(r[2]) for r in self.rows),
-                "samples": len(self.rows), "reasons": reasons}
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def concat_traffic(pairs):
+    """DRAM bytes per concat_kernel launch from the committed ncu capture (read + write per pair x pairs), or None"""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        c = json.load(f).get("concat_kernel")
+    if not c:
+        return None
+    return (c["dram_read_bytes"] + c["dram_write_bytes"]) / c["pairs"] * pairs
 
 
 def cpu_threads():
@@ -134,7 +153,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="ciphertext pairs per GPU per step (headline ct_mul tile)")
@@ -240,10 +259,12 @@ def main():
     eng.stats_reset()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(0.3)                                  # let the sampler come up before the timed region
     out_edges.clear()
+    t_head0 = time.perf_counter()
     secs = timed(step_mul, args.steps, 0)
+    t_head1 = time.perf_counter()
     prof = eng.profile_collect()
-    sampler.stop_flag = True
     st = eng.stats()
     eng.profile_enable(False)
     value = world * M * args.steps / secs
@@ -375,7 +396,7 @@ def main():
             ach = add_bytes * 5 / (kms_timed * 1e-3) / 1e9
             ops[name] = {"value": rate, "unit": name + "/s", "pairs_per_step_per_gpu": n_add, "ms_per_step": spp * 1e3,
                          "roofline": {"kernel": "concat_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                      "algorithmic_bytes_per_launch": add_bytes, "peak_source": peak_src}}
+                                      "algorithmic_bytes_per_launch": add_bytes, "peak_source": peak_src, "traffic": concat_traffic(n_add)}}
         SA.free(); SB.free()
 
         # enc_value: faithful PRF (all 16384 LPN rows, like the reference) and live-row PRF (rows 0..127, same bits)
@@ -434,6 +455,9 @@ def main():
                 ko.ct_mul(3 + i, a, b)
             cpu = {"value": 8 / (time.perf_counter() - t0), "unit": "ct_mul/s", "cores": 1, "kind": "port", "sample": "8 ct_mul fresh x fresh, oracle C port, 1 thread"}
 
+    sampler.stop()
+    clocks = sampler.summary(t_head0, t_head1)       # during the headline's timed region
+    clocks["whole_run"] = sampler.summary()          # and over everything after it (e2e, the other ops, faithful PRF under load)
     if rank == 0:
         line = {
             "metric": "ct_mul/s", "value": value, "unit": "ct_mul/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -443,7 +467,7 @@ def main():
                        "pairs_per_step_per_gpu": M, "out_edges_per_step_per_gpu": edges_per_step, "input_bytes_resident": in_bytes,
                        "l2": "inputs (%.0f MB) and outputs (%.1f GB per step) exceed the 126 MB L2; the 16 MiB matrix H is meant to be L2 resident" % (in_bytes / 1e6, edges_per_step * 1052 / 1e9),
                        "sharding": f"batch index, {world} rank(s), keys replicated by one NCCL broadcast, no steady-state collective", "prf_mode_for_inputs": "live"},
-            "e2e": e2e, "gpu_launches": st["kernel_launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(), "ops": ops,
+            "e2e": e2e, "gpu_launches": st["kernel_launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "ops": ops,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

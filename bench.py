@@ -33,7 +33,8 @@ EDGE_WIRE_BYTES = 1052          # serialised edge (tests/bounty2_test.cpp:98-106
 GATHER_BYTES_PER_EDGE = 128 * 1024
 SHA_PER_EDGE = 70               # 2 midstates + 2 x 34 counter hashes (csrc/sigma.cu)
 AES_LDS_PER_BLOCK = 197         # T-table lookups per AES-256 block after hoisting rounds 1-2 (csrc/aes256.cuh)
-SHA_ALU_INSTR = 1240            # SHF + LOP3 + IADD3 of one unrolled compression
+ALU_LANE_OPS_PER_S = 18.55e12    # measured LOP3/SHF/PRMT rate of this GPU (profiles/micro/int_pipes.cu): 63.8 lanes/clk/SM
+SHA_ALU_INSTR = 1248            # SHF + LOP3 + IADD3 of one unrolled compression
 
 
 def mix64(z):
@@ -274,7 +275,7 @@ def main():
     achieved = gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
     sha_rate = edges_per_step * args.steps * SHA_PER_EDGE / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
     # second ceiling of the same kernel: the SHA-256 counter PRG on the ALU pipe (SHF/LOP3/IADD3: 64 lanes/clk/SM)
-    alu_peak = 148 * 64 * 1.965 / SHA_ALU_INSTR
+    alu_peak = ALU_LANE_OPS_PER_S / 1e9 / SHA_ALU_INSTR
     roofline = {
         "kernel": "sigma_fused_kernel", "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
         "traffic": None,
@@ -283,7 +284,7 @@ def main():
         "kernel_ms_per_step": gather_ms / args.steps, "share_of_step": gather_ms * 1e-3 / secs,
         "hbm_write_gbs": edges_per_step * args.steps * 1024 / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0, "hbm_peak": hbm_peak, "hbm_peak_source": peak_src,
         "alu": {"achieved": sha_rate, "unit": "G SHA-256 compressions/s", "peak": alu_peak, "frac": sha_rate / alu_peak,
-                "peak_source": f"model: {SHA_ALU_INSTR} ALU-pipe instructions per compression (cuobjdump), 64 lanes/clk/SM, 148 SMs at 1965 MHz",
+                "peak_source": f"{SHA_ALU_INSTR} ALU-pipe instructions per compression (cuobjdump) at the measured ALU-pipe rate of 18.55 T lane-ops/s (profiles/r01_int_pipes.txt; sha_variants.cu reaches 15.2 G/s standalone)",
                 "compressions_per_edge": SHA_PER_EDGE},
     }
     ncu_path = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")

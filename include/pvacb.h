@@ -101,6 +101,9 @@ int pvacb_enc_value_ex(pvacb_ctx* ctx, const uint64_t* values, size_t n, uint64_
 int pvacb_enc_value_depth(pvacb_ctx* ctx, const uint64_t* values, size_t n, int depth_hint, uint64_t batch_seed, const uint64_t* tape_states,
                           pvacb_batch** out);
 int pvacb_enc_zero_depth(pvacb_ctx* ctx, size_t n, int depth_hint, uint64_t batch_seed, const uint64_t* tape_states, pvacb_batch** out);
+/* Cipher enc_fp_depth(pk, sk, Fp v, depth_hint)             ops/encrypt.hpp:162  (one share: 1 BASE layer; fp_values = n x (lo, hi), canonical) */
+int pvacb_enc_fp_depth(pvacb_ctx* ctx, const uint64_t* fp_values, size_t n, int depth_hint, uint64_t batch_seed, const uint64_t* tape_states,
+                       pvacb_batch** out);
 /* std::pair<int,int> plan_noise(pk, depth_hint)            ops/encrypt.hpp:16 */
 int pvacb_plan_noise(int depth_hint, int* z2, int* z3);
 /* Cipher ct_add / ct_sub(pk, A, B)                        ops/arithmetic.hpp:12,43 */

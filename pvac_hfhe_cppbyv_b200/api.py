@@ -41,7 +41,7 @@ SYMBOLS = [
     "pvacb_batch_import_wire", "pvacb_batch_synthetic", "pvacb_prf", "pvacb_sigma_from_H", "pvacb_fp_op",
     "pvacb_profile_enable", "pvacb_profile_collect", "pvacb_keys_copy_blob_to", "pvacb_keys_adopt_blob_from", "pvacb_l2_gather_probe",
     "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges", "pvacb_batch_checksum", "pvacb_commit_ct",
-    "pvacb_enc_value_depth", "pvacb_enc_zero_depth", "pvacb_plan_noise", "pvacb_ct_neg", "pvacb_ct_div_const",
+    "pvacb_enc_value_depth", "pvacb_enc_zero_depth", "pvacb_plan_noise", "pvacb_ct_neg", "pvacb_ct_div_const", "pvacb_enc_fp_depth",
 ]
 
 
@@ -115,6 +115,7 @@ def load_library():
         "pvacb_commit_ct": (i32, [vp, vp, P(u8)]),
         "pvacb_enc_value_depth": (i32, [vp, P(u64), sz, i32, u64, P(u64), P(vp)]),
         "pvacb_enc_zero_depth": (i32, [vp, sz, i32, u64, P(u64), P(vp)]),
+        "pvacb_enc_fp_depth": (i32, [vp, P(u64), sz, i32, u64, P(u64), P(vp)]),
         "pvacb_plan_noise": (i32, [i32, P(i32), P(i32)]),
         "pvacb_ct_neg": (i32, [vp, vp, P(vp)]),
         "pvacb_ct_div_const": (i32, [vp, vp, P(u64), P(vp)]),
@@ -302,6 +303,14 @@ class Engine:
         st = _u64(tape_states) if tape_states is not None else None
         out = C.c_void_p()
         self._ck(self.L.pvacb_enc_value_depth(self.h, _p(v, C.c_uint64), len(v), depth_hint, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        return Batch(self, out)
+
+    def enc_fp_depth(self, fp_values, depth_hint=0, batch_seed=0, tape_states=None):
+        """fp_values: (n, 2) uint64 canonical field elements -> one-share ciphertexts (enc_fp_depth, ops/encrypt.hpp:162)"""
+        v = np.ascontiguousarray(fp_values, np.uint64).reshape(-1, 2)
+        st = _u64(tape_states) if tape_states is not None else None
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_enc_fp_depth(self.h, _p(v, C.c_uint64), len(v), depth_hint, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
         return Batch(self, out)
 
     def enc_zero_depth(self, n, depth_hint, batch_seed=0, tape_states=None):

@@ -20,20 +20,22 @@ namespace pvacb {
 
 // share s = 0 is enc_fp_depth(-mask) (drawn first, becomes layer 1 / the trailing edges), s = 1 is enc_fp_depth(v+mask)
 __global__ void enc_plan_kernel(uint64_t n, const uint64_t* __restrict__ values, uint64_t batch_seed, const uint64_t* __restrict__ states,
-                                uint64_t canon_tag, int Z2, int Z3,
+                                uint64_t canon_tag, int Z2, int Z3, int S,
                                 SharePlan* __restrict__ plans, uint32_t* __restrict__ n_edges, uint32_t* __restrict__ n_extra,
                                 uint64_t* __restrict__ j_ztag, uint64_t* __restrict__ j_nlo, uint64_t* __restrict__ j_nhi, uint8_t* __restrict__ j_flags) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    plan_item(states ? states[i] : item_stream_state(batch_seed, i), values[i], canon_tag, Z2, Z3, plans[2 * i], plans[2 * i + 1]);
+    const uint64_t s0 = states ? states[i] : item_stream_state(batch_seed, i);
+    if (S == 2) plan_item(s0, values[i], canon_tag, Z2, Z3, plans[2 * i], plans[2 * i + 1]);
+    else plan_single(s0, fp_make(values[2 * i], values[2 * i + 1]), canon_tag, Z2, Z3, plans[i]);     // enc_fp_depth: values are Fp (lo, hi)
     const int G = Z2 + Z3;
     uint32_t edges = 0, extra = 0;
-    for (int s = 0; s < 2; s++) {
-        const SharePlan& P = plans[2 * i + s];
+    for (int s = 0; s < S; s++) {
+        const SharePlan& P = plans[S * i + s];
         edges += P.n_out;
         extra += P.n_raw - P.n_out;
         // PRF jobs of the share: prf_R(seed), then prf_noise_delta(seed, gid, kind) for all but the last group
-        uint64_t jb = (2 * i + s) * (uint64_t)G;
+        uint64_t jb = ((uint64_t)S * i + s) * (uint64_t)G;
         j_ztag[jb] = P.ztag; j_nlo[jb] = P.nlo; j_nhi[jb] = P.nhi; j_flags[jb] = 2;
         for (int gid = 0; gid + 1 < G; gid++) {
             uint64_t g = (uint64_t)gid + 1, k = (gid < Z2 ? 0ull : 1ull) + 1;   // ops/encrypt.hpp:114-129
@@ -48,24 +50,24 @@ __global__ void enc_plan_kernel(uint64_t n, const uint64_t* __restrict__ values,
 }
 
 // thread per share: layers, final edge fields, sigma jobs
-__global__ void enc_emit_kernel(uint64_t n, const SharePlan* __restrict__ plans, const uint32_t* __restrict__ eoff, const uint32_t* __restrict__ xoff,
+__global__ void enc_emit_kernel(uint64_t n, int S, const SharePlan* __restrict__ plans, const uint32_t* __restrict__ eoff, const uint32_t* __restrict__ xoff,
                                 uint64_t nE_total, uint32_t* __restrict__ b_loff, uint8_t* __restrict__ b_rule, uint64_t* __restrict__ b_ztag,
                                 uint64_t* __restrict__ b_nlo, uint64_t* __restrict__ b_nhi, uint32_t* __restrict__ b_pa, uint32_t* __restrict__ b_pb,
                                 uint32_t* __restrict__ b_lid, uint16_t* __restrict__ b_idx, uint8_t* __restrict__ b_ch, int RAW,
                                 uint32_t* __restrict__ s_seed, uint16_t* __restrict__ s_idx, uint8_t* __restrict__ s_ch, uint64_t* __restrict__ s_salt,
                                 uint32_t* __restrict__ s_row, uint2* __restrict__ fix_pairs) {
     uint64_t sh = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (sh >= 2 * n) return;
-    uint64_t i = sh >> 1;
-    int s = (int)(sh & 1);
+    if (sh >= (uint64_t)S * n) return;
+    uint64_t i = sh / S;
+    int s = (int)(sh % S);
     const SharePlan& P = plans[sh];
-    const SharePlan& Pa = plans[2 * i + 1];
-    uint32_t layer = s == 1 ? 0u : 1u;                       // combine_ciphers(enc(v+mask), enc(-mask)), ops/encrypt.hpp:284-286
-    uint64_t L = 2 * i + layer;
+    const SharePlan& Pa = plans[S * i + (S - 1)];            // the share that becomes layer 0
+    uint32_t layer = (S == 1 || s == 1) ? 0u : 1u;           // combine_ciphers(enc(v+mask), enc(-mask)), ops/encrypt.hpp:284-286
+    uint64_t L = (uint64_t)S * i + layer;
     b_rule[L] = 0; b_ztag[L] = P.ztag; b_nlo[L] = P.nlo; b_nhi[L] = P.nhi; b_pa[L] = 0; b_pb[L] = 0;
-    if (s == 0) { b_loff[i] = (uint32_t)(2 * i); if (i == n - 1) b_loff[n] = (uint32_t)(2 * n); }
-    uint32_t e0 = eoff[i] + (s == 1 ? 0u : Pa.n_out);
-    uint32_t x = xoff[i] + (s == 1 ? 0u : (uint32_t)(Pa.n_raw - Pa.n_out));
+    if (s == 0) { b_loff[i] = (uint32_t)(S * i); if (i == n - 1) b_loff[n] = (uint32_t)(S * n); }
+    uint32_t e0 = eoff[i] + (layer == 0 ? 0u : Pa.n_out);
+    uint32_t x = xoff[i] + (layer == 0 ? 0u : (uint32_t)(Pa.n_raw - Pa.n_out));
     for (int r = 0; r < P.n_raw; r++) {
         uint64_t j = sh * (uint64_t)RAW + r;
         uint32_t row = e0 + P.pos[r];
@@ -82,16 +84,16 @@ __global__ void enc_emit_kernel(uint64_t n, const SharePlan* __restrict__ plans,
 }
 
 // thread per share: weights (ops/encrypt.hpp:184-252), merged per slot
-__global__ void enc_weights_kernel(uint64_t n, const SharePlan* __restrict__ plans, const uint32_t* __restrict__ eoff, const Fp* __restrict__ prf,
+__global__ void enc_weights_kernel(uint64_t n, int S, const SharePlan* __restrict__ plans, const uint32_t* __restrict__ eoff, const Fp* __restrict__ prf,
                                    const Fp* __restrict__ powg, int Z2, int Z3, Fp* __restrict__ b_w, unsigned int* __restrict__ err) {
     uint64_t sh = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (sh >= 2 * n) return;
-    uint64_t i = sh >> 1;
-    int s = (int)(sh & 1);
+    if (sh >= (uint64_t)S * n) return;
+    uint64_t i = sh / S;
+    int s = (int)(sh % S);
     const SharePlan& P = plans[sh];
     Fp wsum[kMaxRaw];
     if (!share_weights(P, prf + sh * (uint64_t)(Z2 + Z3), powg, Z2, Z3, wsum)) atomicOr(err, 1u);
-    uint32_t e0 = eoff[i] + (s == 1 ? 0u : plans[2 * i + 1].n_out);
+    uint32_t e0 = eoff[i] + ((S == 1 || s == 1) ? 0u : plans[2 * i + 1].n_out);
     for (int p = 0; p < P.n_out; p++) b_w[e0 + p] = wsum[p];
 }
 
@@ -105,7 +107,10 @@ void plan_noise_host(int depth_hint, int& z2, int& z3) {
     if (z2 + z3 == 1) { z3 > 0 ? ++z3 : ++z2; }
 }
 
-int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint) {
+// shares = 2: enc_value_depth (values: n u64 plaintexts); shares = 1: enc_fp_depth (values: n x (lo, hi) field elements)
+int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint, int shares) {
+    const uint64_t S = (uint64_t)shares;
+    if (shares != 1 && shares != 2) return PV_E_ARG;
     int Z2, Z3;
     plan_noise_host(depth_hint, Z2, Z3);
     const int G = Z2 + Z3, RAW = kSignal + 2 * Z2 + 3 * Z3;
@@ -118,16 +123,17 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     uint64_t *j_ztag = nullptr, *j_nlo = nullptr, *j_nhi = nullptr;
     uint8_t* j_flags = nullptr;
     Fp* prf = nullptr;
-    const uint64_t njobs = 2 * n * G;
+    const uint64_t njobs = S * n * G;
     if (!on_device) {
-        if ((rc = dev_alloc(ctx, (void**)&d_vals, n * 8))) return rc;
-        PV_CUDA(cudaMemcpyAsync(d_vals, values, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const size_t vbytes = n * (shares == 2 ? 8 : 16);
+        if ((rc = dev_alloc(ctx, (void**)&d_vals, vbytes))) return rc;
+        PV_CUDA(cudaMemcpyAsync(d_vals, values, vbytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (h_states) {
         if ((rc = dev_alloc(ctx, (void**)&d_states, n * 8))) return rc;
         PV_CUDA(cudaMemcpyAsync(d_states, h_states, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if ((rc = dev_alloc(ctx, (void**)&plans, 2 * n * sizeof(SharePlan)))) return rc;
+    if ((rc = dev_alloc(ctx, (void**)&plans, S * n * sizeof(SharePlan)))) return rc;
     if ((rc = dev_alloc(ctx, (void**)&cnt, n * 4))) return rc;
     if ((rc = dev_alloc(ctx, (void**)&xcnt, n * 4))) return rc;
     if ((rc = dev_alloc(ctx, (void**)&eoff, (n + 1) * 4))) return rc;
@@ -137,7 +143,7 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     if ((rc = dev_alloc(ctx, (void**)&j_nhi, njobs * 8))) return rc;
     if ((rc = dev_alloc(ctx, (void**)&j_flags, njobs))) return rc;
     if ((rc = dev_alloc(ctx, (void**)&prf, njobs * 16))) return rc;
-    enc_plan_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, on_device ? values : d_vals, batch_seed, d_states, ctx->kv.canon_tag, Z2, Z3, plans, cnt, xcnt,
+    enc_plan_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, on_device ? values : d_vals, batch_seed, d_states, ctx->kv.canon_tag, Z2, Z3, shares, plans, cnt, xcnt,
                                                                         j_ztag, j_nlo, j_nhi, j_flags);
     if ((rc = scan_u32(ctx, n, cnt, eoff))) return rc;
     if ((rc = scan_u32(ctx, n, xcnt, xoff))) return rc;
@@ -147,8 +153,8 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     const uint64_t nE = tot[0], nX = tot[1];
 
     Batch* b = nullptr;
-    if ((rc = batch_alloc(ctx, n, 2 * n, nE, &b))) return rc;
-    uint64_t nS = 2 * n * (uint64_t)RAW;
+    if ((rc = batch_alloc(ctx, n, S * n, nE, &b))) return rc;
+    uint64_t nS = S * n * (uint64_t)RAW;
     uint32_t *s_seed = nullptr, *s_row = nullptr;
     uint16_t* s_idx = nullptr;
     uint8_t* s_ch = nullptr;
@@ -165,12 +171,12 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     if ((rc = dev_alloc(ctx, (void**)&err, 4))) return rc;
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
     PV_CUDA(cudaMemcpyAsync(b->eoff, eoff, (n + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    enc_emit_kernel<<<(unsigned)((2 * n + 127) / 128), 128, 0, ctx->stream>>>(n, plans, eoff, xoff, nE, b->loff, b->rule, b->ztag, b->nlo, b->nhi, b->pa, b->pb,
+    enc_emit_kernel<<<(unsigned)((S * n + 127) / 128), 128, 0, ctx->stream>>>(n, shares, plans, eoff, xoff, nE, b->loff, b->rule, b->ztag, b->nlo, b->nhi, b->pa, b->pb,
                                                                                b->lid, b->idx, b->ch, RAW, s_seed, s_idx, s_ch, s_salt, s_row, fix);
     ctx->stat_kernel_launches += 1;
     // PRF (R of each share, noise deltas)
     if ((rc = prf_run(ctx, njobs, j_ztag, j_nlo, j_nhi, j_flags, prf, nullptr))) { batch_free(b); return rc; }
-    enc_weights_kernel<<<(unsigned)((2 * n + 63) / 64), 64, 0, ctx->stream>>>(n, plans, eoff, prf, ctx->kv.powg, Z2, Z3, b->w, err);
+    enc_weights_kernel<<<(unsigned)((S * n + 63) / 64), 64, 0, ctx->stream>>>(n, shares, plans, eoff, prf, ctx->kv.powg, Z2, Z3, b->w, err);
     ctx->stat_kernel_launches += 1;
     // sigma of every raw edge
     SigmaJobs J;

@@ -161,4 +161,12 @@ PV_HD uint64_t plan_item(uint64_t s0, uint64_t v, uint64_t canon_tag, int Z2, in
     return t.k;
 }
 
+// enc_fp_depth alone (ops/encrypt.hpp:162-258): one share, no mask; the tape starts at the nonce
+PV_HD uint64_t plan_single(uint64_t s0, Fp v, uint64_t canon_tag, int Z2, int Z3, SharePlan& P) {
+    Tape t{s0, 0};
+    P.value = v;
+    plan_share(t, P, canon_tag, Z2, Z3);
+    return t.k;
+}
+
 }  // namespace pvacb

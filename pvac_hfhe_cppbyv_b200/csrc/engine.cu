@@ -342,6 +342,21 @@ int pvacb_enc_value_depth(pvacb_ctx* x, const uint64_t* values, size_t n, int de
     *out = reinterpret_cast<pvacb_batch*>(b);
     return rc;
 }
+// enc_fp_depth (ops/encrypt.hpp:162): one share per item, 1 BASE layer, 8 + 2 Z2 + 3 Z3 edges; values are field elements (lo, hi)
+int pvacb_enc_fp_depth(pvacb_ctx* x, const uint64_t* fp_values, size_t n, int depth_hint, uint64_t seed, const uint64_t* tape_states, pvacb_batch** out) {
+    Ctx* ctx = C(x);
+    if (!out || (n && !fp_values)) return PV_E_ARG;
+    if (!ctx->have_keys) return PV_E_NOKEYS;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t lo = fp_values[2 * i], hi = fp_values[2 * i + 1];
+        if ((hi >> 63) || (hi == kMask63 && lo == ~0ull)) { ctx->last_error = "enc_fp_depth: value not a canonical field element"; return PV_E_ARG; }
+    }
+    cudaSetDevice(ctx->device);
+    Batch* b = nullptr;
+    int rc = op_enc_value(ctx, fp_values, false, n, seed, tape_states, &b, depth_hint, 1);
+    *out = reinterpret_cast<pvacb_batch*>(b);
+    return rc;
+}
 // enc_zero_depth draws the mask and both shares exactly like enc_value_depth(0, depth): fp_add(0, mask) == mask
 int pvacb_enc_zero_depth(pvacb_ctx* x, size_t n, int depth_hint, uint64_t seed, const uint64_t* tape_states, pvacb_batch** out) {
     std::vector<uint64_t> zeros(n ? n : 1, 0);

@@ -456,3 +456,21 @@ def test_depth_hints_and_riders_vs_oracle(engine, api, port, port_keys):
         assert ct_equal(gn[i], port.ct_export(K.ct_neg(oa[i])))[0]
         assert ct_equal(gd[i], port.ct_export(K.ct_div_const(oa[i], [7, 0])))[0]
     assert [fpv(x) for x in engine.dec_value(engine.ct_div_const(A, [7, 0]))] == [11, 13]
+
+
+def test_enc_fp_depth_vs_oracle(engine, api, port, port_keys):
+    """pvacb_enc_fp_depth (one share, ops/encrypt.hpp:162-258) for full-width field elements and depth hints"""
+    K = port_keys
+    vals = [5, P127 - 1, (1 << 126) + 12345, 0]
+    fpv_in = np.array([[v & (2**64 - 1), v >> 64] for v in vals], np.uint64)
+    for depth in (0, 2, 5):
+        X = engine.enc_fp_depth(fpv_in, depth, 8600 + depth)
+        assert X.totals()[0] == len(vals)                                 # one BASE layer each
+        got = api.split_items(engine.export_soa(X))
+        for i, v in enumerate(vals):
+            want = port.ct_export(K.enc_fp_depth(port.item_stream_state(8600 + depth, i), fpv_in[i], depth))
+            ok, f = ct_equal(got[i], want)
+            assert ok, (depth, i, f)
+        assert [fpv(x) for x in engine.dec_value(X)] == vals
+    with pytest.raises(api.PvacbError):
+        engine.enc_fp_depth(np.array([[2**64 - 1, 2**63 - 1]], np.uint64), 0, 1)      # p itself is not canonical

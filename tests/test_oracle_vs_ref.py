@@ -193,6 +193,11 @@ def test_depth_hints_and_riders(port, ref, both):
         # enc_zero_depth(d) and enc_value_depth(0, d) consume the tape identically
         ok, _ = ct_equal(port.ct_export(zo), port.ct_export(ko.enc_value_depth(700 + depth, 0, depth)))
         assert ok
+    for depth, v in ((0, 5), (2, P - 1), (5, (1 << 126) + 12345)):          # enc_fp_depth alone: one share, full-width field element
+        fo, fr = ko.enc_fp_depth(800 + depth, _w(v), depth), kr.enc_fp_depth(800 + depth, _w(v), depth)
+        ok, k = ct_equal(port.ct_export(fo), ref.ct_export(fr))
+        assert ok, (depth, k)
+        assert _v(ko.dec_value(fo)) == v
     ao, ar = ko.enc_value(41, 77), kr.enc_value(41, 77)
     assert ct_equal(port.ct_export(ko.ct_neg(ao)), ref.ct_export(kr.ct_neg(ar)))[0]
     k7 = _w(7)

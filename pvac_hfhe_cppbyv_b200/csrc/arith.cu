@@ -102,11 +102,12 @@ concat_kernel(BatchView A, BatchView B, int mode, uint32_t* __restrict__ o_loff,
 }
 
 int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode, Batch** out) {
+    Scratch scratch(ctx);
     Batch* o = nullptr;
     int rc = batch_alloc(ctx, A->n, A->nL + B->nL, A->nE + B->nE, &o);
     if (rc) return rc;
     unsigned int* err = nullptr;
-    if ((rc = dev_alloc(ctx, (void**)&err, 4))) { batch_free(o); return rc; }
+    if ((rc = scratch.alloc(err, 4))) { batch_free(o); return rc; }
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
     uint64_t n = A->n;
     concat_offsets_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->loff, B->loff, A->eoff, B->eoff, o->loff, o->eoff, err);
@@ -122,8 +123,7 @@ int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode, Batch** out) {
     PV_CUDA(cudaGetLastError());
     ctx->stat_kernel_launches += n ? 2 : 1;
     unsigned int h_err = 0;
-    { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
-    dev_free(ctx, err);
+    { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) { batch_free(o); return rc; } }
     if (h_err) {       // guard_budget(pk, C, "add") -> compact_edges, ops/arithmetic.hpp:28
         if ((rc = guard_budget_batch(ctx, &o))) { batch_free(o); return rc; }
     }
@@ -253,12 +253,13 @@ layers_remap_kernel(const uint32_t* __restrict__ loff, const uint32_t* __restric
 // compact_layers of every ciphertext of b, in place (layer arrays shrink; edge arrays keep their place).
 int compact_layers_batch(Ctx* ctx, Batch* b) {
     if (b->n == 0 || b->nL == 0) return PV_OK;
+    Scratch scratch(ctx);
     uint8_t* used = nullptr;
     uint32_t *cnt = nullptr, *noff = nullptr;
     int rc;
-    if ((rc = dev_alloc(ctx, (void**)&used, b->nL))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&cnt, b->n * 4))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&noff, (b->n + 1) * 4))) return rc;
+    if ((rc = scratch.alloc(used, b->nL))) return rc;
+    if ((rc = scratch.alloc(cnt, b->n * 4))) return rc;
+    if ((rc = scratch.alloc(noff, (b->n + 1) * 4))) return rc;
     PV_CUDA(cudaMemsetAsync(used, 0, b->nL, ctx->stream));
     layers_mark_kernel<<<(unsigned)b->n, 128, 0, ctx->stream>>>(b->n, b->loff, b->eoff, b->rule, b->pa, b->pb, b->lid, used, cnt, nullptr);
     if ((rc = scan_u32(ctx, b->n, cnt, noff))) return rc;
@@ -270,13 +271,13 @@ int compact_layers_batch(Ctx* ctx, Batch* b) {
         uint8_t* t_rule = nullptr;
         uint64_t *t_ztag = nullptr, *t_nlo = nullptr, *t_nhi = nullptr;
         uint32_t *t_pa = nullptr, *t_pb = nullptr;
-        if ((rc = dev_alloc(ctx, (void**)&remap, b->nL * 4))) return rc;
-        if ((rc = dev_alloc(ctx, (void**)&t_rule, total))) return rc;
-        if ((rc = dev_alloc(ctx, (void**)&t_ztag, (size_t)total * 8))) return rc;
-        if ((rc = dev_alloc(ctx, (void**)&t_nlo, (size_t)total * 8))) return rc;
-        if ((rc = dev_alloc(ctx, (void**)&t_nhi, (size_t)total * 8))) return rc;
-        if ((rc = dev_alloc(ctx, (void**)&t_pa, (size_t)total * 4))) return rc;
-        if ((rc = dev_alloc(ctx, (void**)&t_pb, (size_t)total * 4))) return rc;
+        if ((rc = scratch.alloc(remap, b->nL * 4))) return rc;
+        if ((rc = scratch.alloc(t_rule, total))) return rc;
+        if ((rc = scratch.alloc(t_ztag, (size_t)total * 8))) return rc;
+        if ((rc = scratch.alloc(t_nlo, (size_t)total * 8))) return rc;
+        if ((rc = scratch.alloc(t_nhi, (size_t)total * 8))) return rc;
+        if ((rc = scratch.alloc(t_pa, (size_t)total * 4))) return rc;
+        if ((rc = scratch.alloc(t_pb, (size_t)total * 4))) return rc;
         layers_remap_kernel<<<(unsigned)b->n, 128, 0, ctx->stream>>>(b->loff, b->eoff, noff, used, remap, b->rule, b->ztag, b->nlo, b->nhi, b->pa, b->pb,
                                                                       t_rule, t_ztag, t_nlo, t_nhi, t_pa, t_pb, b->lid);
         PV_CUDA(cudaMemcpyAsync(b->rule, t_rule, total, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -289,9 +290,7 @@ int compact_layers_batch(Ctx* ctx, Batch* b) {
         PV_CUDA(cudaGetLastError());
         ctx->stat_kernel_launches += 1;
         b->nL = total;
-        dev_free(ctx, remap); dev_free(ctx, t_rule); dev_free(ctx, t_ztag); dev_free(ctx, t_nlo); dev_free(ctx, t_nhi); dev_free(ctx, t_pa); dev_free(ctx, t_pb);
     }
-    dev_free(ctx, used); dev_free(ctx, cnt); dev_free(ctx, noff);
     return PV_OK;
 }
 

@@ -93,16 +93,17 @@ dec_edges_kernel(uint64_t n, const uint32_t* __restrict__ loff, const uint32_t* 
 
 int op_dec_value(Ctx* ctx, const Batch* Cb, uint64_t* h_out) {
     if (Cb->n == 0) return PV_OK;
+    Scratch scratch(ctx);
     int rc;
     uint8_t* flags = nullptr;
     Fp *R = nullptr, *Rinv = nullptr, *res = nullptr;
     unsigned int* err = nullptr;
     uint64_t nLa = Cb->nL ? Cb->nL : 1;
-    if ((rc = dev_alloc(ctx, (void**)&flags, nLa))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&R, nLa * 16))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&Rinv, nLa * 16))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&res, Cb->n * 16))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&err, 4))) return rc;
+    if ((rc = scratch.alloc(flags, nLa))) return rc;
+    if ((rc = scratch.alloc(R, nLa * 16))) return rc;
+    if ((rc = scratch.alloc(Rinv, nLa * 16))) return rc;
+    if ((rc = scratch.alloc(res, Cb->n * 16))) return rc;
+    if ((rc = scratch.alloc(err, 4))) return rc;
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
     if (Cb->nL) {
         dec_flags_kernel<<<(unsigned)((Cb->nL + 255) / 256), 256, 0, ctx->stream>>>(Cb->nL, Cb->rule, flags);
@@ -126,7 +127,6 @@ int op_dec_value(Ctx* ctx, const Batch* Cb, uint64_t* h_out) {
     PV_CUDA(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PV_CUDA(cudaMemcpyAsync(h_out, res, Cb->n * 16, cudaMemcpyDeviceToHost, ctx->stream));
     PV_CUDA(cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, flags); dev_free(ctx, R); dev_free(ctx, Rinv); dev_free(ctx, res); dev_free(ctx, err);
     if (h_err) {
         ctx->last_error = (h_err & 1) ? "dec_value: layer parent out of range" : "dec_value: cycle in the layer graph";
         return PV_E_LAYER_GRAPH;

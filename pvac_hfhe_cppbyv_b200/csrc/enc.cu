@@ -111,6 +111,7 @@ void plan_noise_host(int depth_hint, int& z2, int& z3) {
 int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint, int shares) {
     const uint64_t S = (uint64_t)shares;
     if (shares != 1 && shares != 2) return PV_E_ARG;
+    Scratch scratch(ctx);
     int Z2, Z3;
     plan_noise_host(depth_hint, Z2, Z3);
     const int G = Z2 + Z3, RAW = kSignal + 2 * Z2 + 3 * Z3;
@@ -126,23 +127,23 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     const uint64_t njobs = S * n * G;
     if (!on_device) {
         const size_t vbytes = n * (shares == 2 ? 8 : 16);
-        if ((rc = dev_alloc(ctx, (void**)&d_vals, vbytes))) return rc;
+        if ((rc = scratch.alloc(d_vals, vbytes))) return rc;
         PV_CUDA(cudaMemcpyAsync(d_vals, values, vbytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (h_states) {
-        if ((rc = dev_alloc(ctx, (void**)&d_states, n * 8))) return rc;
+        if ((rc = scratch.alloc(d_states, n * 8))) return rc;
         PV_CUDA(cudaMemcpyAsync(d_states, h_states, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if ((rc = dev_alloc(ctx, (void**)&plans, S * n * sizeof(SharePlan)))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&cnt, n * 4))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&xcnt, n * 4))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&eoff, (n + 1) * 4))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&xoff, (n + 1) * 4))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&j_ztag, njobs * 8))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&j_nlo, njobs * 8))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&j_nhi, njobs * 8))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&j_flags, njobs))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&prf, njobs * 16))) return rc;
+    if ((rc = scratch.alloc(plans, S * n * sizeof(SharePlan)))) return rc;
+    if ((rc = scratch.alloc(cnt, n * 4))) return rc;
+    if ((rc = scratch.alloc(xcnt, n * 4))) return rc;
+    if ((rc = scratch.alloc(eoff, (n + 1) * 4))) return rc;
+    if ((rc = scratch.alloc(xoff, (n + 1) * 4))) return rc;
+    if ((rc = scratch.alloc(j_ztag, njobs * 8))) return rc;
+    if ((rc = scratch.alloc(j_nlo, njobs * 8))) return rc;
+    if ((rc = scratch.alloc(j_nhi, njobs * 8))) return rc;
+    if ((rc = scratch.alloc(j_flags, njobs))) return rc;
+    if ((rc = scratch.alloc(prf, njobs * 16))) return rc;
     enc_plan_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, on_device ? values : d_vals, batch_seed, d_states, ctx->kv.canon_tag, Z2, Z3, shares, plans, cnt, xcnt,
                                                                         j_ztag, j_nlo, j_nhi, j_flags);
     if ((rc = scan_u32(ctx, n, cnt, eoff))) return rc;
@@ -161,14 +162,14 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     uint64_t *s_salt = nullptr, *tmp_rows = nullptr;
     uint2* fix = nullptr;
     unsigned int* err = nullptr;
-    if ((rc = dev_alloc(ctx, (void**)&s_seed, nS * 4))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&s_row, nS * 4))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&s_idx, nS * 2))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&s_ch, nS))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&s_salt, nS * 8))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&fix, (nX ? nX : 1) * sizeof(uint2)))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&tmp_rows, (nX ? nX : 1) * (size_t)kMWords * 8))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&err, 4))) return rc;
+    if ((rc = scratch.alloc(s_seed, nS * 4))) { batch_free(b); return rc; }
+    if ((rc = scratch.alloc(s_row, nS * 4))) { batch_free(b); return rc; }
+    if ((rc = scratch.alloc(s_idx, nS * 2))) { batch_free(b); return rc; }
+    if ((rc = scratch.alloc(s_ch, nS))) { batch_free(b); return rc; }
+    if ((rc = scratch.alloc(s_salt, nS * 8))) { batch_free(b); return rc; }
+    if ((rc = scratch.alloc(fix, (nX ? nX : 1) * sizeof(uint2)))) { batch_free(b); return rc; }
+    if ((rc = scratch.alloc(tmp_rows, (nX ? nX : 1) * (size_t)kMWords * 8))) { batch_free(b); return rc; }
+    if ((rc = scratch.alloc(err, 4))) { batch_free(b); return rc; }
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
     PV_CUDA(cudaMemcpyAsync(b->eoff, eoff, (n + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     enc_emit_kernel<<<(unsigned)((S * n + 127) / 128), 128, 0, ctx->stream>>>(n, shares, plans, eoff, xoff, nE, b->loff, b->rule, b->ztag, b->nlo, b->nhi, b->pa, b->pb,
@@ -186,10 +187,6 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     if ((rc = sigma_xor_rows(ctx, nX, fix, b->sigma, nE, tmp_rows))) { batch_free(b); return rc; }
     unsigned int h_err = 0;
     { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) { batch_free(b); return rc; } }
-    dev_free(ctx, d_vals); dev_free(ctx, d_states); dev_free(ctx, plans); dev_free(ctx, cnt); dev_free(ctx, xcnt); dev_free(ctx, eoff); dev_free(ctx, xoff);
-    dev_free(ctx, j_ztag); dev_free(ctx, j_nlo); dev_free(ctx, j_nhi); dev_free(ctx, j_flags); dev_free(ctx, prf);
-    dev_free(ctx, s_seed); dev_free(ctx, s_row); dev_free(ctx, s_idx); dev_free(ctx, s_ch); dev_free(ctx, s_salt); dev_free(ctx, fix);
-    dev_free(ctx, tmp_rows); dev_free(ctx, err);
     if (h_err) {
         batch_free(b);
         ctx->last_error = "enc_value: a merged edge weight is zero (compact_edges drop branch, p ~ 2^-127)";

@@ -148,6 +148,25 @@ void batch_free(Batch* b);
 int dev_alloc(Ctx* ctx, void** p, size_t bytes);
 void dev_free(Ctx* ctx, void* p);
 
+// temporaries of one host-side op: freed (stream-ordered) when the scope ends, on every return path
+struct Scratch {
+    Ctx* ctx;
+    std::vector<void*> ptrs;
+    explicit Scratch(Ctx* c) : ctx(c) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() { for (void* p : ptrs) dev_free(ctx, p); }
+    template <class T>
+    int alloc(T*& p, size_t bytes) {
+        void* v = nullptr;
+        int rc = dev_alloc(ctx, &v, bytes);
+        if (rc) return rc;
+        ptrs.push_back(v);
+        p = static_cast<T*>(v);
+        return PV_OK;
+    }
+};
+
 // ---- PRF (prf.cu): out[j] = prf_R(seed_j) (family 0) or prf_R_noise(seed_j) (family 1); inactive jobs give 0
 int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_nlo, const uint64_t* d_nhi,
             const uint8_t* d_flags /*bit0 family, bit1 active*/, Fp* d_out, uint64_t* d_ybits_out /*optional debug: [njobs*3][rows/64]*/);

@@ -94,6 +94,7 @@ __global__ void prf_finalize_kernel(uint64_t njobs, const uint8_t* __restrict__ 
 int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_nlo, const uint64_t* d_nhi, const uint8_t* d_flags,
             Fp* d_out, uint64_t* d_ybits_out) {
     if (njobs == 0) return PV_OK;
+    Scratch scratch(ctx);
     const uint64_t ncores = njobs * 3;
     const int rpc_log2 = ctx->prf_mode == PRF_LIVE ? 6 : 13;
     const int wpc = (1 << rpc_log2) / 32;  // ybits words per core
@@ -101,12 +102,12 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     uint64_t *ctr0 = nullptr, *top = nullptr, *ybits = nullptr;
     unsigned int* rare = nullptr;
     int rc;
-    if ((rc = dev_alloc(ctx, (void**)&rk, ncores * 60 * 4))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&ctr0, ncores * 8))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&top, ncores * 16))) return rc;
+    if ((rc = scratch.alloc(rk, ncores * 60 * 4))) return rc;
+    if ((rc = scratch.alloc(ctr0, ncores * 8))) return rc;
+    if ((rc = scratch.alloc(top, ncores * 16))) return rc;
     if (d_ybits_out) ybits = d_ybits_out;
-    else if ((rc = dev_alloc(ctx, (void**)&ybits, ncores * wpc * 8))) return rc;
-    if ((rc = dev_alloc(ctx, (void**)&rare, 4))) return rc;
+    else if ((rc = scratch.alloc(ybits, ncores * wpc * 8))) return rc;
+    if ((rc = scratch.alloc(rare, 4))) return rc;
     PV_CUDA(cudaMemsetAsync(rare, 0, 4, ctx->stream));
 
     prf_setup_kernel<<<(unsigned)((ncores + 127) / 128), 128, 0, ctx->stream>>>(ctx->kv, ncores, d_ztag, d_nlo, d_nhi, d_flags, rk, ctr0, top);
@@ -127,8 +128,6 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
 
     unsigned int h_rare = 0;
     { SmallRead sr; sr.add(&h_rare, rare, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
-    dev_free(ctx, rk); dev_free(ctx, ctr0); dev_free(ctx, top); dev_free(ctx, rare);
-    if (!d_ybits_out) dev_free(ctx, ybits);
     if (h_rare) {
         ctx->last_error = "AesCtr256::bounded rejection branch hit (p = 2^-61 per row); not supported on device";
         return PV_E_RARE_PATH;

@@ -86,6 +86,38 @@ PV_HD void sha_compress_from(const uint32_t* from, uint32_t w[16], uint32_t out[
     out[0] = from[0] + a; out[1] = from[1] + b; out[2] = from[2] + c; out[3] = from[3] + d;
     out[4] = from[4] + e; out[5] = from[5] + f; out[6] = from[6] + g; out[7] = from[7] + h;
 }
+#if defined(__CUDACC__)
+// Same compression with the two-input additions issued as IMAD (x * one + y, `one` a run-time 1 so that ptxas keeps the
+// multiply-add): they run on the FMA pipe, which the hashing leaves idle, instead of the ALU pipe that SHF/LOP3 and the
+// gather's XORs already fill. Used by the fused sigma kernel (PVACB_SIGMA_FMA=1), see profiles/r01_notes.md.
+__device__ __forceinline__ uint32_t sha_add_fma(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void sha_compress_from_fma(const uint32_t* from, uint32_t w[16], uint32_t out[8], uint32_t one) {
+    PVACB_SHA_K_DECL;
+    uint32_t a = from[0], b = from[1], c = from[2], d = from[3], e = from[4], f = from[5], g = from[6], h = from[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+            uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+            w[i & 15] = sha_add_fma(sha_add_fma(w[i & 15], s0, one), sha_add_fma(w[(i - 7) & 15], s1, one), one);
+        }
+        uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+        uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+        uint32_t ch = (e & f) ^ (~e & g), maj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t1 = sha_add_fma(sha_add_fma(h, S1, one), sha_add_fma(ch, PVACB_SHA_K(i) + w[i & 15], one), one);
+        uint32_t t2 = sha_add_fma(S0, maj, one);
+        h = g; g = f; f = e; e = sha_add_fma(d, t1, one); d = c; c = b; b = a; a = sha_add_fma(t1, t2, one);
+    }
+    out[0] = from[0] + a; out[1] = from[1] + b; out[2] = from[2] + c; out[3] = from[3] + d;
+    out[4] = from[4] + e; out[5] = from[5] + f; out[6] = from[6] + g; out[7] = from[7] + h;
+}
+#endif
+
 // LE64 of 8 big-endian digest bytes held as two state words (what load_le64(digest + 8k) returns)
 PV_HD uint64_t sha_le64_of(uint32_t h_even, uint32_t h_odd) { return (uint64_t)sha_bswap(h_even) | ((uint64_t)sha_bswap(h_odd) << 32); }
 

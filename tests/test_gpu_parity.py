@@ -474,3 +474,28 @@ def test_enc_fp_depth_vs_oracle(engine, api, port, port_keys):
         assert [fpv(x) for x in engine.dec_value(X)] == vals
     with pytest.raises(api.PvacbError):
         engine.enc_fp_depth(np.array([[2**64 - 1, 2**63 - 1]], np.uint64), 0, 1)      # p itself is not canonical
+
+
+def test_ragged_batches_with_empty_ciphertexts(engine, api, port, port_keys):
+    """one batch mixing fresh, summed, product and EMPTY ciphertexts (no layers, no edges) through add / sub / mul / dec /
+    commit: every result equal to the oracle's, item by item"""
+    K = port_keys
+    f = [K.enc_value(port.item_stream_state(8700, i), 10 + i) for i in range(4)]
+    empty_ct = port.ct_import({k: v[:0] for k, v in port.ct_export(f[0]).items()})
+    left = [f[0], empty_ct, K.ct_mul(5, f[0], f[1]), K.ct_add(f[2], f[3]), empty_ct]
+    right = [f[1], f[2], f[3], empty_ct, empty_ct]
+    A = engine.import_soa(api.join_items([port.ct_export(c) for c in left]))
+    B = engine.import_soa(api.join_items([port.ct_export(c) for c in right]))
+    st = np.array([port.item_stream_state(8701, i) for i in range(5)], np.uint64)
+    got = {"add": engine.ct_add(A, B), "sub": engine.ct_sub(A, B), "mul": engine.ct_mul(A, B, tape_states=st)}
+    want = {"add": [K.ct_add(a, b) for a, b in zip(left, right)], "sub": [K.ct_sub(a, b) for a, b in zip(left, right)],
+            "mul": [K.ct_mul(int(st[i]), a, b) for i, (a, b) in enumerate(zip(left, right))]}
+    for name, batch in got.items():
+        items = api.split_items(engine.export_soa(batch))
+        dec = engine.dec_value(batch)
+        com = engine.commit_ct(batch)
+        for i in range(5):
+            ok, fld = ct_equal(items[i], port.ct_export(want[name][i]))
+            assert ok, (name, i, fld)
+            assert np.array_equal(dec[i], K.dec_value(want[name][i])), (name, i)
+            assert com[i].tobytes() == K.commit_ct(want[name][i]), (name, i)

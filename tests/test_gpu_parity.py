@@ -499,3 +499,15 @@ def test_ragged_batches_with_empty_ciphertexts(engine, api, port, port_keys):
             assert ok, (name, i, fld)
             assert np.array_equal(dec[i], K.dec_value(want[name][i])), (name, i)
             assert com[i].tobytes() == K.commit_ct(want[name][i]), (name, i)
+
+
+def test_c_abi_program_runs(tmp_path):
+    """tests/c/abi_smoke.c: keygen / enc / add / sub / mul / dec / commit through the C ABI from plain C"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "pvac_hfhe_cppbyv_b200")
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_smoke.c"), "-L", pkg, "-lpvacb",
+                           f"-Wl,-rpath,{pkg}", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "abi_smoke ok: 3 products" in r.stdout, r.stdout + r.stderr

@@ -234,3 +234,16 @@ def test_bucket_table(ht, kat):
         assert ht.ht_next_bkt(int(n)) == nb == ht.ht_unordered_buckets_real(int(n))
     for n in (1, 2, 13, 1521, 1560, 1600, 3160, 48080, 100000, 1444804):
         assert ht.ht_next_bkt(n) == ht.ht_unordered_buckets_real(n)
+
+
+def test_c_abi_program_compiles_as_c99(tmp_path):
+    """include/pvacb.h is plain C: tests/c/abi_smoke.c builds with gcc -std=c99 -pedantic and links against libpvacb.so;
+    without a GPU its first call fails with PVACB_E_CUDA (2) instead of falling back to anything."""
+    import torch
+    exe = str(tmp_path / "abi_smoke")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                        "-L", PKG, "-lpvacb", f"-Wl,-rpath,{PKG}", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 1 and "pvacb_ctx_create(0, &ctx) -> 2" in run.stderr

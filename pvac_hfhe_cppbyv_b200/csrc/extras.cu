@@ -1,6 +1,8 @@
 // Entry points around the hot path: batch slicing, synthetic benchmark batches, and the device building blocks exposed
 // for parity tests (pvacb_prf, pvacb_sigma_from_H, pvacb_fp_op). All of them run CUDA kernels; none has a CPU path.
 #include "engine.h"
+#include <cstdlib>
+#include <cstdio>
 #include "../../include/pvacb.h"
 
 #include <vector>
@@ -244,14 +246,32 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
     cudaEventCreate(&a); cudaEventCreate(&b);
     double best = 0;
     const uint4* H4 = reinterpret_cast<const uint4*>(ctx->kv.H);
-    for (int shape = 0; shape < 6; shape++) {
-        const int ctas_per_sm = (shape & 1) ? 8 : 4;
+    static const int kCtas[5] = {4, 8, 1, 2, 3};
+    // PVACB_PROBE_SMEM=<bytes per CTA>: run the probe with that much dynamic shared memory (shrinks L1), to see whether the
+    // gather ceiling depends on the L1 / shared-memory split the sigma kernel runs with
+    const int probe_smem = getenv("PVACB_PROBE_SMEM") ? atoi(getenv("PVACB_PROBE_SMEM")) : 0;
+    if (getenv("PVACB_PROBE_CARVEOUT")) {
+        const int pct = atoi(getenv("PVACB_PROBE_CARVEOUT"));
+        cudaFuncSetAttribute(l2_gather_probe_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(l2_gather_probe_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(l2_gather_probe_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    if (probe_smem > 48 * 1024) {
+        cudaFuncSetAttribute(l2_gather_probe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, probe_smem);
+        cudaFuncSetAttribute(l2_gather_probe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, probe_smem);
+        cudaFuncSetAttribute(l2_gather_probe_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, probe_smem);
+    }
+    const int nshapes = getenv("PVACB_PROBE_VERBOSE") ? 15 : 6;         // the first six shapes hold the maximum; the rest map the curve
+    for (int sh = 0; sh < nshapes; sh++) {
+        const int shape = sh < 6 ? sh : 2 * ((sh - 6) / 3) + 0;            // columns-in-flight index in shape / 2
+        const int ctas_per_sm = sh < 6 ? ((sh & 1) ? 8 : 4) : kCtas[2 + (sh - 6) % 3];
+        double shape_best = 0;
         const unsigned grid = (unsigned)ctx->sm_count * ctas_per_sm;
         for (int r = 0; r < reps + 2; r++) {
             cudaEventRecord(a, ctx->stream);
-            if (shape / 2 == 0) l2_gather_probe_kernel<4><<<grid, 256, 0, ctx->stream>>>(H4, cols_per_warp, sink);
-            else if (shape / 2 == 1) l2_gather_probe_kernel<8><<<grid, 256, 0, ctx->stream>>>(H4, cols_per_warp, sink);
-            else l2_gather_probe_kernel<16><<<grid, 256, 0, ctx->stream>>>(H4, cols_per_warp, sink);
+            if (shape / 2 == 0) l2_gather_probe_kernel<4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (shape / 2 == 1) l2_gather_probe_kernel<8><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else l2_gather_probe_kernel<16><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             cudaEventRecord(b, ctx->stream);
             PV_CUDA(cudaEventSynchronize(b));
             float ms = 0;
@@ -259,7 +279,9 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
             double bytes = (double)grid * 8 * cols_per_warp * 1024.0;
             double g = bytes / (ms * 1e-3) / 1e9;
             if (r > 1 && g > best) best = g;
+            if (r > 1 && g > shape_best) shape_best = g;
         }
+        if (getenv("PVACB_PROBE_VERBOSE")) fprintf(stderr, "l2 gather probe: %d columns in flight per warp, %d warps/SM: %.0f GB/s\n", 4 << (shape / 2), ctas_per_sm * 8, shape_best);
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     dev_free(ctx, sink);

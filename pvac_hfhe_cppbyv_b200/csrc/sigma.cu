@@ -126,7 +126,8 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint1
     __syncwarp();
 }
 
-template <int G, int WARPS, int MINB, bool FMA>
+// EXP (tuning experiments only, wrong results): 1 = no gather loads (hash + de-dup only), 2 = no hashing (synthetic candidates)
+template <int G, int WARPS, int MINB, bool FMA, int EXP = 0, int CPS = 8>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, unsigned long long* __restrict__ work, uint32_t one) {
     extern __shared__ __align__(16) uint8_t sigma_smem[];
@@ -180,7 +181,10 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
             for (int i = 4; i < 15; i++) w[i] = 0;
             w[15] = label ? 78u * 8u : 79u * 8u;
             uint32_t d[8];
-            if (FMA) sha_compress_from_fma(S.mid[sl], w, d, one);
+            if (EXP == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) d[i] = (uint32_t)(h * 8 + i) * 2654435761u + w[0];
+            } else if (FMA) sha_compress_from_fma(S.mid[sl], w, d, one);
             else sha_compress_from(S.mid[sl], w, d);
             const uint32_t N = label ? (uint32_t)kMBits : (uint32_t)kNBits;
             uint2 pk;
@@ -195,25 +199,60 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
             const uint64_t job = job0 + e;
             const uint16_t* gc = S.cand + e * 2 * kCandPerLabel;
             dedupe_label(S.bm, S.cols, S.more, gc, label_xseed(), J, canon, job, (uint32_t)kNBits, lane);
-            // clear the bitmap again: every word that got a bit belongs to one of the chosen columns
-            for (int i = lane; i < kXColWt; i += 32) S.bm[S.cols[i] >> 11] = 0;
             uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
+            // 8 column offsets per step, broadcast reads. The NEXT step's offsets are fetched right after this step's loads
+            // have been issued: shared-memory round trips are slow while the gathers saturate L1TEX (ncu: short-scoreboard
+            // and mio-throttle stalls), so they must not sit between two batches of global loads.
+            if (CPS == 8) {
+                uint4 c0 = *reinterpret_cast<const uint4*>(&S.cols[0]);
+                uint4 c1 = *reinterpret_cast<const uint4*>(&S.cols[4]);
 #pragma unroll 1
-            for (int i = 0; i < kXColWt; i += 8) {
-                uint4 c0 = *reinterpret_cast<const uint4*>(&S.cols[i]);       // 8 column offsets, broadcast
-                uint4 c1 = *reinterpret_cast<const uint4*>(&S.cols[i + 4]);
-                uint32_t co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                uint4 v[16];
+                for (int i = 0; i < kXColWt; i += 8) {
+                    const uint32_t co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    uint4 v[16];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint4* p = Hl + co[k];
-                    v[2 * k] = __ldcg(p);
-                    v[2 * k + 1] = __ldcg(p + 32);
+                    for (int k = 0; k < 8; k++) {
+                        const uint4* p = Hl + co[k];
+                        if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
+                        v[2 * k] = __ldcg(p);
+                        v[2 * k + 1] = __ldcg(p + 32);
+                    }
+                    if (i == 0) {
+                        // clear the bitmap again (every word that got a bit belongs to one of the chosen columns) -- under the first loads
+                        for (int q = lane; q < kXColWt; q += 32) S.bm[S.cols[q] >> 11] = 0;
+                    }
+                    if (i + 8 < kXColWt) {
+                        c0 = *reinterpret_cast<const uint4*>(&S.cols[i + 8]);
+                        c1 = *reinterpret_cast<const uint4*>(&S.cols[i + 12]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
+                        a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
+                    }
                 }
+            } else {
+                uint4 c0 = *reinterpret_cast<const uint4*>(&S.cols[0]);
+#pragma unroll 1
+                for (int i = 0; i < kXColWt; i += 4) {
+                    const uint32_t co[4] = {c0.x, c0.y, c0.z, c0.w};
+                    uint4 v[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
-                    a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
+                    for (int k = 0; k < 4; k++) {
+                        const uint4* p = Hl + co[k];
+                        if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
+                        v[2 * k] = __ldcg(p);
+                        v[2 * k + 1] = __ldcg(p + 32);
+                    }
+                    if (i == 0) {
+                        for (int q = lane; q < kXColWt; q += 32) S.bm[S.cols[q] >> 11] = 0;
+                    }
+                    if (i + 4 < kXColWt) c0 = *reinterpret_cast<const uint4*>(&S.cols[i + 4]);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
+                        a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
+                    }
                 }
             }
             __syncwarp();
@@ -256,14 +295,18 @@ int sigma_xor_rows(Ctx* ctx, uint64_t npairs, const uint2* d_pairs, uint64_t* ou
     return PV_OK;
 }
 
-template <int G, int WARPS, int MINB, bool FMA = false>
+template <int G, int WARPS, int MINB, bool FMA = false, int EXP = 0, int CPS = 8>
 static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
-    auto kern = sigma_fused_kernel<G, WARPS, MINB, FMA>;
+    auto kern = sigma_fused_kernel<G, WARPS, MINB, FMA, EXP, CPS>;
     constexpr int smem = (int)sizeof(SigmaWarpSmem<G>) * WARPS;
     static bool attr_done = false;
     if (!attr_done) {
         PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        // ask for exactly the shared memory MINB CTAs need, not the maximum: with the 228 KB carve-out (28 KB of L1 left) the L2
+        // gather ceiling drops from 19.9 to 16.3 TB/s (pvacb_l2_gather_probe under PVACB_PROBE_CARVEOUT, profiles/r01_notes.md)
+        int carve = (int)(((size_t)MINB * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (getenv("PVACB_SIGMA_CARVEOUT")) carve = atoi(getenv("PVACB_SIGMA_CARVEOUT"));
+        PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
         attr_done = true;
     }
     const uint64_t ngroups = (J.n + G - 1) / G;
@@ -280,25 +323,22 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
     if (J.n == 0) return PV_OK;
     int rc;
     // shape (G edges per warp-group, warps per CTA, CTAs per SM). G*68 hashes should fill whole 32-lane rounds (G = 8: 17
-    // rounds exactly); shared memory per warp = 2304 + 616 G bytes bounds the resident warps. PVACB_SIGMA_CFG picks another
+    // rounds exactly, G = 6: 12.75); shared memory per warp = 2560 + 616 G bytes bounds the resident warps, and the total must
+    // stay under ~196 KB per SM or the L2 gather ceiling drops by 18 % (see sigma_launch). PVACB_SIGMA_CFG picks another
     // compiled shape for tuning runs. Small batches use groups of 2 edges so that more warps (and SMs) take part.
     static int cfg = -1;
     if (cfg < 0) {
         const char* e = getenv("PVACB_SIGMA_CFG");
-        cfg = e ? atoi(e) : 7;
+        cfg = e ? atoi(e) : 0;
     }
-    if (J.n < (uint64_t)ctx->sm_count * 7 * 4 * 8) rc = sigma_launch<2, 4, 8>(ctx, J);
+    if (J.n < (uint64_t)ctx->sm_count * 7 * 4 * 6) rc = sigma_launch<2, 4, 8, true, 0, 4>(ctx, J);
     else switch (cfg) {
-        default: rc = sigma_launch<8, 4, 7, true>(ctx, J); break;    // 7: SHA additions on the FMA pipe (1.3 % faster than 0)
-        case 0: rc = sigma_launch<8, 4, 7>(ctx, J); break;
-        case 1: rc = sigma_launch<7, 4, 8>(ctx, J); break;
-        case 2: rc = sigma_launch<8, 8, 3>(ctx, J); break;
-        case 3: rc = sigma_launch<4, 4, 8>(ctx, J); break;
-        case 4: rc = sigma_launch<8, 4, 6>(ctx, J); break;
-        case 5: rc = sigma_launch<8, 4, 5>(ctx, J); break;
-        case 6: rc = sigma_launch<6, 4, 8>(ctx, J); break;
-        case 8: rc = sigma_launch<8, 4, 6, true>(ctx, J); break;
-        case 9: rc = sigma_launch<7, 4, 8, true>(ctx, J); break;
+        default: rc = sigma_launch<6, 4, 7, true, 0, 4>(ctx, J); break;   // 28 warps/SM, 182 KB of shared memory: L1 keeps 60 KB
+        case 1: rc = sigma_launch<8, 4, 6, true, 0, 4>(ctx, J); break;    // 24 warps/SM, exact 17-round groups
+        case 2: rc = sigma_launch<5, 4, 8, true, 0, 4>(ctx, J); break;    // 32 warps/SM
+        case 3: rc = sigma_launch<8, 4, 7, true, 0, 4>(ctx, J); break;    // 28 warps/SM but 217 KB shared: the slow L1 split
+        case 21: rc = sigma_launch<6, 4, 7, true, 1, 4>(ctx, J); break;   // experiment: no gather loads (wrong results)
+        case 22: rc = sigma_launch<6, 4, 7, true, 2, 4>(ctx, J); break;   // experiment: no hashing (wrong results)
     }
     if (rc) return rc;
     PV_CUDA(cudaGetLastError());

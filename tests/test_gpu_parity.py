@@ -511,3 +511,43 @@ def test_c_abi_program_runs(tmp_path):
                            f"-Wl,-rpath,{pkg}", "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "abi_smoke ok: 3 products" in r.stdout, r.stdout + r.stderr
+
+
+def test_ct_fuzz_random_circuits(engine, api, port, port_keys):
+    """tests/test_ct_fuzz.cpp on batches: random 3-6 step add / sub / mul chains (at most two multiplications) over a pool of
+    encrypted values; each of the 16 lanes of a batch runs the same circuit on different plaintexts. Every decrypt equals the
+    plain evaluation mod p; for one trial lane 0 is replayed on the oracle and compared bit for bit."""
+    rng = np.random.default_rng(20261018)
+    lanes, K = 16, 6
+    vals = rng.integers(0, 2**64, (K, lanes), dtype=np.uint64)
+    enc = [engine.enc_value(vals[k], 9100 + k) for k in range(K)]
+    orc = [port_keys.enc_value(port.item_stream_state(9100 + k, 0), int(vals[k][0])) for k in range(K)]
+    for trial in range(6):
+        i0 = int(rng.integers(K))
+        acc, plain = enc[i0], [int(x) for x in vals[i0]]
+        oacc = orc[i0]
+        muls = 0
+        for step in range(int(rng.integers(3, 7))):
+            j = int(rng.integers(K))
+            op = int(rng.integers(3))
+            if op == 2 and muls >= 2:
+                op = int(rng.integers(2))
+            rhs = [int(x) for x in vals[j]]
+            if op == 0:
+                acc, plain = engine.ct_add(acc, enc[j]), [(a + b) % P127 for a, b in zip(plain, rhs)]
+                if trial == 0:
+                    oacc = port_keys.ct_add(oacc, orc[j])
+            elif op == 1:
+                acc, plain = engine.ct_sub(acc, enc[j]), [(a - b) % P127 for a, b in zip(plain, rhs)]
+                if trial == 0:
+                    oacc = port_keys.ct_sub(oacc, orc[j])
+            else:
+                seed = 9200 + 10 * trial + step
+                acc, plain = engine.ct_mul(acc, enc[j], seed), [a * b % P127 for a, b in zip(plain, rhs)]
+                muls += 1
+                if trial == 0:
+                    oacc = port_keys.ct_mul(port.item_stream_state(seed, 0), oacc, orc[j])
+        assert [fpv(x) for x in engine.dec_value(acc)] == plain, trial
+        if trial == 0:
+            ok, f = ct_equal(api.split_items(engine.export_soa(engine.slice(acc, 0, 1)))[0], port.ct_export(oacc))
+            assert ok, f

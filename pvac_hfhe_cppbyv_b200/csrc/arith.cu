@@ -141,10 +141,8 @@ __global__ void scale_w_kernel(uint64_t nE, const Fp* __restrict__ in, Fp s, Fp*
 
 int op_ct_scale(Ctx* ctx, const Batch* A, Fp s, Batch** out) {
     Batch* o = nullptr;
-    int rc = batch_alloc(ctx, A->n, A->nL, A->nE, &o);
+    int rc = batch_clone(ctx, A, &o);
     if (rc) return rc;
-    // identical layout -> one device copy of everything, then overwrite the weights
-    PV_CUDA(cudaMemcpyAsync(o->base, A->base, A->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     if (A->nE) scale_w_kernel<<<(unsigned)((A->nE + 255) / 256), 256, 0, ctx->stream>>>(A->nE, A->w, s, o->w);
     PV_CUDA(cudaGetLastError());
     ctx->stat_kernel_launches += 1;

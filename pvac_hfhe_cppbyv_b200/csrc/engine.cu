@@ -72,6 +72,30 @@ int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out) {
     *out = b;
     return PV_OK;
 }
+// a new batch with the same contents. Field by field: a batch whose layers were compacted in place (compact_layers_batch)
+// keeps the allocation layout of its original layer count, so its bytes are NOT one flat image of (n, nL, nE).
+int batch_clone(Ctx* ctx, const Batch* s, Batch** out) {
+    Batch* o = nullptr;
+    int rc = batch_alloc(ctx, s->n, s->nL, s->nE, &o);
+    if (rc) return rc;
+    auto cp = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream) : cudaSuccess;
+    };
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ck(cp(o->loff, s->loff, (s->n + 1) * 4)); ck(cp(o->eoff, s->eoff, (s->n + 1) * 4));
+    ck(cp(o->rule, s->rule, s->nL)); ck(cp(o->ztag, s->ztag, s->nL * 8)); ck(cp(o->nlo, s->nlo, s->nL * 8)); ck(cp(o->nhi, s->nhi, s->nL * 8));
+    ck(cp(o->pa, s->pa, s->nL * 4)); ck(cp(o->pb, s->pb, s->nL * 4));
+    ck(cp(o->lid, s->lid, s->nE * 4)); ck(cp(o->idx, s->idx, s->nE * 2)); ck(cp(o->ch, s->ch, s->nE)); ck(cp(o->w, s->w, s->nE * 16));
+    ck(cp(o->sigma, s->sigma, s->nE * (size_t)kMWords * 8));
+    if (e != cudaSuccess) {
+        batch_free(o);
+        ctx->last_error = std::string("batch_clone: ") + cudaGetErrorString(e);
+        return PV_E_CUDA;
+    }
+    *out = o;
+    return PV_OK;
+}
 void batch_free(Batch* b) {
     if (!b) return;
     dev_free(b->ctx, b->base);

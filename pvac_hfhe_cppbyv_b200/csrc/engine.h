@@ -143,6 +143,7 @@ int read_small_sync(Ctx* ctx, const SmallRead& r);   // enqueue + cudaStreamSync
 
 int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out);
 void batch_free(Batch* b);
+int batch_clone(Ctx* ctx, const Batch* src, Batch** out);   // field-by-field device copy
 
 // scratch allocator: stream-ordered
 int dev_alloc(Ctx* ctx, void** p, size_t bytes);

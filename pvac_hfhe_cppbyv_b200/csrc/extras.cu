@@ -297,9 +297,8 @@ int pvacb_compact_edges(pvacb_ctx* x, const pvacb_batch* pb, pvacb_batch** out) 
     if (!out) return PV_E_ARG;
     cudaSetDevice(ctx->device);
     Batch* cpy = nullptr;
-    int rc = batch_alloc(ctx, s->n, s->nL, s->nE, &cpy);
+    int rc = batch_clone(ctx, s, &cpy);
     if (rc) return rc;
-    PV_CUDA(cudaMemcpyAsync(cpy->base, s->base, s->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     if ((rc = guard_budget_batch(ctx, &cpy, 0))) { batch_free(cpy); return rc; }
     *out = reinterpret_cast<pvacb_batch*>(cpy);
     return PV_OK;

@@ -53,6 +53,10 @@ int read_small_sync(Ctx* ctx, const SmallRead& r) {
 }
 
 int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out) {
+    if (n >= (1ull << 32) - 1 || nL >= (1ull << 32) || nE >= (1ull << 32)) {      // per-ciphertext offsets are 32-bit
+        ctx->last_error = "batch too large: layer / edge offsets are 32-bit, split the batch into tiles";
+        return PV_E_SHAPE;
+    }
     Batch* b = new Batch();
     b->ctx = ctx; b->n = n; b->nL = nL; b->nE = nE;
     size_t off = 0;

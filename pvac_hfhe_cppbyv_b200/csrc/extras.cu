@@ -60,7 +60,15 @@ __global__ void synth_sigma_kernel(uint64_t nwords, uint64_t seed, uint64_t* sig
 // L2 gather probe: the access pattern of sigma_gather_kernel (a warp XOR-reads pseudo-random 1 KiB columns of the 16 MiB
 // matrix H with 128-bit loads) with nothing else around it. U = columns in flight per warp. The best bandwidth over a
 // few (U, CTAs/SM) shapes is used as the practical ceiling of the sigma kernel.
-template <int U>
+// LD: 0 ld.global.cg (what the sigma kernel uses), 1 plain ld.global, 2 ld.global.nc, 3 ld.global.cs  (PVACB_PROBE_LD)
+template <int LD>
+__device__ __forceinline__ uint4 probe_load(const uint4* p) {
+    if (LD == 1) return *p;
+    if (LD == 2) return __ldg(p);
+    if (LD == 3) return __ldcs(p);
+    return __ldcg(p);
+}
+template <int U, int LD = 0>
 __global__ void __launch_bounds__(256) l2_gather_probe_kernel(const uint4* __restrict__ H4, uint32_t cols_per_warp, uint4* __restrict__ sink) {
     const int lane = threadIdx.x & 31;
     uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -73,8 +81,8 @@ __global__ void __launch_bounds__(256) l2_gather_probe_kernel(const uint4* __res
             state = state * 1664525u + 1013904223u;
             uint32_t col = (state >> 10) & (kNBits - 1);
             const uint4* p = H4 + (size_t)col * 64 + lane;
-            v[2 * k] = __ldcg(p);
-            v[2 * k + 1] = __ldcg(p + 32);
+            v[2 * k] = probe_load<LD>(p);
+            v[2 * k + 1] = probe_load<LD>(p + 32);
         }
 #pragma unroll
         for (int k = 0; k < U; k++) {
@@ -269,7 +277,11 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
         const unsigned grid = (unsigned)ctx->sm_count * ctas_per_sm;
         for (int r = 0; r < reps + 2; r++) {
             cudaEventRecord(a, ctx->stream);
-            if (shape / 2 == 0) l2_gather_probe_kernel<4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            const int ld = getenv("PVACB_PROBE_LD") ? atoi(getenv("PVACB_PROBE_LD")) : 0;
+            if (ld == 1) l2_gather_probe_kernel<8, 1><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (ld == 2) l2_gather_probe_kernel<8, 2><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (ld == 3) l2_gather_probe_kernel<8, 3><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (shape / 2 == 0) l2_gather_probe_kernel<4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (shape / 2 == 1) l2_gather_probe_kernel<8><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else l2_gather_probe_kernel<16><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             cudaEventRecord(b, ctx->stream);

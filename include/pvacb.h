@@ -96,7 +96,7 @@ int pvacb_enc_value(pvacb_ctx* ctx, const uint64_t* values, size_t n, uint64_t b
  * tape_states == NULL falls back to the batch_seed derivation above. */
 int pvacb_enc_value_ex(pvacb_ctx* ctx, const uint64_t* values, size_t n, uint64_t batch_seed, const uint64_t* tape_states,
                        pvacb_batch** out);
-/* Cipher enc_value_depth(pk, sk, v, depth_hint)            ops/encrypt.hpp:281  (plan_noise(depth_hint) noise groups; depth_hint 0..9)
+/* Cipher enc_value_depth(pk, sk, v, depth_hint)            ops/encrypt.hpp:281  (plan_noise(depth_hint) noise groups; depth_hint 0..23)
  * Cipher enc_zero_depth(pk, sk, depth_hint)                ops/encrypt.hpp:293  (identical draws to enc_value_depth(0, depth_hint)) */
 int pvacb_enc_value_depth(pvacb_ctx* ctx, const uint64_t* values, size_t n, int depth_hint, uint64_t batch_seed, const uint64_t* tape_states,
                           pvacb_batch** out);
@@ -127,6 +127,15 @@ int pvacb_dec_value(pvacb_ctx* ctx, const pvacb_batch* c, uint64_t* out);
 /* std::array<uint8_t,32> commit_ct(pk, C)                  ops/commit.hpp:12   out: n x 32 bytes (SHA-256 over layers, edges and sigma) */
 int pvacb_commit_ct(pvacb_ctx* ctx, const pvacb_batch* c, uint8_t* out);
 
+/* std::vector<Cipher> enc_text(pk, sk, msg) / std::string dec_text(pk, sk, cts)     utils/text.hpp:39,63
+ * for n messages at once: bytes = all messages back to back, msg_off[n+1] their byte ranges (<= 330 bytes each). Message m
+ * draws from ONE tape stream (tape_states[m] or the batch_seed derivation) exactly like the reference: enc_value(length), then
+ * enc_fp_depth(15-byte block j, depth_hint 2 + j). The result batch is WAVE-MAJOR: the n length ciphertexts in message
+ * order, then block 0 of every message that has one (message order), then block 1, ... pvacb_dec_text expects that order. */
+int pvacb_enc_text(pvacb_ctx* ctx, const uint8_t* bytes, const uint64_t* msg_off, size_t n, uint64_t batch_seed, const uint64_t* tape_states,
+                   pvacb_batch** out);
+int pvacb_dec_text(pvacb_ctx* ctx, const pvacb_batch* c, size_t n_msgs, uint8_t* out_bytes, size_t cap, uint64_t* out_off /* n_msgs + 1 */);
+
 /* ---- batches --------------------------------------------------------------------------------------------------- */
 void pvacb_batch_free(pvacb_batch* b);
 size_t pvacb_batch_count(const pvacb_batch* b);
@@ -134,6 +143,8 @@ int pvacb_batch_totals(const pvacb_batch* b, uint64_t* n_layers, uint64_t* n_edg
 size_t pvacb_batch_device_bytes(const pvacb_batch* b);
 /* per-ciphertext layer / edge offsets, n+1 entries each (host) */
 int pvacb_batch_offsets(pvacb_ctx* ctx, const pvacb_batch* b, uint32_t* layer_off, uint32_t* edge_off);
+/* the items of parts[0], parts[1], ... as one new batch (device copy; the inverse of pvacb_batch_slice) */
+int pvacb_batch_concat(pvacb_ctx* ctx, const pvacb_batch* const* parts, size_t nparts, pvacb_batch** out);
 /* slice [first, first+count) of a batch as a new batch (device copy) */
 int pvacb_batch_slice(pvacb_ctx* ctx, const pvacb_batch* b, size_t first, size_t count, pvacb_batch** out);
 

@@ -16,6 +16,7 @@
 #ifndef PVACB_HPP
 #define PVACB_HPP
 
+#include <array>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -89,6 +90,37 @@ public:
         std::vector<Fp> out(c.size());
         static_assert(sizeof(Fp) == 16, "Fp is two u64 limbs");
         ck(pvacb_dec_value(ctx_, c.handle(), reinterpret_cast<uint64_t*>(out.data())));
+        return out;
+    }
+    Ciphers ct_neg(const Ciphers& a) { pvacb_batch* o = nullptr; ck(pvacb_ct_neg(ctx_, a.handle(), &o)); return Ciphers(o); }
+    Ciphers ct_div_const(const Ciphers& a, Fp k) { pvacb_batch* o = nullptr; uint64_t w[2] = {k.lo, k.hi}; ck(pvacb_ct_div_const(ctx_, a.handle(), w, &o)); return Ciphers(o); }
+    Ciphers compact_edges(const Ciphers& a) { pvacb_batch* o = nullptr; ck(pvacb_compact_edges(ctx_, a.handle(), &o)); return Ciphers(o); }
+    Ciphers enc_value_depth(const std::vector<uint64_t>& v, int depth_hint, uint64_t batch_seed) {
+        pvacb_batch* o = nullptr;
+        ck(pvacb_enc_value_depth(ctx_, v.data(), v.size(), depth_hint, batch_seed, nullptr, &o));
+        return Ciphers(o);
+    }
+    // commit_ct (ops/commit.hpp:12): one 32-byte digest per ciphertext
+    std::vector<std::array<uint8_t, 32>> commit_ct(const Ciphers& c) {
+        std::vector<std::array<uint8_t, 32>> out(c.size());
+        ck(pvacb_commit_ct(ctx_, c.handle(), reinterpret_cast<uint8_t*>(out.data())));
+        return out;
+    }
+    // enc_text / dec_text (utils/text.hpp:39,63) for several messages at once; the batch is wave-major (see pvacb.h)
+    Ciphers enc_text(const std::vector<std::string>& msgs, uint64_t batch_seed) {
+        std::vector<uint64_t> off(msgs.size() + 1, 0);
+        std::string flat;
+        for (size_t i = 0; i < msgs.size(); i++) { flat += msgs[i]; off[i + 1] = flat.size(); }
+        pvacb_batch* o = nullptr;
+        ck(pvacb_enc_text(ctx_, reinterpret_cast<const uint8_t*>(flat.data()), off.data(), msgs.size(), batch_seed, nullptr, &o));
+        return Ciphers(o);
+    }
+    std::vector<std::string> dec_text(const Ciphers& c, size_t n_msgs) {
+        std::vector<uint8_t> buf(15 * c.size() + 16);
+        std::vector<uint64_t> off(n_msgs + 1, 0);
+        ck(pvacb_dec_text(ctx_, c.handle(), n_msgs, buf.data(), buf.size(), off.data()));
+        std::vector<std::string> out(n_msgs);
+        for (size_t i = 0; i < n_msgs; i++) out[i].assign(reinterpret_cast<const char*>(buf.data()) + off[i], (size_t)(off[i + 1] - off[i]));
         return out;
     }
     // the reference's on-disk format (tests/bounty2_test.cpp:63-143)

@@ -76,6 +76,7 @@ def lib():
         "orc_ct_sub": (vp, [vp, vp]),
         "orc_ct_scale": (vp, [vp, P(u64)]),
         "orc_commit_ct": (None, [vp, vp, P(u8)]),
+        "orc_enc_text": (i32, [vp, u64, P(u8), u64, P(vp), i32, P(u64)]),
         "orc_compact_edges": (vp, [vp]),
         "orc_ct_mul": (vp, [vp, u64, vp, vp, P(u64)]),
         "orc_dec_value": (i32, [vp, vp, P(u64)]),
@@ -286,6 +287,16 @@ class Keys:
         o = np.zeros(32, np.uint8)
         lib().orc_commit_ct(self.h, c, _p(o, C.c_uint8))
         return o.tobytes()
+
+    def enc_text(self, tape_state, msg: bytes):
+        global _last_draws
+        cap = 2 + len(msg) // 15 + 1
+        arr = (C.c_void_p * cap)()
+        m = np.frombuffer(msg or b"\0", np.uint8).copy()
+        d = C.c_uint64()
+        n = lib().orc_enc_text(self.h, tape_state, _p(m, C.c_uint8), len(msg), arr, cap, C.byref(d))
+        _last_draws = int(d.value)
+        return [arr[i] for i in range(n)]
 
     def compact_edges(self, a):
         return lib().orc_compact_edges(a)

@@ -696,6 +696,33 @@ orc_ct* orc_enc_zero_depth(const orc_keys* k, uint64_t tape_state, int depth_hin
     if (draws) *draws = t.draws;
     return c;
 }
+/* utils/text.hpp:15-61 -- enc_value(length), then enc_fp_depth(pack_15_bytes(block j), 2 + j), all from one tape. Returns the
+ * number of ciphertexts written to out (1 + ceil(len / 15)), or -1 if cap is too small. */
+int orc_enc_text(const orc_keys* k, uint64_t tape_state, const uint8_t* msg, uint64_t len, orc_ct** out, int cap, uint64_t* draws) {
+    int need = 1 + (int)((len + 14) / 15);
+    if (cap < need) return -1;
+    tape_t t = { tape_state, 0 };
+    {
+        fp_t val = fp_from_u64(len);
+        fp_t mask = rand_fp_nonzero(&t);
+        orc_ct* b = enc_fp_depth(k, &t, fp_neg(mask), 0);
+        orc_ct* a = enc_fp_depth(k, &t, fp_add(val, mask), 0);
+        out[0] = concat_ct(a, b);
+        orc_ct_free(a); orc_ct_free(b);
+    }
+    int depth = 2;
+    for (uint64_t pos = 0; pos < len; pos += 15, depth++) {
+        uint64_t take = len - pos < 15 ? len - pos : 15, lo = 0, hi = 0;
+        for (uint64_t i = 0; i < take; i++) {
+            if (i < 8) lo |= (uint64_t)msg[pos + i] << (8 * i);
+            else hi |= (uint64_t)msg[pos + i] << (8 * (i - 8));
+        }
+        fp_t x = fp_from_words(lo, hi);
+        out[1 + pos / 15] = enc_fp_depth(k, &t, x, depth);
+    }
+    if (draws) *draws = t.draws;
+    return need;
+}
 orc_ct* orc_ct_add(const orc_ct* a, const orc_ct* b) { return concat_ct(a, b); }
 /* ops/arithmetic.hpp:33-37 */
 orc_ct* orc_ct_scale(const orc_ct* a, const uint64_t* s) {

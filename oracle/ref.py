@@ -81,6 +81,8 @@ def lib():
         "ref_ct_neg": (vp, [vp, vp]),
         "ref_ct_div_const": (vp, [vp, vp, P(u64)]),
         "ref_commit_ct": (None, [vp, vp, P(u8)]),
+        "ref_enc_text": (i32, [vp, u64, P(u8), u64, P(vp), i32]),
+        "ref_dec_text": (i32, [vp, P(vp), i32, P(u8), i32]),
         "ref_compact_edges": (vp, [vp, vp]),
         "ref_ct_mul": (vp, [vp, u64, vp, vp]),
         "ref_dec_value": (None, [vp, vp, P(u64)]),
@@ -260,6 +262,19 @@ class Keys:
         o = np.zeros(32, np.uint8)
         lib().ref_commit_ct(self.h, c, _p(o, C.c_uint8))
         return o.tobytes()
+
+    def enc_text(self, tape_state, msg: bytes):
+        cap = 2 + len(msg) // 15 + 1
+        arr = (C.c_void_p * cap)()
+        m = np.frombuffer(msg or b"\0", np.uint8).copy()
+        n = lib().ref_enc_text(self.h, tape_state, _p(m, C.c_uint8), len(msg), arr, cap)
+        return [arr[i] for i in range(n)]
+
+    def dec_text(self, cts):
+        arr = (C.c_void_p * len(cts))(*cts)
+        buf = np.zeros(15 * len(cts) + 16, np.uint8)
+        n = lib().ref_dec_text(self.h, arr, len(cts), _p(buf, C.c_uint8), len(buf))
+        return buf[:n].tobytes()
 
     def compact_edges(self, a):
         return lib().ref_compact_edges(self.h, a)

@@ -220,6 +220,23 @@ void* ref_enc_value(void* h, uint64_t tape_state, uint64_t v) {
     ref_seed(tape_state);
     return new Cipher(enc_value(k->pk, k->sk, v));
 }
+int ref_enc_text(void* h, uint64_t tape_state, const uint8_t* msg, uint64_t len, void** out, int cap) {
+    Keys* k = (Keys*)h;
+    ref_seed(tape_state);
+    std::vector<Cipher> cts = enc_text(k->pk, k->sk, std::string((const char*)msg, (size_t)len));
+    if ((int)cts.size() > cap) return -1;
+    for (size_t i = 0; i < cts.size(); i++) out[i] = new Cipher(cts[i]);
+    return (int)cts.size();
+}
+int ref_dec_text(void* h, void** cts, int n, uint8_t* out, int cap) {
+    Keys* k = (Keys*)h;
+    std::vector<Cipher> v;
+    for (int i = 0; i < n; i++) v.push_back(*(Cipher*)cts[i]);
+    std::string s = dec_text(k->pk, k->sk, v);
+    if ((int)s.size() > cap) return -1;
+    memcpy(out, s.data(), s.size());
+    return (int)s.size();
+}
 void* ref_enc_value_depth(void* h, uint64_t tape_state, uint64_t v, int depth) {
     Keys* k = (Keys*)h;
     ref_seed(tape_state);

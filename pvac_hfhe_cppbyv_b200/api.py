@@ -42,6 +42,7 @@ SYMBOLS = [
     "pvacb_profile_enable", "pvacb_profile_collect", "pvacb_keys_copy_blob_to", "pvacb_keys_adopt_blob_from", "pvacb_l2_gather_probe",
     "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges", "pvacb_batch_checksum", "pvacb_commit_ct",
     "pvacb_enc_value_depth", "pvacb_enc_zero_depth", "pvacb_plan_noise", "pvacb_ct_neg", "pvacb_ct_div_const", "pvacb_enc_fp_depth",
+    "pvacb_enc_text", "pvacb_dec_text", "pvacb_batch_concat",
 ]
 
 
@@ -116,6 +117,9 @@ def load_library():
         "pvacb_enc_value_depth": (i32, [vp, P(u64), sz, i32, u64, P(u64), P(vp)]),
         "pvacb_enc_zero_depth": (i32, [vp, sz, i32, u64, P(u64), P(vp)]),
         "pvacb_enc_fp_depth": (i32, [vp, P(u64), sz, i32, u64, P(u64), P(vp)]),
+        "pvacb_enc_text": (i32, [vp, P(u8), P(u64), sz, u64, P(u64), P(vp)]),
+        "pvacb_dec_text": (i32, [vp, vp, sz, P(u8), sz, P(u64)]),
+        "pvacb_batch_concat": (i32, [vp, P(vp), sz, P(vp)]),
         "pvacb_plan_noise": (i32, [i32, P(i32), P(i32)]),
         "pvacb_ct_neg": (i32, [vp, vp, P(vp)]),
         "pvacb_ct_div_const": (i32, [vp, vp, P(u64), P(vp)]),
@@ -333,6 +337,30 @@ class Engine:
         kk = _u64(k)
         out = C.c_void_p()
         self._ck(self.L.pvacb_ct_div_const(self.h, a.h, _p(kk, C.c_uint64), C.byref(out)))
+        return Batch(self, out)
+
+    def enc_text(self, msgs, batch_seed=0, tape_states=None):
+        """msgs: list of bytes -> one WAVE-MAJOR batch (lengths, then block 0 of every message, then block 1, ...)"""
+        off = np.zeros(len(msgs) + 1, np.uint64)
+        for i, m in enumerate(msgs):
+            off[i + 1] = off[i] + len(m)
+        flat = np.frombuffer(b"".join(msgs) or b"\0", np.uint8).copy()
+        st = _u64(tape_states) if tape_states is not None else None
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_enc_text(self.h, _p(flat, C.c_uint8), _p(off, C.c_uint64), len(msgs), batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        return Batch(self, out)
+
+    def dec_text(self, c, n_msgs):
+        cap = 15 * max(len(c) - n_msgs, 0) + 16
+        buf = np.zeros(cap, np.uint8)
+        off = np.zeros(n_msgs + 1, np.uint64)
+        self._ck(self.L.pvacb_dec_text(self.h, c.h, n_msgs, _p(buf, C.c_uint8), cap, _p(off, C.c_uint64)))
+        return [buf[int(off[i]):int(off[i + 1])].tobytes() for i in range(n_msgs)]
+
+    def concat(self, parts):
+        arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_batch_concat(self.h, arr, len(parts), C.byref(out)))
         return Batch(self, out)
 
     def compact_edges(self, a):

@@ -22,12 +22,15 @@ namespace pvacb {
 __global__ void enc_plan_kernel(uint64_t n, const uint64_t* __restrict__ values, uint64_t batch_seed, const uint64_t* __restrict__ states,
                                 uint64_t canon_tag, int Z2, int Z3, int S,
                                 SharePlan* __restrict__ plans, uint32_t* __restrict__ n_edges, uint32_t* __restrict__ n_extra,
-                                uint64_t* __restrict__ j_ztag, uint64_t* __restrict__ j_nlo, uint64_t* __restrict__ j_nhi, uint8_t* __restrict__ j_flags) {
+                                uint64_t* __restrict__ j_ztag, uint64_t* __restrict__ j_nlo, uint64_t* __restrict__ j_nhi, uint8_t* __restrict__ j_flags,
+                                uint64_t* __restrict__ draws /* optional: tape words consumed per item */) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t s0 = states ? states[i] : item_stream_state(batch_seed, i);
-    if (S == 2) plan_item(s0, values[i], canon_tag, Z2, Z3, plans[2 * i], plans[2 * i + 1]);
-    else plan_single(s0, fp_make(values[2 * i], values[2 * i + 1]), canon_tag, Z2, Z3, plans[i]);     // enc_fp_depth: values are Fp (lo, hi)
+    uint64_t used;
+    if (S == 2) used = plan_item(s0, values[i], canon_tag, Z2, Z3, plans[2 * i], plans[2 * i + 1]);
+    else used = plan_single(s0, fp_make(values[2 * i], values[2 * i + 1]), canon_tag, Z2, Z3, plans[i]);     // enc_fp_depth: values are Fp (lo, hi)
+    if (draws) draws[i] = used;
     const int G = Z2 + Z3;
     uint32_t edges = 0, extra = 0;
     for (int s = 0; s < S; s++) {
@@ -108,14 +111,14 @@ void plan_noise_host(int depth_hint, int& z2, int& z3) {
 }
 
 // shares = 2: enc_value_depth (values: n u64 plaintexts); shares = 1: enc_fp_depth (values: n x (lo, hi) field elements)
-int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint, int shares) {
+int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint, int shares, uint64_t* h_draws) {
     const uint64_t S = (uint64_t)shares;
     if (shares != 1 && shares != 2) return PV_E_ARG;
     Scratch scratch(ctx);
     int Z2, Z3;
     plan_noise_host(depth_hint, Z2, Z3);
     const int G = Z2 + Z3, RAW = kSignal + 2 * Z2 + 3 * Z3;
-    if (Z2 > kMaxZ2 || Z3 > kMaxZ3 || G < 1) { ctx->last_error = "enc_value: depth_hint outside the supported range 0..9"; return PV_E_ARG; }
+    if (Z2 > kMaxZ2 || Z3 > kMaxZ3 || G < 1) { ctx->last_error = "enc_value: depth_hint outside the supported range 0..23"; return PV_E_ARG; }
     int rc;
     if (n == 0) return batch_alloc(ctx, 0, 0, 0, out);
     uint64_t *d_vals = nullptr, *d_states = nullptr;
@@ -144,8 +147,11 @@ int op_enc_value(Ctx* ctx, const uint64_t* values, bool on_device, uint64_t n, u
     if ((rc = scratch.alloc(j_nhi, njobs * 8))) return rc;
     if ((rc = scratch.alloc(j_flags, njobs))) return rc;
     if ((rc = scratch.alloc(prf, njobs * 16))) return rc;
+    uint64_t* d_draws = nullptr;
+    if (h_draws && (rc = scratch.alloc(d_draws, n * 8))) return rc;
     enc_plan_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(n, on_device ? values : d_vals, batch_seed, d_states, ctx->kv.canon_tag, Z2, Z3, shares, plans, cnt, xcnt,
-                                                                        j_ztag, j_nlo, j_nhi, j_flags);
+                                                                        j_ztag, j_nlo, j_nhi, j_flags, d_draws);
+    if (h_draws) PV_CUDA(cudaMemcpyAsync(h_draws, d_draws, n * 8, cudaMemcpyDeviceToHost, ctx->stream));   // complete at the next stream sync below
     if ((rc = scan_u32(ctx, n, cnt, eoff))) return rc;
     if ((rc = scan_u32(ctx, n, xcnt, xoff))) return rc;
     uint32_t tot[2] = {0, 0};

@@ -7,9 +7,9 @@
 
 namespace pvacb {
 
-constexpr int kMaxZ2 = 8, kMaxZ3 = 4;
-constexpr int kMaxRaw = kSignal + 2 * kMaxZ2 + 3 * kMaxZ3;   // 36
-constexpr int kMaxRnd = (kSignal - 1) + kMaxZ2 + 2 * kMaxZ3; // 23
+constexpr int kMaxZ2 = 16, kMaxZ3 = 8;      // plan_noise(depth_hint) for depth_hint <= 23 (enc_text uses 2 + block index)
+constexpr int kMaxRaw = kSignal + 2 * kMaxZ2 + 3 * kMaxZ3;   // 64
+constexpr int kMaxRnd = (kSignal - 1) + kMaxZ2 + 2 * kMaxZ3; // 39
 
 struct SharePlan {
     Fp value;                 // the share being encrypted (v+mask or -mask)

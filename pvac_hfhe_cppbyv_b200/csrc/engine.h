@@ -194,7 +194,8 @@ int sigma_xor_rows(Ctx* ctx, uint64_t npairs, const uint2* d_pairs, uint64_t* ou
 int scan_u32(Ctx* ctx, uint64_t n, const uint32_t* in, uint32_t* out);
 
 // ---- ops
-int op_enc_value(Ctx* ctx, const uint64_t* h_or_d_values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint = 0, int shares = 2);
+int op_enc_value(Ctx* ctx, const uint64_t* h_or_d_values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint = 0, int shares = 2,
+                 uint64_t* h_draws = nullptr /* optional: tape words each item consumed */);
 void plan_noise_host(int depth_hint, int& z2, int& z3);
 int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode /*0 add, 1 sub*/, Batch** out);
 int op_ct_scale(Ctx* ctx, const Batch* A, Fp s, Batch** out);

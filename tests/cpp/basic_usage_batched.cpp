@@ -1,7 +1,6 @@
 // Config 1 of BASELINE.json through the batched C++ API (include/pvacb.hpp): the arithmetic scenarios of the reference's
-// examples/basic_usage.cpp (its sections 2-14 and 16-22, 27-29 -- everything on the enc/add/sub/mul/dec path; x^16 needs
-// > 62 GB in the reference itself, commit_ct and the text codec are out of scope), each run on a batch of LANES independent
-// lanes at once instead of one ciphertext. Lane 0 carries the reference's own operand values.
+// examples/basic_usage.cpp (all of its sections except x^16, which needs > 62 GB in the reference itself), each run on a
+// batch of LANES independent lanes at once instead of one ciphertext. Lane 0 carries the reference's own operand values.
 //
 //   g++ -std=c++17 -O2 -I include tests/cpp/basic_usage_batched.cpp -L pvac_hfhe_cppbyv_b200 -lpvacb -Wl,-rpath,... -o basic_usage_batched
 #include <cstdio>
@@ -158,6 +157,23 @@ int main() {
         Ciphers x = enc({100}), y = enc({100});
         check(dec(x) == dec(y), "both = 100");
         check(eng.to_wire(x) != eng.to_wire(y), "diff rnd");
+    }
+
+    section("commit uniq");
+    {
+        auto cm = eng.commit_ct(enc({100, 100}));
+        check(cm[0] != cm[1], "diff ct -> diff commit");
+    }
+
+    // the four text sections of the reference as ONE batch of messages
+    section("text ascii / special / utf8 / empty");
+    {
+        const std::vector<std::string> msgs = {"Hello, pvac-hfhe! This is a test of the text encryption.", "!@#$%^&*()_+-=[]{}|;':\",./<>?`~ \t\n", "\xd0\x9f\xd1\x80\xd0\xb8\xd0\xb2\xd0\xb5\xd1\x82 \xe4\xbd\xa0\xe5\xa5\xbd \xf0\x9f\x94\x90", ""};
+        auto back = eng.dec_text(eng.enc_text(msgs, g_seed++), msgs.size());
+        check(back[0] == msgs[0], "ascii roundtrip");
+        check(back[1] == msgs[1], "special roundtrip");
+        check(back[2] == msgs[2], "utf8 roundtrip");
+        check(back[3] == msgs[3], "empty roundtrip");
     }
 
     section("perf 100 adds");

@@ -204,3 +204,15 @@ def test_depth_hints_and_riders(port, ref, both):
     do, dr = ko.ct_div_const(ao, k7), kr.ct_div_const(ar, k7)
     assert ct_equal(port.ct_export(do), ref.ct_export(dr))[0]
     assert _v(ko.dec_value(do)) == 11 and _v(ko.dec_value(ko.ct_neg(ao))) == P - 77
+
+
+def test_enc_text(port, ref, both):
+    """utils/text.hpp:39-87: length ciphertext + one enc_fp_depth per 15-byte block with depth hints 2, 3, ... from one tape"""
+    ko, kr = both
+    for seed, msg in ((51, b""), (52, b"hello"), (53, b"exactly15bytes!"), (54, "pvac éè 你好 16+ bytes, three blocks".encode()), (55, bytes(range(256))[:100])):
+        co, cr = ko.enc_text(seed, msg), kr.enc_text(seed, msg)
+        assert len(co) == len(cr) == 1 + (len(msg) + 14) // 15
+        for a, b in zip(co, cr):
+            ok, k = ct_equal(port.ct_export(a), ref.ct_export(b))
+            assert ok, (seed, k)
+        assert kr.dec_text(cr) == msg

@@ -136,6 +136,14 @@ int pvacb_enc_text(pvacb_ctx* ctx, const uint8_t* bytes, const uint64_t* msg_off
                    pvacb_batch** out);
 int pvacb_dec_text(pvacb_ctx* ctx, const pvacb_batch* c, size_t n_msgs, uint8_t* out_bytes, size_t cap, uint64_t* out_off /* n_msgs + 1 */);
 
+/* Cipher ct_recrypt(pk, ek, C)                             ops/recrypt.hpp:26  (zero_pool = EvalKey::zero_pool as a batch, e.g. from
+ * pvacb_enc_zero_depth; item i draws its pool indices from its tape stream). double sigma_density(pk, C)  ops/encrypt.hpp:29.
+ * void ubk_apply(pk, C)  crypto/matrix.hpp:306 (returns a new batch). pvacb_ubk_perm: Ubk::perm (8192 entries). */
+int pvacb_ct_recrypt(pvacb_ctx* ctx, const pvacb_batch* c, const pvacb_batch* zero_pool, uint64_t batch_seed, const uint64_t* tape_states, pvacb_batch** out);
+int pvacb_sigma_density(pvacb_ctx* ctx, const pvacb_batch* c, double* out /* n */);
+int pvacb_ubk_apply(pvacb_ctx* ctx, const pvacb_batch* c, pvacb_batch** out);
+int pvacb_ubk_perm(pvacb_ctx* ctx, uint16_t* perm_out /* 8192 */);
+
 /* ---- batches --------------------------------------------------------------------------------------------------- */
 void pvacb_batch_free(pvacb_batch* b);
 size_t pvacb_batch_count(const pvacb_batch* b);
@@ -145,6 +153,8 @@ size_t pvacb_batch_device_bytes(const pvacb_batch* b);
 int pvacb_batch_offsets(pvacb_ctx* ctx, const pvacb_batch* b, uint32_t* layer_off, uint32_t* edge_off);
 /* the items of parts[0], parts[1], ... as one new batch (device copy; the inverse of pvacb_batch_slice) */
 int pvacb_batch_concat(pvacb_ctx* ctx, const pvacb_batch* const* parts, size_t nparts, pvacb_batch** out);
+/* out item i = item index[i] of srcs[which[i]] (up to 4 source batches): gather / scatter / interleave of ciphertexts */
+int pvacb_batch_select(pvacb_ctx* ctx, const pvacb_batch* const* srcs, int nsrc, const uint32_t* which, const uint32_t* index, size_t n, pvacb_batch** out);
 /* slice [first, first+count) of a batch as a new batch (device copy) */
 int pvacb_batch_slice(pvacb_ctx* ctx, const pvacb_batch* b, size_t first, size_t count, pvacb_batch** out);
 

@@ -77,6 +77,10 @@ def lib():
         "orc_ct_scale": (vp, [vp, P(u64)]),
         "orc_commit_ct": (None, [vp, vp, P(u8)]),
         "orc_enc_text": (i32, [vp, u64, P(u8), u64, P(vp), i32, P(u64)]),
+        "orc_ubk_perm": (None, [u64, P(C.c_int32)]),
+        "orc_ubk_apply": (vp, [vp, vp]),
+        "orc_sigma_density": (C.c_double, [vp]),
+        "orc_ct_recrypt": (vp, [vp, u64, vp, P(vp), i32, P(u64)]),
         "orc_compact_edges": (vp, [vp]),
         "orc_ct_mul": (vp, [vp, u64, vp, vp, P(u64)]),
         "orc_dec_value": (i32, [vp, vp, P(u64)]),
@@ -297,6 +301,25 @@ class Keys:
         n = lib().orc_enc_text(self.h, tape_state, _p(m, C.c_uint8), len(msg), arr, cap, C.byref(d))
         _last_draws = int(d.value)
         return [arr[i] for i in range(n)]
+
+    def ubk_perm(self):
+        o = np.zeros(8192, np.int32)
+        lib().orc_ubk_perm(self.export(with_H=False)["canon_tag"], _p(o, C.c_int32))
+        return o
+
+    def ubk_apply(self, c):
+        return lib().orc_ubk_apply(self.h, c)
+
+    def sigma_density(self, c):
+        return float(lib().orc_sigma_density(c))
+
+    def ct_recrypt(self, tape_state, c, pool):
+        global _last_draws
+        arr = (C.c_void_p * max(len(pool), 1))(*pool)
+        d = C.c_uint64()
+        r = lib().orc_ct_recrypt(self.h, tape_state, c, arr, len(pool), C.byref(d))
+        _last_draws = int(d.value)
+        return r
 
     def compact_edges(self, a):
         return lib().orc_compact_edges(a)

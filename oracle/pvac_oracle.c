@@ -867,6 +867,91 @@ void orc_commit_ct(const orc_keys* k, const orc_ct* C, uint8_t out[32]) {
     sha_final(&s, out);
 }
 
+/* ------------------------------------------------------------------ UBK, sigma_density, ct_recrypt */
+/* crypto/matrix.hpp:95-164 -- Fisher-Yates over 0..m-1 driven by SHA-256("UBK" || LE64(tag) || LE64(ctr)), 4 words per hash */
+void orc_ubk_perm(uint64_t canon_tag, int32_t* perm /* 8192 */) {
+    for (int i = 0; i < ORC_M_BITS; i++) perm[i] = i;
+    uint64_t ctr = 0;
+    uint8_t buf[32];
+    int idx = 32;
+    for (int i = ORC_M_BITS - 1; i > 0; --i) {
+        uint64_t M = (uint64_t)i + 1, lim = UINT64_MAX - (UINT64_MAX % M), x;
+        for (;;) {
+            if (idx >= 32) {
+                sha_t s; sha_init(&s);
+                sha_update(&s, "UBK", 3);
+                sha_u64le(&s, canon_tag);
+                sha_u64le(&s, ctr++);
+                sha_final(&s, buf);
+                idx = 0;
+            }
+            x = le64(buf + idx);
+            idx += 8;
+            if (x <= lim) break;
+        }
+        int j = (int)(x % M);
+        int32_t t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+    }
+}
+/* crypto/matrix.hpp:167-188,306-310 -- every sigma: out bit inv[src] set for every set bit src */
+static void ubk_apply(const orc_keys* k, orc_ct* c) {
+    static int32_t perm[ORC_M_BITS], inv[ORC_M_BITS];
+    static uint64_t tag_of = 0; static int have = 0;
+    if (!have || tag_of != k->canon_tag) {
+        orc_ubk_perm(k->canon_tag, perm);
+        for (int i = 0; i < ORC_M_BITS; i++) inv[perm[i]] = i;
+        tag_of = k->canon_tag; have = 1;
+    }
+    for (uint32_t e = 0; e < c->nE; e++) {
+        uint64_t o[ORC_M_WORDS];
+        memset(o, 0, sizeof o);
+        for (int src = 0; src < ORC_M_BITS; src++)
+            if ((c->E[e].s[src >> 6] >> (src & 63)) & 1) { int j = inv[src]; o[j >> 6] |= 1ull << (j & 63); }
+        memcpy(c->E[e].s, o, sizeof o);
+    }
+}
+orc_ct* orc_ubk_apply(const orc_keys* k, const orc_ct* a) {
+    orc_ct* c = ct_new();
+    for (uint32_t i = 0; i < a->nL; i++) ct_push_layer(c, a->L[i]);
+    for (uint32_t i = 0; i < a->nE; i++) *ct_push_edge(c) = a->E[i];
+    ubk_apply(k, c);
+    return c;
+}
+/* ops/encrypt.hpp:29-37 */
+double orc_sigma_density(const orc_ct* c) {
+    if (c->nE == 0) return 0.0;
+    long double ones = 0, total = 0;
+    for (uint32_t e = 0; e < c->nE; e++) {
+        uint64_t p = 0;
+        for (int w = 0; w < ORC_M_WORDS; w++) p += (uint64_t)__builtin_popcountll(c->E[e].s[w]);
+        ones += p;
+        total += ORC_M_BITS;
+    }
+    return (double)(ones / total);
+}
+/* ops/recrypt.hpp:26-41 */
+orc_ct* orc_ct_recrypt(const orc_keys* k, uint64_t tape_state, const orc_ct* in, orc_ct* const* pool, int npool, uint64_t* draws) {
+    tape_t t = { tape_state, 0 };
+    orc_ct* r = ct_new();
+    for (uint32_t i = 0; i < in->nL; i++) ct_push_layer(r, in->L[i]);
+    for (uint32_t i = 0; i < in->nE; i++) *ct_push_edge(r) = in->E[i];
+    if (npool == 0 || in->nE == 0) { if (draws) *draws = 0; return r; }
+    for (int it = 0; it < 8; it++) {
+        double d = orc_sigma_density(r);
+        if (!(d < 0.495 || d > 0.505)) break;
+        uint64_t idx = tape_u64(&t) % (uint64_t)npool;
+        orc_ct* s = concat_ct(r, pool[idx]);     /* ct_add: includes guard_budget + compact_layers */
+        orc_ct_free(r);
+        r = s;
+        ubk_apply(k, r);
+        if (r->nE > 1200000u) compact_edges(r);
+    }
+    compact_edges(r);
+    compact_layers(r);
+    if (draws) *draws = t.draws;
+    return r;
+}
+
 /* ops/decrypt.hpp:12-89. Returns 0, or -1 where the reference aborts (parent out of range / cycle). */
 static int layer_R(const orc_keys* k, const orc_ct* C, uint32_t lid, int* vis, fp_t* cache, fp_t* out) {
     if (lid >= C->nL) return -1;

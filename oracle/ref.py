@@ -83,6 +83,10 @@ def lib():
         "ref_commit_ct": (None, [vp, vp, P(u8)]),
         "ref_enc_text": (i32, [vp, u64, P(u8), u64, P(vp), i32]),
         "ref_dec_text": (i32, [vp, P(vp), i32, P(u8), i32]),
+        "ref_ubk_perm": (None, [vp, P(C.c_int32)]),
+        "ref_ubk_apply": (vp, [vp, vp]),
+        "ref_sigma_density": (C.c_double, [vp, vp]),
+        "ref_ct_recrypt": (vp, [vp, u64, vp, P(vp), i32]),
         "ref_compact_edges": (vp, [vp, vp]),
         "ref_ct_mul": (vp, [vp, u64, vp, vp]),
         "ref_dec_value": (None, [vp, vp, P(u64)]),
@@ -275,6 +279,21 @@ class Keys:
         buf = np.zeros(15 * len(cts) + 16, np.uint8)
         n = lib().ref_dec_text(self.h, arr, len(cts), _p(buf, C.c_uint8), len(buf))
         return buf[:n].tobytes()
+
+    def ubk_perm(self):
+        o = np.zeros(8192, np.int32)
+        lib().ref_ubk_perm(self.h, _p(o, C.c_int32))
+        return o
+
+    def ubk_apply(self, c):
+        return lib().ref_ubk_apply(self.h, c)
+
+    def sigma_density(self, c):
+        return float(lib().ref_sigma_density(self.h, c))
+
+    def ct_recrypt(self, tape_state, c, pool):
+        arr = (C.c_void_p * max(len(pool), 1))(*pool)
+        return lib().ref_ct_recrypt(self.h, tape_state, c, arr, len(pool))
 
     def compact_edges(self, a):
         return lib().ref_compact_edges(self.h, a)

@@ -237,6 +237,27 @@ int ref_dec_text(void* h, void** cts, int n, uint8_t* out, int cap) {
     memcpy(out, s.data(), s.size());
     return (int)s.size();
 }
+void ref_ubk_perm(void* h, int32_t* perm) {
+    Keys* k = (Keys*)h;
+    if (k->pk.ubk.perm.empty()) k->pk.ubk = gen_ubk_public(k->pk.canon_tag, k->pk.prm.m_bits);
+    for (size_t i = 0; i < k->pk.ubk.perm.size(); i++) perm[i] = k->pk.ubk.perm[i];
+}
+void* ref_ubk_apply(void* h, void* c) {
+    Keys* k = (Keys*)h;
+    if (k->pk.ubk.perm.empty()) k->pk.ubk = gen_ubk_public(k->pk.canon_tag, k->pk.prm.m_bits);
+    Cipher* r = new Cipher(*(Cipher*)c);
+    ubk_apply(k->pk, *r);
+    return r;
+}
+double ref_sigma_density(void* h, void* c) { return sigma_density(((Keys*)h)->pk, *(Cipher*)c); }
+void* ref_ct_recrypt(void* h, uint64_t tape_state, void* c, void** pool, int npool) {
+    Keys* k = (Keys*)h;
+    if (k->pk.ubk.perm.empty()) k->pk.ubk = gen_ubk_public(k->pk.canon_tag, k->pk.prm.m_bits);
+    EvalKey ek;
+    for (int i = 0; i < npool; i++) ek.zero_pool.push_back(*(Cipher*)pool[i]);
+    ref_seed(tape_state);
+    return new Cipher(ct_recrypt(k->pk, ek, *(Cipher*)c));
+}
 void* ref_enc_value_depth(void* h, uint64_t tape_state, uint64_t v, int depth) {
     Keys* k = (Keys*)h;
     ref_seed(tape_state);

@@ -43,6 +43,7 @@ SYMBOLS = [
     "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges", "pvacb_batch_checksum", "pvacb_commit_ct",
     "pvacb_enc_value_depth", "pvacb_enc_zero_depth", "pvacb_plan_noise", "pvacb_ct_neg", "pvacb_ct_div_const", "pvacb_enc_fp_depth",
     "pvacb_enc_text", "pvacb_dec_text", "pvacb_batch_concat",
+    "pvacb_ct_recrypt", "pvacb_sigma_density", "pvacb_ubk_apply", "pvacb_ubk_perm", "pvacb_batch_select",
 ]
 
 
@@ -120,6 +121,11 @@ def load_library():
         "pvacb_enc_text": (i32, [vp, P(u8), P(u64), sz, u64, P(u64), P(vp)]),
         "pvacb_dec_text": (i32, [vp, vp, sz, P(u8), sz, P(u64)]),
         "pvacb_batch_concat": (i32, [vp, P(vp), sz, P(vp)]),
+        "pvacb_ct_recrypt": (i32, [vp, vp, vp, u64, P(u64), P(vp)]),
+        "pvacb_sigma_density": (i32, [vp, vp, P(C.c_double)]),
+        "pvacb_ubk_apply": (i32, [vp, vp, P(vp)]),
+        "pvacb_ubk_perm": (i32, [vp, P(u16)]),
+        "pvacb_batch_select": (i32, [vp, P(vp), i32, P(u32), P(u32), sz, P(vp)]),
         "pvacb_plan_noise": (i32, [i32, P(i32), P(i32)]),
         "pvacb_ct_neg": (i32, [vp, vp, P(vp)]),
         "pvacb_ct_div_const": (i32, [vp, vp, P(u64), P(vp)]),
@@ -361,6 +367,38 @@ class Engine:
         arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
         out = C.c_void_p()
         self._ck(self.L.pvacb_batch_concat(self.h, arr, len(parts), C.byref(out)))
+        return Batch(self, out)
+
+    def ct_recrypt(self, c, zero_pool, batch_seed=0, tape_states=None):
+        st = _u64(tape_states) if tape_states is not None else None
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_ct_recrypt(self.h, c.h, zero_pool.h, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        return Batch(self, out)
+
+    def make_evalkey(self, pool_size, depth_hint, batch_seed):
+        """EvalKey of the reference (ops/recrypt.hpp:12): (zero_pool batch, enc_one batch); every entry on its own tape stream"""
+        return self.enc_zero_depth(pool_size, depth_hint, batch_seed), self.enc_value(np.array([1], np.uint64), batch_seed + 1)
+
+    def sigma_density(self, c):
+        out = np.zeros(len(c), np.float64)
+        self._ck(self.L.pvacb_sigma_density(self.h, c.h, _p(out, C.c_double)))
+        return out
+
+    def ubk_apply(self, c):
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_ubk_apply(self.h, c.h, C.byref(out)))
+        return Batch(self, out)
+
+    def ubk_perm(self):
+        o = np.zeros(8192, np.uint16)
+        self._ck(self.L.pvacb_ubk_perm(self.h, _p(o, C.c_uint16)))
+        return o
+
+    def select(self, srcs, which, index):
+        arr = (C.c_void_p * len(srcs))(*[s.h for s in srcs])
+        w, ix = np.ascontiguousarray(which, np.uint32), np.ascontiguousarray(index, np.uint32)
+        out = C.c_void_p()
+        self._ck(self.L.pvacb_batch_select(self.h, arr, len(srcs), _p(w, C.c_uint32), _p(ix, C.c_uint32), len(w), C.byref(out)))
         return Batch(self, out)
 
     def compact_edges(self, a):

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libpvacb.so")
 
-SOURCES = ["engine.cu", "prf.cu", "sigma.cu", "enc.cu", "arith.cu", "mul.cu", "compact.cu", "commit.cu", "text.cu", "dec.cu", "extras.cu", "keygen.cpp"]
+SOURCES = ["engine.cu", "prf.cu", "sigma.cu", "enc.cu", "arith.cu", "mul.cu", "compact.cu", "commit.cu", "text.cu", "recrypt.cu", "dec.cu", "extras.cu", "keygen.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -125,6 +125,10 @@ static void derive_key_view(Ctx* ctx) {
     kv.T0 = ctx->d_aes->t0;
     kv.sbox = ctx->d_aes->sbox;
     lpn_masks_from_secret(&h[9], ctx->lpn_m);
+    ctx->h_ubk_perm.resize(kMBits);
+    gen_ubk_perm_host(kv.canon_tag, ctx->h_ubk_perm.data());
+    if (!ctx->d_ubk_perm) cudaMalloc((void**)&ctx->d_ubk_perm, kMBits * 2);
+    cudaMemcpy(ctx->d_ubk_perm, ctx->h_ubk_perm.data(), kMBits * 2, cudaMemcpyHostToDevice);
     ctx->have_keys = true;
 }
 
@@ -216,6 +220,7 @@ void pvacb_ctx_destroy(pvacb_ctx* x) {
     cudaFree(ctx->d_aes);
     cudaFree(ctx->d_primes);
     cudaFree(ctx->d_work);
+    cudaFree(ctx->d_ubk_perm);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);

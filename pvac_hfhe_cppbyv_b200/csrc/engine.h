@@ -50,6 +50,8 @@ struct Ctx {
     uint64_t* d_primes = nullptr;    // libstdc++ bucket-count table
     int n_primes = 0;
     unsigned long long* d_work = nullptr;   // work-queue counter of the persistent sigma kernel
+    uint16_t* d_ubk_perm = nullptr;         // UBK: public permutation of the sigma bits (crypto/matrix.hpp:95-164), derived from canon_tag
+    std::vector<uint16_t> h_ubk_perm;
     uint32_t* h_mail = nullptr;             // mapped pinned "mailbox": kernels drop small results here (see SmallRead)
     uint32_t* d_mail = nullptr;             // device alias of h_mail
     KeyView kv{};
@@ -202,6 +204,9 @@ int op_ct_scale(Ctx* ctx, const Batch* A, Fp s, Batch** out);
 int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, const uint64_t* h_states, Batch** out);
 int op_dec_value(Ctx* ctx, const Batch* C, uint64_t* h_out /*n x 2*/);
 int op_commit_ct(Ctx* ctx, const Batch* b, uint8_t* h_out /*n x 32*/);
+void gen_ubk_perm_host(uint64_t canon_tag, uint16_t perm[kMBits]);
+int batch_select(Ctx* ctx, const Batch* const* srcs, int nsrc, const std::vector<uint32_t>& which, const std::vector<uint32_t>& index, Batch** out);
+int batch_concat(Ctx* ctx, const Batch* const* parts, size_t nparts, Batch** out);
 
 // compact_layers (ops/encrypt.hpp:73-104) of every ciphertext of b, in place (layer arrays shrink, edges stay).
 int compact_layers_batch(Ctx* ctx, Batch* b);

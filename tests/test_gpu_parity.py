@@ -600,3 +600,48 @@ def test_enc_text_dec_text_vs_oracle(engine, api, port, port_keys):
     parts = [engine.slice(T, 0, 3), engine.slice(T, 3, len(T) - 3)]
     back = api.split_items(engine.export_soa(engine.concat(parts)))
     assert all(ct_equal(a, b)[0] for a, b in zip(back, got)) and len(back) == len(got)
+
+
+def test_recrypt_ubk_density_vs_oracle(engine, api, port, port_keys):
+    """pvacb_ct_recrypt / pvacb_ubk_apply / pvacb_sigma_density / pvacb_ubk_perm (ops/recrypt.hpp:26-41, crypto/matrix.hpp:95-188,
+    ops/encrypt.hpp:29-37) on one ragged batch: a balanced ciphertext (compaction only), an all-zero-sigma one (8 balancing rounds),
+    a half-zero one (a few rounds), an empty one (returned as it is) -- each bit-identical to the oracle, which is pinned on the
+    unmodified reference for the same cases."""
+    K = port_keys
+    assert np.array_equal(engine.ubk_perm().astype(np.int32), K.ubk_perm())
+    base = [K.enc_value(port.item_stream_state(9500, i), 5 + i) for i in range(4)]
+    ex = [port.ct_export(c) for c in base]
+    z_all = {k: v.copy() for k, v in ex[1].items()}; z_all["sigma"][:] = 0
+    z_half = {k: v.copy() for k, v in ex[2].items()}; z_half["sigma"][:30] = 0
+    empty = {k: v[:0] for k, v in ex[3].items()}
+    items = [ex[0], z_all, z_half, empty]
+    X = engine.import_soa(api.join_items(items))
+    pool_dev = engine.enc_zero_depth(3, 1, 9600)
+    pool_orc = [K.enc_zero_depth(port.item_stream_state(9600, i), 1) for i in range(3)]
+    # building blocks
+    dens = engine.sigma_density(X)
+    assert [float(d) for d in dens] == [K.sigma_density(port.ct_import(it)) for it in items]
+    U = api.split_items(engine.export_soa(engine.ubk_apply(X)))
+    for i, it in enumerate(items):
+        assert ct_equal(U[i], port.ct_export(K.ubk_apply(port.ct_import(it))))[0], i
+    # recrypt
+    st = np.array([port.item_stream_state(9700, i) for i in range(4)], np.uint64)
+    R = engine.ct_recrypt(X, pool_dev, tape_states=st)
+    got = api.split_items(engine.export_soa(R))
+    rounds = []
+    for i, it in enumerate(items):
+        want = K.ct_recrypt(int(st[i]), port.ct_import(it), pool_orc)
+        rounds.append(port.tape_draws())
+        ok, f = ct_equal(got[i], port.ct_export(want))
+        assert ok, (i, f)
+    assert rounds[0] == 0 and rounds[1] == 8 and 0 < rounds[2] <= 8 and rounds[3] == 0
+    assert [fpv(x) for x in engine.dec_value(R)] == [5, 6, 7, 0]
+    # an empty pool returns everything unchanged
+    none = engine.enc_zero_depth(0, 1, 1)
+    back = api.split_items(engine.export_soa(engine.ct_recrypt(X, none, 1)))
+    assert all(ct_equal(b, it)[0] for b, it in zip(back, items))
+    # batch_select: reorder / duplicate / interleave
+    S = api.split_items(engine.export_soa(engine.select([X, pool_dev], [1, 0, 0, 1, 0], [2, 3, 0, 0, 0])))
+    P = api.split_items(engine.export_soa(pool_dev))
+    for g, w in zip(S, [P[2], items[3], items[0], P[0], items[0]]):
+        assert ct_equal(g, w)[0]

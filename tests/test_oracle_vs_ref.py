@@ -216,3 +216,39 @@ def test_enc_text(port, ref, both):
             ok, k = ct_equal(port.ct_export(a), ref.ct_export(b))
             assert ok, (seed, k)
         assert kr.dec_text(cr) == msg
+
+
+def _zero_sigma(d, rows):
+    o = {k: v.copy() for k, v in d.items()}
+    o["sigma"][rows] = 0
+    return o
+
+
+def test_recrypt_ubk_density(port, ref, both):
+    """ops/recrypt.hpp:26-41, crypto/matrix.hpp:95-188: the public permutation, ubk_apply, sigma_density and ct_recrypt -- both its
+    usual path (density already balanced: compact_edges + compact_layers only) and the balancing loop, forced with all-zero sigmas"""
+    ko, kr = both
+    assert np.array_equal(ko.ubk_perm(), kr.ubk_perm()) and sorted(ko.ubk_perm().tolist()) == list(range(8192))
+    a_o, a_r = ko.enc_value(61, 5), kr.enc_value(61, 5)
+    assert ct_equal(port.ct_export(ko.ubk_apply(a_o)), ref.ct_export(kr.ubk_apply(a_r)))[0]
+    assert ko.sigma_density(a_o) == kr.sigma_density(a_r) and 0.49 < ko.sigma_density(a_o) < 0.51
+    pool_o = [ko.enc_zero_depth(70 + i, 1) for i in range(3)]
+    pool_r = [kr.enc_zero_depth(70 + i, 1) for i in range(3)]
+    # balanced input: no pool draw, result = compact_edges + compact_layers
+    ro, rr = ko.ct_recrypt(80, a_o, pool_o), kr.ct_recrypt(80, a_r, pool_r)
+    assert ct_equal(port.ct_export(ro), ref.ct_export(rr))[0] and port.tape_draws() == 0
+    assert ct_equal(port.ct_export(ro), port.ct_export(ko.compact_edges(a_o)))[0]
+    # all-zero sigmas: density 0 -> the loop runs all 8 times (each adds a pool entry and permutes), decrypt unchanged
+    z = _zero_sigma(port.ct_export(a_o), slice(None))
+    ro, rr = ko.ct_recrypt(81, port.ct_import(z), pool_o), kr.ct_recrypt(81, ref.ct_import(z), pool_r)
+    ok, k = ct_equal(port.ct_export(ro), ref.ct_export(rr))
+    assert ok, k
+    assert port.tape_draws() == 8 and _v(ko.dec_value(ro)) == 5
+    # half of the rows zero: density ~0.25, a few iterations
+    z2 = _zero_sigma(port.ct_export(a_o), slice(0, 30))
+    ro, rr = ko.ct_recrypt(82, port.ct_import(z2), pool_o), kr.ct_recrypt(82, ref.ct_import(z2), pool_r)
+    assert ct_equal(port.ct_export(ro), ref.ct_export(rr))[0]
+    # early returns: empty pool, empty ciphertext
+    e = {k: v[:0] for k, v in port.ct_export(a_o).items()}
+    assert ct_equal(port.ct_export(ko.ct_recrypt(83, port.ct_import(e), pool_o)), ref.ct_export(kr.ct_recrypt(83, ref.ct_import(e), pool_r)))[0]
+    assert ct_equal(port.ct_export(ko.ct_recrypt(84, a_o, [])), ref.ct_export(kr.ct_recrypt(84, a_r, [])))[0]

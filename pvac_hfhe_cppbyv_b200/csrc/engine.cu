@@ -46,6 +46,7 @@ int read_small_sync(Ctx* ctx, const SmallRead& r) {
     if (r.n > SmallRead::kMaxItems || total > (uint32_t)SmallRead::kMaxWords) { ctx->last_error = "read_small_sync: too many words"; return PV_E_ARG; }
     small_read_kernel<<<1, 1, 0, ctx->stream>>>(a, ctx->d_mail);
     PV_CUDA(cudaGetLastError());
+    ctx->stat_kernel_launches += 1;
     PV_CUDA(cudaStreamSynchronize(ctx->stream));
     uint32_t o = 0;
     for (int i = 0; i < r.n; i++) { memcpy(r.dst[i], ctx->h_mail + o, r.words[i] * 4); o += r.words[i]; }

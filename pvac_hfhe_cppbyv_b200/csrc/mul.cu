@@ -431,7 +431,8 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
             sr.add(&last[0], epos + (nKeys - 1), 4); sr.add(&last[1], ecnt + (nKeys - 1), 4); sr.add(&h_err, err, 4);
             if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
         }
-        ctx->stat_kernel_launches += 7;
+        // pairs, bucket_insert, sortkey, emit_count + cub: radix sort (histogram, exclusive sum, one onesweep pass per 8 key bits) and scan (init + scan)
+        ctx->stat_kernel_launches += 4 + 2 + (uint64_t)((2 * pbits + ibits + 7) / 8) + 2;
         if (h_err) {
             cleanup();
             if (h_err & 2) { ctx->last_error = "ct_mul: edge layer id out of range"; return PV_E_FORMAT; }

@@ -1,5 +1,5 @@
 // dec_value (ops/decrypt.hpp:12-89) for a batch:
-//   1. prf_R of every BASE layer (prf.cu; the expensive part),
+//   1. prf_R of every DISTINCT BASE-layer seed (prf.cu; the expensive part) -- equal seeds share one evaluation,
 //   2. PROD layers: R = R[pa]*R[pb] resolved per ciphertext (any DAG order; cycles / bad parents are reported where the
 //      reference aborts),
 //   3. one Fermat inversion per layer,
@@ -8,11 +8,6 @@
 #include "engine.h"
 
 namespace pvacb {
-
-__global__ void dec_flags_kernel(uint64_t nL, const uint8_t* __restrict__ rule, uint8_t* __restrict__ flags) {
-    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l < nL) flags[l] = rule[l] == 0 ? 2 : 0;   // active, family 0 (prf_R)
-}
 
 // thread per ciphertext; R[] holds prf_R for BASE layers and 0 elsewhere on entry
 __global__ void dec_resolve_kernel(uint64_t n, const uint32_t* __restrict__ loff, const uint8_t* __restrict__ rule, const uint32_t* __restrict__ pa,
@@ -91,6 +86,48 @@ dec_edges_kernel(uint64_t n, const uint32_t* __restrict__ loff, const uint32_t* 
     }
 }
 
+// ---- BASE layers with equal seeds share one PRF evaluation. The reference memoises by layer id, so c*c (every seed twice),
+// the depth chains (step 3: 320 layers, 2 distinct seeds) or a sum that reuses an operand recompute prf_R for every copy
+// (ops/decrypt.hpp:12-60); R depends on the seed only, so evaluating it once per distinct seed gives the same values.
+// Open-addressing table keyed by a 64-bit hash of the seed; the representative is the smallest layer index with that hash and
+// a layer only aliases it after comparing the full seed (a hash collision just means "evaluate your own").
+__device__ __forceinline__ uint64_t seed_hash(uint64_t z, uint64_t lo, uint64_t hi) {
+    uint64_t h = mix64(hi + 0x9E3779B97F4A7C15ull);
+    h = mix64(lo ^ h);
+    h = mix64(z ^ h);
+    return h | 1ull;            // 0 marks an empty slot
+}
+__global__ void dec_seed_insert_kernel(uint64_t nL, const uint8_t* __restrict__ rule, const uint64_t* __restrict__ ztag, const uint64_t* __restrict__ nlo,
+                                       const uint64_t* __restrict__ nhi, unsigned long long* __restrict__ tkey, uint32_t* __restrict__ trep, uint64_t mask) {
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nL || rule[l] != 0) return;
+    const unsigned long long h = seed_hash(ztag[l], nlo[l], nhi[l]);
+    for (uint64_t slot = h & mask;; slot = (slot + 1) & mask) {
+        unsigned long long old = atomicCAS(&tkey[slot], 0ull, h);
+        if (old == 0ull || old == h) { atomicMin(&trep[slot], (uint32_t)l); return; }
+    }
+}
+__global__ void dec_seed_lookup_kernel(uint64_t nL, const uint8_t* __restrict__ rule, const uint64_t* __restrict__ ztag, const uint64_t* __restrict__ nlo,
+                                       const uint64_t* __restrict__ nhi, const unsigned long long* __restrict__ tkey, const uint32_t* __restrict__ trep,
+                                       uint64_t mask, uint8_t* __restrict__ flags, uint32_t* __restrict__ alias) {
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nL) return;
+    alias[l] = (uint32_t)l;
+    if (rule[l] != 0) { flags[l] = 0; return; }
+    const unsigned long long h = seed_hash(ztag[l], nlo[l], nhi[l]);
+    uint64_t slot = h & mask;
+    while (tkey[slot] != h) slot = (slot + 1) & mask;
+    const uint32_t rep = trep[slot];
+    if (rep != (uint32_t)l && ztag[rep] == ztag[l] && nlo[rep] == nlo[l] && nhi[rep] == nhi[l]) { flags[l] = 0; alias[l] = rep; }
+    else flags[l] = 2;          // active, family 0 (prf_R)
+}
+__global__ void dec_alias_copy_kernel(uint64_t nL, const uint32_t* __restrict__ alias, Fp* __restrict__ R) {
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nL) return;
+    const uint32_t a = alias[l];
+    if (a != (uint32_t)l) R[l] = R[a];      // representatives are never aliased themselves: no ordering hazard
+}
+
 int op_dec_value(Ctx* ctx, const Batch* Cb, uint64_t* h_out) {
     if (Cb->n == 0) return PV_OK;
     Scratch scratch(ctx);
@@ -106,9 +143,20 @@ int op_dec_value(Ctx* ctx, const Batch* Cb, uint64_t* h_out) {
     if ((rc = scratch.alloc(err, 4))) return rc;
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
     if (Cb->nL) {
-        dec_flags_kernel<<<(unsigned)((Cb->nL + 255) / 256), 256, 0, ctx->stream>>>(Cb->nL, Cb->rule, flags);
-        ctx->stat_kernel_launches += 1;
+        uint64_t tsize = 1024;
+        while (tsize < 2 * Cb->nL) tsize <<= 1;
+        unsigned long long* tkey = nullptr;
+        uint32_t *trep = nullptr, *alias = nullptr;
+        if ((rc = scratch.alloc(tkey, tsize * 8)) || (rc = scratch.alloc(trep, tsize * 4)) || (rc = scratch.alloc(alias, nLa * 4))) return rc;
+        PV_CUDA(cudaMemsetAsync(tkey, 0, tsize * 8, ctx->stream));
+        PV_CUDA(cudaMemsetAsync(trep, 0xFF, tsize * 4, ctx->stream));
+        const unsigned lb = (unsigned)((Cb->nL + 255) / 256);
+        dec_seed_insert_kernel<<<lb, 256, 0, ctx->stream>>>(Cb->nL, Cb->rule, Cb->ztag, Cb->nlo, Cb->nhi, tkey, trep, tsize - 1);
+        dec_seed_lookup_kernel<<<lb, 256, 0, ctx->stream>>>(Cb->nL, Cb->rule, Cb->ztag, Cb->nlo, Cb->nhi, tkey, trep, tsize - 1, flags, alias);
+        ctx->stat_kernel_launches += 2;
         if ((rc = prf_run(ctx, Cb->nL, Cb->ztag, Cb->nlo, Cb->nhi, flags, R, nullptr))) return rc;
+        dec_alias_copy_kernel<<<lb, 256, 0, ctx->stream>>>(Cb->nL, alias, R);
+        ctx->stat_kernel_launches += 1;
         dec_resolve_kernel<<<(unsigned)((Cb->n + 127) / 128), 128, 0, ctx->stream>>>(Cb->n, Cb->loff, Cb->rule, Cb->pa, Cb->pb, R, err);
         dec_inv_kernel<<<(unsigned)((Cb->nL + 127) / 128), 128, 0, ctx->stream>>>(Cb->nL, R, Rinv);
         ctx->stat_kernel_launches += 2;

@@ -19,13 +19,16 @@ namespace pvacb {
 // ------------------------------------------------------------------ setup
 __global__ void prf_setup_kernel(KeyView kv, uint64_t ncores, const uint64_t* __restrict__ ztag, const uint64_t* __restrict__ nlo,
                                  const uint64_t* __restrict__ nhi, const uint8_t* __restrict__ flags, uint32_t* __restrict__ rk_out,
-                                 uint64_t* __restrict__ ctr0_out, uint64_t* __restrict__ top_out) {
+                                 uint64_t* __restrict__ ctr0_out, uint64_t* __restrict__ top_out, unsigned int* __restrict__ active_cores) {
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncores) return;
-    uint64_t job = c / 3;
+    const bool in_range = c < ncores;
+    uint64_t job = in_range ? c / 3 : 0;
     int t = (int)(c % 3);
-    uint8_t fl = flags[job];
-    if (!(fl & 2)) return;
+    uint8_t fl = in_range ? flags[job] : 0;
+    const bool active = in_range && (fl & 2);
+    const unsigned m = __ballot_sync(0xffffffffu, active);          // cores really evaluated (inactive jobs cost nothing): for the statistics
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(active_cores, (unsigned)__popc(m));
+    if (!active) return;
     uint32_t rk[60];
     uint64_t ctr0, top0, top1;
     prf_core_setup(kv.kd_mid, kv.digest3, kv.T0, kv.sbox, ztag[job], nlo[job], nhi[job], fnv_prf_dom(fl & 1, t), rk, ctr0, top0, top1);
@@ -107,10 +110,10 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     if ((rc = scratch.alloc(top, ncores * 16))) return rc;
     if (d_ybits_out) ybits = d_ybits_out;
     else if ((rc = scratch.alloc(ybits, ncores * wpc * 8))) return rc;
-    if ((rc = scratch.alloc(rare, 4))) return rc;
-    PV_CUDA(cudaMemsetAsync(rare, 0, 4, ctx->stream));
+    if ((rc = scratch.alloc(rare, 8))) return rc;                    // [0] rare-path flag, [1] active cores
+    PV_CUDA(cudaMemsetAsync(rare, 0, 8, ctx->stream));
 
-    prf_setup_kernel<<<(unsigned)((ncores + 127) / 128), 128, 0, ctx->stream>>>(ctx->kv, ncores, d_ztag, d_nlo, d_nhi, d_flags, rk, ctr0, top);
+    prf_setup_kernel<<<(unsigned)((ncores + 127) / 128), 128, 0, ctx->stream>>>(ctx->kv, ncores, d_ztag, d_nlo, d_nhi, d_flags, rk, ctr0, top, rare + 1);
     if (!ctx->lpn_attr_set) {
         PV_CUDA(cudaFuncSetAttribute(prf_lpn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesRepBytes));
         ctx->lpn_attr_set = true;
@@ -124,10 +127,9 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     prf_finalize_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, ctx->stream>>>(njobs, d_flags, ybits, wpc, top, d_out);
     PV_CUDA(cudaGetLastError());
     ctx->stat_kernel_launches += 3;
-    ctx->stat_aes_blocks += ncores * ((65ull << rpc_log2) + 1);
-
-    unsigned int h_rare = 0;
-    { SmallRead sr; sr.add(&h_rare, rare, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
+    unsigned int h_rare = 0, h_active = 0;
+    { SmallRead sr; sr.add(&h_rare, rare, 4); sr.add(&h_active, rare + 1, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
+    ctx->stat_aes_blocks += (uint64_t)h_active * ((65ull << rpc_log2) + 1);
     if (h_rare) {
         ctx->last_error = "AesCtr256::bounded rejection branch hit (p = 2^-61 per row); not supported on device";
         return PV_E_RARE_PATH;

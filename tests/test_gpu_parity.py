@@ -645,3 +645,16 @@ def test_recrypt_ubk_density_vs_oracle(engine, api, port, port_keys):
     P = api.split_items(engine.export_soa(pool_dev))
     for g, w in zip(S, [P[2], items[3], items[0], P[0], items[0]]):
         assert ct_equal(g, w)[0]
+
+
+def test_dec_shares_prf_between_equal_seeds(engine, api):
+    """dec_value evaluates prf_R once per DISTINCT BASE-layer seed of the batch (the reference recomputes it per layer id,
+    ops/decrypt.hpp:12-60): c*c has 4 BASE layers but 2 seeds, (c+c)*c has 6 BASE layers and the same 2 seeds. Same decrypts."""
+    c = engine.enc_value(np.array([9], np.uint64), 9800)
+    sq = engine.ct_mul(c, c, 9801)
+    tri = engine.ct_mul(engine.ct_add(c, c), c, 9802)
+    cores_per_prf = 3 * (65 * 64 + 1) if engine.L.pvacb_get_prf_mode(engine.h) == api.PRF_LIVE else 3 * (65 * 8192 + 1)
+    for ct, want in ((c, 9), (sq, 81), (tri, 162)):
+        engine.stats_reset()
+        assert fpv(engine.dec_value(ct)[0]) == want
+        assert engine.stats()["aes_blocks"] == 2 * cores_per_prf          # two distinct seeds, whatever the layer count

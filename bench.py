@@ -422,13 +422,25 @@ def main():
                                      "aes_blocks_per_s": blocks_per_s, "lookups_per_block": AES_LDS_PER_BLOCK,
                                      "peak_source": "model: conflict-free LDS.32 issue limit, 32 lanes/clk/SM x 148 SMs x 1965 MHz (ncu: sm__inst_executed_pipe_lsu 94-97%)",
                                      "share_of_step": (lpn_ms / max(lpn_l, 1)) * 1e-3 / spp}}
-        # dec_value of fresh ciphertexts
+        # dec_value of fresh ciphertexts: two PRF evaluations per item + the 23 B/edge weight stream
         for mode, tag, n_dec in ((api.PRF_FAITHFUL, "dec_value_faithful", 2048), (api.PRF_LIVE, "dec_value_live", M)):
             eng.set_prf_mode(mode)
             D = eng.slice(A, 0, min(n_dec, M))
             nd = len(D)
+            eng.stats_reset()
+            eng.profile_enable(True)
+            eng.profile_collect()
             rate, spp = op_rate(lambda k: eng.dec_value(D), nd, steps=3, warmup=3)
-            ops[tag] = {"value": rate, "unit": "dec_value/s", "items_per_step_per_gpu": nd, "ms_per_step": spp * 1e3}
+            pr = eng.profile_collect()
+            eng.profile_enable(False)
+            stx = eng.stats()
+            lpn_ms, lpn_l = pr["prf_lpn"]
+            blocks_per_s = stx["aes_blocks"] / max(lpn_l, 1) / (lpn_ms / max(lpn_l, 1) * 1e-3)
+            lds_peak = 148 * 32 * 1.965e9
+            ops[tag] = {"value": rate, "unit": "dec_value/s", "items_per_step_per_gpu": nd, "ms_per_step": spp * 1e3,
+                        "roofline": {"kernel": "prf_lpn_kernel", "bound": "shared-memory LSU (T-table AES)", "achieved": blocks_per_s * AES_LDS_PER_BLOCK / 1e12,
+                                     "unit": "T shared-memory lookups/s", "peak": lds_peak / 1e12, "frac": blocks_per_s * AES_LDS_PER_BLOCK / lds_peak,
+                                     "aes_blocks_per_s": blocks_per_s, "share_of_step": (lpn_ms / max(lpn_l, 1)) * 1e-3 / spp}}
             D.free()
         eng.set_prf_mode(api.PRF_LIVE)
 

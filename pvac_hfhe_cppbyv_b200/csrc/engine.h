@@ -67,6 +67,7 @@ struct Ctx {
     struct ProfSpan { int tag; cudaEvent_t a, b; };
     std::vector<ProfSpan> prof_spans;
     bool lpn_attr_set = false;
+    std::vector<const void*> configured_kernels;   // kernels whose per-device function attributes this context has set
 };
 
 // profiling tags (pvacb_profile_collect)

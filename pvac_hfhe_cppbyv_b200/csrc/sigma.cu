@@ -299,7 +299,9 @@ template <int G, int WARPS, int MINB, bool FMA = false, int EXP = 0, int CPS = 8
 static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
     auto kern = sigma_fused_kernel<G, WARPS, MINB, FMA, EXP, CPS>;
     constexpr int smem = (int)sizeof(SigmaWarpSmem<G>) * WARPS;
-    static bool attr_done = false;
+    const void* kid = reinterpret_cast<const void*>(kern);
+    bool attr_done = false;                        // function attributes are per device: remember them per context, not per process
+    for (const void* k : ctx->configured_kernels) attr_done |= (k == kid);
     if (!attr_done) {
         PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         // ask for exactly the shared memory MINB CTAs need, not the maximum: with the 228 KB carve-out (28 KB of L1 left) the L2
@@ -307,7 +309,7 @@ static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
         int carve = (int)(((size_t)MINB * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
         if (getenv("PVACB_SIGMA_CARVEOUT")) carve = atoi(getenv("PVACB_SIGMA_CARVEOUT"));
         PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
-        attr_done = true;
+        ctx->configured_kernels.push_back(kid);
     }
     const uint64_t ngroups = (J.n + G - 1) / G;
     uint64_t grid = (ngroups + WARPS - 1) / WARPS;

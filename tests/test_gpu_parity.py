@@ -658,3 +658,28 @@ def test_dec_shares_prf_between_equal_seeds(engine, api):
         engine.stats_reset()
         assert fpv(engine.dec_value(ct)[0]) == want
         assert engine.stats()["aes_blocks"] == 2 * cores_per_prf          # two distinct seeds, whatever the layer count
+
+
+def test_two_contexts_in_one_process(engine, api):
+    """two GPUs driven from one process: keys generated on device 0, the 16.8 MB blob copied peer to peer (NVLink) and adopted on
+    device 1; both contexts then produce byte-identical ciphertexts and products. Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    e1 = api.Engine(device=1, prf_mode=api.PRF_LIVE)
+    try:
+        b0 = torch.empty(api.KEY_BLOB_BYTES, dtype=torch.uint8, device="cuda:0")
+        engine.copy_key_blob_to(b0.data_ptr())
+        torch.cuda.synchronize(0)
+        b1 = b0.to("cuda:1")
+        torch.cuda.synchronize(1)
+        e1.adopt_key_blob_from(b1.data_ptr())
+        v = np.array([3, 2**64 - 1, 12345], np.uint64)
+        out = []
+        for eng in (engine, e1):
+            A, B = eng.enc_value(v, 9900), eng.enc_value(v[::-1].copy(), 9901)
+            P = eng.ct_mul(A, B, 9902)
+            out.append((ct_digest(eng.export_soa(A)), ct_digest(eng.export_soa(P)), eng.dec_value(P).tobytes()))
+        assert out[0] == out[1]
+    finally:
+        e1.close()

@@ -404,6 +404,7 @@ int pvacb_plan_noise(int depth_hint, int* z2, int* z3) {
 static int binop(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, int mode, pvacb_batch** out) {
     Ctx* ctx = C(x);
     if (!a || !b || !out) return PV_E_ARG;
+    if (check_owner(ctx, Bt(a)) || check_owner(ctx, Bt(b))) return PV_E_ARG;
     if (Bt(a)->n != Bt(b)->n) { ctx->last_error = "batches differ in length"; return PV_E_SHAPE; }
     cudaSetDevice(ctx->device);
     Batch* o = nullptr;
@@ -437,6 +438,7 @@ int pvacb_ct_mul_ex(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, ui
     Ctx* ctx = C(x);
     if (!a || !b || !out) return PV_E_ARG;
     if (!ctx->have_keys) return PV_E_NOKEYS;
+    if (check_owner(ctx, Bt(a)) || check_owner(ctx, Bt(b))) return PV_E_ARG;
     if (Bt(a)->n != Bt(b)->n) { ctx->last_error = "batches differ in length"; return PV_E_SHAPE; }
     cudaSetDevice(ctx->device);
     Batch* o = nullptr;
@@ -451,6 +453,7 @@ int pvacb_dec_value(pvacb_ctx* x, const pvacb_batch* c, uint64_t* out) {
     Ctx* ctx = C(x);
     if (!c || !out) return PV_E_ARG;
     if (!ctx->have_keys) return PV_E_NOKEYS;
+    if (check_owner(ctx, Bt(c))) return PV_E_ARG;
     cudaSetDevice(ctx->device);
     return op_dec_value(ctx, Bt(c), out);
 }

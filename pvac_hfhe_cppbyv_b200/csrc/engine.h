@@ -144,6 +144,11 @@ struct SmallRead {
 };
 int read_small_sync(Ctx* ctx, const SmallRead& r);   // enqueue + cudaStreamSynchronize(ctx->stream) + scatter to the host dsts
 
+// a batch lives in the memory of the context (device) that made it
+inline int check_owner(Ctx* ctx, const Batch* b) {
+    if (b && b->ctx != ctx) { ctx->last_error = "batch belongs to another context (device)"; return PV_E_ARG; }
+    return PV_OK;
+}
 int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out);
 void batch_free(Batch* b);
 int batch_clone(Ctx* ctx, const Batch* src, Batch** out);   // field-by-field device copy

@@ -681,5 +681,7 @@ def test_two_contexts_in_one_process(engine, api):
             P = eng.ct_mul(A, B, 9902)
             out.append((ct_digest(eng.export_soa(A)), ct_digest(eng.export_soa(P)), eng.dec_value(P).tobytes()))
         assert out[0] == out[1]
+        with pytest.raises(api.PvacbError):          # a batch is tied to the context (device) that made it
+            e1.ct_add(A, engine.enc_value(v, 1))
     finally:
         e1.close()

@@ -126,6 +126,84 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint1
     __syncwarp();
 }
 
+// phase C for one edge: ordered de-duplication of both labels, XOR-gather of the 128 chosen columns, noise flips, store.
+// gc = the edge's candidates [2][136] in shared memory; bm / cols / more = the warp's scratch.
+template <int EXP, int CPS>
+__device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_t* more, const uint16_t* gc, const SigmaJobs& J, uint64_t canon, uint64_t job,
+                                           const uint4* Hl, int lane) {
+    dedupe_label(bm, cols, more, gc, label_xseed(), J, canon, job, (uint32_t)kNBits, lane);
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
+    // 8 column offsets per step, broadcast reads. The NEXT step's offsets are fetched right after this step's loads
+    // have been issued: shared-memory round trips are slow while the gathers saturate L1TEX (ncu: short-scoreboard
+    // and mio-throttle stalls), so they must not sit between two batches of global loads.
+    if (CPS == 8) {
+        uint4 c0 = *reinterpret_cast<const uint4*>(&cols[0]);
+        uint4 c1 = *reinterpret_cast<const uint4*>(&cols[4]);
+#pragma unroll 1
+        for (int i = 0; i < kXColWt; i += 8) {
+            const uint32_t co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            uint4 v[16];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint4* p = Hl + co[k];
+                if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
+                v[2 * k] = __ldcg(p);
+                v[2 * k + 1] = __ldcg(p + 32);
+            }
+            if (i == 0) {
+                // clear the bitmap again (every word that got a bit belongs to one of the chosen columns) -- under the first loads
+                for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 11] = 0;
+            }
+            if (i + 8 < kXColWt) {
+                c0 = *reinterpret_cast<const uint4*>(&cols[i + 8]);
+                c1 = *reinterpret_cast<const uint4*>(&cols[i + 12]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
+                a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
+            }
+        }
+    } else {
+        uint4 c0 = *reinterpret_cast<const uint4*>(&cols[0]);
+#pragma unroll 1
+        for (int i = 0; i < kXColWt; i += 4) {
+            const uint32_t co[4] = {c0.x, c0.y, c0.z, c0.w};
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint4* p = Hl + co[k];
+                if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
+                v[2 * k] = __ldcg(p);
+                v[2 * k + 1] = __ldcg(p + 32);
+            }
+            if (i == 0) {
+                for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 11] = 0;
+            }
+            if (i + 4 < kXColWt) c0 = *reinterpret_cast<const uint4*>(&cols[i + 4]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
+                a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
+            }
+        }
+    }
+    __syncwarp();
+    // noise bits: the de-dup bitmap is the flip mask (values < 8192: the first KiB of bm)
+    dedupe_label(bm, nullptr, more, gc + kCandPerLabel, label_noise(), J, canon, job, (uint32_t)kMBits, lane);
+    uint4* bn = reinterpret_cast<uint4*>(bm);
+    uint4 n0 = bn[lane], n1 = bn[lane + 32];
+    a0.x ^= n0.x; a0.y ^= n0.y; a0.z ^= n0.z; a0.w ^= n0.w;
+    a1.x ^= n1.x; a1.y ^= n1.y; a1.z ^= n1.z; a1.w ^= n1.w;
+    bn[lane] = make_uint4(0, 0, 0, 0);
+    bn[lane + 32] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    uint64_t row = J.out_row ? J.out_row[job] : job;
+    uint4* o = reinterpret_cast<uint4*>(row < J.out_split ? J.out + row * kMWords : J.out2 + (row - J.out_split) * kMWords);
+    __stcs(o + lane, a0);        // streaming store: the 1 KiB rows are write-once, keep L2 for H
+    __stcs(o + lane + 32, a1);
+}
+
 // EXP (tuning experiments only, wrong results): 1 = no gather loads (hash + de-dup only), 2 = no hashing (synthetic candidates)
 template <int G, int WARPS, int MINB, bool FMA, int EXP = 0, int CPS = 8>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
@@ -195,81 +273,7 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
         __syncwarp();
         // ---- phase C: de-duplicate, gather, flip, store
 #pragma unroll 1
-        for (int e = 0; e < ng; e++) {
-            const uint64_t job = job0 + e;
-            const uint16_t* gc = S.cand + e * 2 * kCandPerLabel;
-            dedupe_label(S.bm, S.cols, S.more, gc, label_xseed(), J, canon, job, (uint32_t)kNBits, lane);
-            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
-            // 8 column offsets per step, broadcast reads. The NEXT step's offsets are fetched right after this step's loads
-            // have been issued: shared-memory round trips are slow while the gathers saturate L1TEX (ncu: short-scoreboard
-            // and mio-throttle stalls), so they must not sit between two batches of global loads.
-            if (CPS == 8) {
-                uint4 c0 = *reinterpret_cast<const uint4*>(&S.cols[0]);
-                uint4 c1 = *reinterpret_cast<const uint4*>(&S.cols[4]);
-#pragma unroll 1
-                for (int i = 0; i < kXColWt; i += 8) {
-                    const uint32_t co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                    uint4 v[16];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const uint4* p = Hl + co[k];
-                        if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
-                        v[2 * k] = __ldcg(p);
-                        v[2 * k + 1] = __ldcg(p + 32);
-                    }
-                    if (i == 0) {
-                        // clear the bitmap again (every word that got a bit belongs to one of the chosen columns) -- under the first loads
-                        for (int q = lane; q < kXColWt; q += 32) S.bm[S.cols[q] >> 11] = 0;
-                    }
-                    if (i + 8 < kXColWt) {
-                        c0 = *reinterpret_cast<const uint4*>(&S.cols[i + 8]);
-                        c1 = *reinterpret_cast<const uint4*>(&S.cols[i + 12]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
-                        a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
-                    }
-                }
-            } else {
-                uint4 c0 = *reinterpret_cast<const uint4*>(&S.cols[0]);
-#pragma unroll 1
-                for (int i = 0; i < kXColWt; i += 4) {
-                    const uint32_t co[4] = {c0.x, c0.y, c0.z, c0.w};
-                    uint4 v[8];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint4* p = Hl + co[k];
-                        if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
-                        v[2 * k] = __ldcg(p);
-                        v[2 * k + 1] = __ldcg(p + 32);
-                    }
-                    if (i == 0) {
-                        for (int q = lane; q < kXColWt; q += 32) S.bm[S.cols[q] >> 11] = 0;
-                    }
-                    if (i + 4 < kXColWt) c0 = *reinterpret_cast<const uint4*>(&S.cols[i + 4]);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
-                        a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
-                    }
-                }
-            }
-            __syncwarp();
-            // noise bits: the de-dup bitmap is the flip mask (values < 8192: the first KiB of bm)
-            dedupe_label(S.bm, nullptr, S.more, gc + kCandPerLabel, label_noise(), J, canon, job, (uint32_t)kMBits, lane);
-            uint4* bn = reinterpret_cast<uint4*>(S.bm);
-            uint4 n0 = bn[lane], n1 = bn[lane + 32];
-            a0.x ^= n0.x; a0.y ^= n0.y; a0.z ^= n0.z; a0.w ^= n0.w;
-            a1.x ^= n1.x; a1.y ^= n1.y; a1.z ^= n1.z; a1.w ^= n1.w;
-            bn[lane] = make_uint4(0, 0, 0, 0);
-            bn[lane + 32] = make_uint4(0, 0, 0, 0);
-            __syncwarp();
-            uint64_t row = J.out_row ? J.out_row[job] : job;
-            uint4* o = reinterpret_cast<uint4*>(row < J.out_split ? J.out + row * kMWords : J.out2 + (row - J.out_split) * kMWords);
-            __stcs(o + lane, a0);        // streaming store: the 1 KiB rows are write-once, keep L2 for H
-            __stcs(o + lane + 32, a1);
-        }
+        for (int e = 0; e < ng; e++) sigma_edge<EXP, CPS>(S.bm, S.cols, S.more, S.cand + e * 2 * kCandPerLabel, J, canon, job0 + e, Hl, lane);
         __syncwarp();
     }
 }

@@ -52,11 +52,11 @@ __device__ __noinline__ void prg_hash_words(const LabelStream ls, const uint64_t
     for (int k = 0; k < 4; k++) out[k] = sha_digest_le64(st, k);
 }
 
-template <int G>
+template <int G, int NH = kCandHashes>
 struct __align__(16) SigmaWarpSmem {
     uint32_t bm[kNBits / 32];               // 2 KiB: de-dup bitmap of the columns, then of the noise bits (= the flip mask)
     uint32_t cols[kXColWt];                 // chosen columns in draw order, as offsets into H in 16-byte units (col * 64)
-    uint16_t cand[G * 2 * kCandPerLabel];   // phase B output: [edge][label][136]
+    uint16_t cand[G * 2 * NH * 4];          // phase B output: [edge][label][4 NH]  (NH = 34: 136 candidates)
     union {
         uint32_t mid[G * 2][8];             // phase A output: SHA-256 state after block 0, per (edge, label)
         uint16_t more[128];                 // phase C, rare: continuation candidates
@@ -67,7 +67,7 @@ struct __align__(16) SigmaWarpSmem {
 // ordered de-duplication of one label. Lanes hold candidates 4*lane..4*lane+3, positions 128..135 follow in gc[128..].
 // Returns with exactly 128 distinct values marked in bm (x_col_wt = err_wt = 128); winners are appended to cols if given.
 __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint16_t* more, const uint16_t* gc, const LabelStream ls,
-                                             const SigmaJobs& J, uint64_t canon, uint64_t job, uint32_t N, int lane) {
+                                             const SigmaJobs& J, uint64_t canon, uint64_t job, uint32_t N, int lane, int n_hashes = kCandHashes) {
     uint2 pk = reinterpret_cast<const uint2*>(gc)[lane];
     uint16_t c[4] = {(uint16_t)(pk.x & 0xffff), (uint16_t)(pk.x >> 16), (uint16_t)(pk.y & 0xffff), (uint16_t)(pk.y >> 16)};
     // the four atomics go out back to back (their results are only needed by the ballots below): one shared-memory round
@@ -90,9 +90,9 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint1
     if (have < kXColWt) {
         // sequential tail, exactly like the reference's one-word-at-a-time loop
         int pos = 128;
-        uint64_t next_ctr = kCandHashes;
+        uint64_t next_ctr = (uint64_t)n_hashes;
         const uint16_t* cur = gc;
-        int cur_base = 0, cur_end = kCandPerLabel;
+        int cur_base = 0, cur_end = 4 * n_hashes;
         uint64_t x[8];
         bool have_x = false;
         while (have < kXColWt) {
@@ -128,10 +128,10 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint1
 
 // phase C for one edge: ordered de-duplication of both labels, XOR-gather of the 128 chosen columns, noise flips, store.
 // gc = the edge's candidates [2][136] in shared memory; bm / cols / more = the warp's scratch.
-template <int EXP, int CPS>
+template <int EXP, int CPS, int NH>
 __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_t* more, const uint16_t* gc, const SigmaJobs& J, uint64_t canon, uint64_t job,
                                            const uint4* Hl, int lane) {
-    dedupe_label(bm, cols, more, gc, label_xseed(), J, canon, job, (uint32_t)kNBits, lane);
+    dedupe_label(bm, cols, more, gc, label_xseed(), J, canon, job, (uint32_t)kNBits, lane, NH);
     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
     // 8 column offsets per step, broadcast reads. The NEXT step's offsets are fetched right after this step's loads
     // have been issued: shared-memory round trips are slow while the gathers saturate L1TEX (ncu: short-scoreboard
@@ -190,7 +190,7 @@ __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_
     }
     __syncwarp();
     // noise bits: the de-dup bitmap is the flip mask (values < 8192: the first KiB of bm)
-    dedupe_label(bm, nullptr, more, gc + kCandPerLabel, label_noise(), J, canon, job, (uint32_t)kMBits, lane);
+    dedupe_label(bm, nullptr, more, gc + 4 * NH, label_noise(), J, canon, job, (uint32_t)kMBits, lane, NH);
     uint4* bn = reinterpret_cast<uint4*>(bm);
     uint4 n0 = bn[lane], n1 = bn[lane + 32];
     a0.x ^= n0.x; a0.y ^= n0.y; a0.z ^= n0.z; a0.w ^= n0.w;
@@ -205,12 +205,14 @@ __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_
 }
 
 // EXP (tuning experiments only, wrong results): 1 = no gather loads (hash + de-dup only), 2 = no hashing (synthetic candidates)
-template <int G, int WARPS, int MINB, bool FMA, int EXP = 0, int CPS = 8>
+// NH = counter hashes per label computed up front (34 = 136 candidates: the 128 picks plus 8 spare). NH = 32 leaves no spare, so
+// every label with a duplicate takes the in-kernel continuation of the PRG stream: a test shape for that rare path.
+template <int G, int WARPS, int MINB, bool FMA, int EXP = 0, int CPS = 8, int NH = kCandHashes>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, unsigned long long* __restrict__ work, uint32_t one) {
     extern __shared__ __align__(16) uint8_t sigma_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    SigmaWarpSmem<G>& S = reinterpret_cast<SigmaWarpSmem<G>*>(sigma_smem)[wid];
+    SigmaWarpSmem<G, NH>& S = reinterpret_cast<SigmaWarpSmem<G, NH>*>(sigma_smem)[wid];
     for (int i = lane; i < kNBits / 32; i += 32) S.bm[i] = 0;
     __syncwarp();
     const uint64_t ngroups = (J.n + G - 1) / G;
@@ -243,10 +245,10 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
         }
         __syncwarp();
         // ---- phase B: hash h = (edge, label, ctr), one compression: block 1 = tail of the salt, LE64(ctr), 0x80, bit length
-        const int nh = ng * 2 * kCandHashes;
+        const int nh = ng * 2 * NH;
         for (int h = lane; h < nh; h += 32) {
-            const int sl = h / kCandHashes;          // edge * 2 + label
-            const uint32_t ctr = (uint32_t)(h - sl * kCandHashes);
+            const int sl = h / NH;                   // edge * 2 + label
+            const uint32_t ctr = (uint32_t)(h - sl * NH);
             const int label = sl & 1;
             const int sh = label ? 48 : 56;          // 8 * (label length - 8)
             const uint64_t q8 = (S.salt[sl >> 1] >> (64 - sh)) | ((uint64_t)ctr << sh);
@@ -268,12 +270,12 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
             uint2 pk;
             pk.x = (uint32_t)cand_from_word(sha_le64_of(d[0], d[1]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[2], d[3]), N) << 16);
             pk.y = (uint32_t)cand_from_word(sha_le64_of(d[4], d[5]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[6], d[7]), N) << 16);
-            reinterpret_cast<uint2*>(S.cand + sl * kCandPerLabel)[ctr] = pk;
+            reinterpret_cast<uint2*>(S.cand + sl * (4 * NH))[ctr] = pk;
         }
         __syncwarp();
         // ---- phase C: de-duplicate, gather, flip, store
 #pragma unroll 1
-        for (int e = 0; e < ng; e++) sigma_edge<EXP, CPS>(S.bm, S.cols, S.more, S.cand + e * 2 * kCandPerLabel, J, canon, job0 + e, Hl, lane);
+        for (int e = 0; e < ng; e++) sigma_edge<EXP, CPS, NH>(S.bm, S.cols, S.more, S.cand + e * 2 * (4 * NH), J, canon, job0 + e, Hl, lane);
         __syncwarp();
     }
 }
@@ -299,10 +301,10 @@ int sigma_xor_rows(Ctx* ctx, uint64_t npairs, const uint2* d_pairs, uint64_t* ou
     return PV_OK;
 }
 
-template <int G, int WARPS, int MINB, bool FMA = false, int EXP = 0, int CPS = 8>
+template <int G, int WARPS, int MINB, bool FMA = false, int EXP = 0, int CPS = 8, int NH = kCandHashes>
 static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
-    auto kern = sigma_fused_kernel<G, WARPS, MINB, FMA, EXP, CPS>;
-    constexpr int smem = (int)sizeof(SigmaWarpSmem<G>) * WARPS;
+    auto kern = sigma_fused_kernel<G, WARPS, MINB, FMA, EXP, CPS, NH>;
+    constexpr int smem = (int)sizeof(SigmaWarpSmem<G, NH>) * WARPS;
     const void* kid = reinterpret_cast<const void*>(kern);
     bool attr_done = false;                        // function attributes are per device: remember them per context, not per process
     for (const void* k : ctx->configured_kernels) attr_done |= (k == kid);
@@ -337,7 +339,8 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
         const char* e = getenv("PVACB_SIGMA_CFG");
         cfg = e ? atoi(e) : 0;
     }
-    if (J.n < (uint64_t)ctx->sm_count * 7 * 4 * 6) rc = sigma_launch<2, 4, 8, true, 0, 4>(ctx, J);
+    if (cfg == 40) rc = sigma_launch<6, 4, 7, true, 0, 4, 32>(ctx, J);   // test shape: no spare candidates, the PRG continuation runs for ~3 of 4 edges
+    else if (J.n < (uint64_t)ctx->sm_count * 7 * 4 * 6) rc = sigma_launch<2, 4, 8, true, 0, 4>(ctx, J);
     else switch (cfg) {
         default: rc = sigma_launch<6, 4, 7, true, 0, 4>(ctx, J); break;   // 28 warps/SM, 182 KB of shared memory: L1 keeps 60 KB
         case 1: rc = sigma_launch<8, 4, 6, true, 0, 4>(ctx, J); break;    // 24 warps/SM, exact 17-round groups

@@ -152,6 +152,34 @@ __device__ __forceinline__ void sha_compress_from_rolled(const uint32_t* from, u
     out[0] = from[0] + a; out[1] = from[1] + b; out[2] = from[2] + c; out[3] = from[3] + d;
     out[4] = from[4] + e; out[5] = from[5] + f; out[6] = from[6] + g; out[7] = from[7] + h;
 }
+// Fully rolled: four trips of (16 rounds, then the schedule of the next 16 words unless this was the last trip) -- ONE copy of
+// the round code (~10 KB of SASS instead of ~14 KB), same dynamic instruction count.
+__device__ __forceinline__ void sha_compress_from_rolled4(const uint32_t* from, uint32_t w[16], uint32_t out[8], uint32_t one) {
+    uint32_t a = from[0], b = from[1], c = from[2], d = from[3], e = from[4], f = from[5], g = from[6], h = from[7];
+#pragma unroll 1
+    for (int it = 0; it < 64; it += 16) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+            uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+            uint32_t ch = (e & f) ^ (~e & g), maj = (a & b) ^ (a & c) ^ (b & c);
+            uint32_t t1 = sha_add_fma(sha_add_fma(h, S1, one), sha_add_fma(ch, c_shaK[it + j] + w[j], one), one);
+            uint32_t t2 = sha_add_fma(S0, maj, one);
+            h = g; g = f; f = e; e = sha_add_fma(d, t1, one); d = c; c = b; b = a; a = sha_add_fma(t1, t2, one);
+        }
+        if (it < 48) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                uint32_t w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];
+                uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+                uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+                w[j] = sha_add_fma(sha_add_fma(w[j], s0, one), sha_add_fma(w[(j + 9) & 15], s1, one), one);
+            }
+        }
+    }
+    out[0] = from[0] + a; out[1] = from[1] + b; out[2] = from[2] + c; out[3] = from[3] + d;
+    out[4] = from[4] + e; out[5] = from[5] + f; out[6] = from[6] + g; out[7] = from[7] + h;
+}
 #endif
 
 // LE64 of 8 big-endian digest bytes held as two state words (what load_le64(digest + 8k) returns)

@@ -207,9 +207,11 @@ __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_
 // EXP (tuning experiments only, wrong results): 1 = no gather loads (hash + de-dup only), 2 = no hashing (synthetic candidates)
 // NH = counter hashes per label computed up front (34 = 136 candidates: the 128 picks plus 8 spare). NH = 32 leaves no spare, so
 // every label with a duplicate takes the in-kernel continuation of the PRG stream: a test shape for that rare path.
-// ROLLED: SHA-256 rounds 16..63 as a 3-trip loop (sha_compress_from_rolled): the unrolled compressions of phases A and B are 45 KB of
-// code and the hashing warps stalled 13-19 % of the time on instruction fetch; rolled, the kernel is 3.8 % faster.
-template <int G, int WARPS, int MINB, bool FMA, int EXP = 0, int CPS = 8, int NH = kCandHashes, bool ROLLED = true>
+// ROLLED: 0 = fully unrolled SHA-256 compressions (45 KB of code in phases A and B: the hashing warps stalled 13-19 % of the time on
+// instruction fetch); 1 = rounds 0..15 unrolled, 16..63 as a 3-trip loop (3.8 % faster); 2 = four trips of (16 rounds, next
+// schedule): one copy of the round code, the hot code of the kernel is 26 KB, below the 32 KB L1.5 instruction cache (another
+// 2 %); 3 = form 2 for the midstates only.
+template <int G, int WARPS, int MINB, bool FMA, int EXP = 0, int CPS = 8, int NH = kCandHashes, int ROLLED = 2>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, unsigned long long* __restrict__ work, uint32_t one) {
     extern __shared__ __align__(16) uint8_t sigma_smem[];
@@ -240,7 +242,8 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
             sha_block_from_le64(q, w);
             if (ROLLED) {
                 uint32_t d[8];
-                sha_compress_from_rolled(kShaIv, w, d, one);
+                if (ROLLED >= 2) sha_compress_from_rolled4(kShaIv, w, d, one);
+                else sha_compress_from_rolled(kShaIv, w, d, one);
 #pragma unroll
                 for (int i = 0; i < 8; i++) S.mid[lane][i] = d[i];
             } else {
@@ -273,7 +276,8 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
             if (EXP == 2) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) d[i] = (uint32_t)(h * 8 + i) * 2654435761u + w[0];
-            } else if (ROLLED) sha_compress_from_rolled(S.mid[sl], w, d, one);
+            } else if (ROLLED == 2) sha_compress_from_rolled4(S.mid[sl], w, d, one);
+            else if (ROLLED) sha_compress_from_rolled(S.mid[sl], w, d, one);
             else if (FMA) sha_compress_from_fma(S.mid[sl], w, d, one);
             else sha_compress_from(S.mid[sl], w, d);
             const uint32_t N = label ? (uint32_t)kMBits : (uint32_t)kNBits;
@@ -311,7 +315,7 @@ int sigma_xor_rows(Ctx* ctx, uint64_t npairs, const uint2* d_pairs, uint64_t* ou
     return PV_OK;
 }
 
-template <int G, int WARPS, int MINB, bool FMA = false, int EXP = 0, int CPS = 8, int NH = kCandHashes, bool ROLLED = true>
+template <int G, int WARPS, int MINB, bool FMA = false, int EXP = 0, int CPS = 8, int NH = kCandHashes, int ROLLED = 2>
 static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
     auto kern = sigma_fused_kernel<G, WARPS, MINB, FMA, EXP, CPS, NH, ROLLED>;
     constexpr int smem = (int)sizeof(SigmaWarpSmem<G, NH>) * WARPS;
@@ -356,7 +360,9 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
         case 1: rc = sigma_launch<8, 4, 6, true, 0, 4>(ctx, J); break;    // 24 warps/SM, exact 17-round groups
         case 2: rc = sigma_launch<5, 4, 8, true, 0, 4>(ctx, J); break;    // 32 warps/SM
         case 3: rc = sigma_launch<8, 4, 7, true, 0, 4>(ctx, J); break;    // 28 warps/SM but 217 KB shared: the slow L1 split
-        case 4: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, false>(ctx, J); break;   // the default shape with fully unrolled compressions
+        case 4: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 0>(ctx, J); break;   // the default shape with fully unrolled compressions
+        case 5: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 1>(ctx, J); break;   // rounds 0..15 unrolled + 3-trip loop (two copies of the round code)
+        case 6: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 3>(ctx, J); break;   // 4-trip loop for the midstates only
         case 21: rc = sigma_launch<6, 4, 7, true, 1, 4>(ctx, J); break;   // experiment: no gather loads (wrong results)
         case 22: rc = sigma_launch<6, 4, 7, true, 2, 4>(ctx, J); break;   // experiment: no hashing (wrong results)
     }

@@ -34,7 +34,8 @@ GATHER_BYTES_PER_EDGE = 128 * 1024
 SHA_PER_EDGE = 70               # 2 midstates + 2 x 34 counter hashes (csrc/sigma.cu)
 AES_LDS_PER_BLOCK = 197         # T-table lookups per AES-256 block after hoisting rounds 1-2 (csrc/aes256.cuh)
 ALU_LANE_OPS_PER_S = 18.55e12    # measured LOP3/SHF/PRMT rate of this GPU (profiles/micro/int_pipes.cu): 63.8 lanes/clk/SM
-SHA_ALU_INSTR = 1248            # SHF + LOP3 + IADD3 of one unrolled compression
+SHA_ALU_INSTR = 1024            # ALU-pipe instructions (SHF + LOP3) of one compression in the rolled form (cuobjdump); the adds run as IMAD on the FMA pipe
+ALU_WARP_INSTR_PER_EDGE = 3395  # fallback for profiles/r01_ncu_summary.json: ALU-pipe warp instructions per edge of sigma_fused_kernel (ncu)
 
 
 def mix64(z):
@@ -274,8 +275,16 @@ def main():
     gather_bytes = edges_per_step * args.steps * GATHER_BYTES_PER_EDGE
     achieved = gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
     sha_rate = edges_per_step * args.steps * SHA_PER_EDGE / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
-    # second ceiling of the same kernel: the SHA-256 counter PRG on the ALU pipe (SHF/LOP3/IADD3: 64 lanes/clk/SM)
-    alu_peak = ALU_LANE_OPS_PER_S / 1e9 / SHA_ALU_INSTR
+    # second ceiling of the same kernel: the ALU pipe (SHF / LOP3 / IADD3, 64 lanes/clk/SM). Per edge it executes the SHA-256 counter
+    # PRG (70 compressions, 2/3 of the ALU work), the 512 three-input XORs of the gather and the de-duplication; the count per edge
+    # comes from the committed ncu capture.
+    alu_per_edge = ALU_WARP_INSTR_PER_EDGE
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
+            alu_per_edge = json.load(f).get("sigma_fused_kernel", {}).get("alu_pipe_warp_instructions_per_edge", alu_per_edge)
+    except OSError:
+        pass
+    alu_rate = edges_per_step * args.steps * alu_per_edge * 32 / (gather_ms * 1e-3) / 1e12 if gather_ms > 0 else 0.0
     roofline = {
         "kernel": "sigma_fused_kernel", "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
         "traffic": None,
@@ -283,9 +292,11 @@ def main():
         "algorithmic_bytes_per_launch": gather_bytes / max(gather_launches, 1), "launches": gather_launches,
         "kernel_ms_per_step": gather_ms / args.steps, "share_of_step": gather_ms * 1e-3 / secs,
         "hbm_write_gbs": edges_per_step * args.steps * 1024 / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0, "hbm_peak": hbm_peak, "hbm_peak_source": peak_src,
-        "alu": {"achieved": sha_rate, "unit": "G SHA-256 compressions/s", "peak": alu_peak, "frac": sha_rate / alu_peak,
-                "peak_source": f"{SHA_ALU_INSTR} ALU-pipe instructions per compression (cuobjdump) at the measured ALU-pipe rate of 18.55 T lane-ops/s (profiles/r01_int_pipes.txt; sha_variants.cu reaches 15.2 G/s standalone)",
-                "compressions_per_edge": SHA_PER_EDGE},
+        "alu": {"achieved": alu_rate, "unit": "T lane-ops/s (ALU pipe)", "peak": ALU_LANE_OPS_PER_S / 1e12, "frac": alu_rate / (ALU_LANE_OPS_PER_S / 1e12),
+                "peak_source": "measured LOP3/SHF issue rate of this GPU, 63.8 lanes/clk/SM (profiles/r01_int_pipes.txt)",
+                "alu_warp_instructions_per_edge": alu_per_edge, "sha256_compressions_per_s_G": sha_rate, "compressions_per_edge": SHA_PER_EDGE,
+                "sha_alu_instructions_per_compression": SHA_ALU_INSTR,
+                "sha_share_of_alu_work": SHA_PER_EDGE * SHA_ALU_INSTR / 32.0 / alu_per_edge},
     }
     ncu_path = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
     if os.path.exists(ncu_path):

@@ -20,5 +20,5 @@ assert all((int(d[i][0]) | (int(d[i][1]) << 64)) == int(va[i]) * int(vb[i]) % ((
 SA, SB = eng.synthetic(1 << 14, 20, 5), eng.synthetic(1 << 14, 20, 6)
 for k in range(2):
     eng.ct_add(SA, SB).free()           # concat_kernel, 2.7 GB per launch
-print("prof_run ok", eng.stats())
+print("prof_run ok", eng.stats(), "edges of the last product batch:", P.totals()[1])
 eng.close()

@@ -55,7 +55,7 @@ __device__ __noinline__ void prg_hash_words(const LabelStream ls, const uint64_t
 template <int G, int NH = kCandHashes>
 struct __align__(16) SigmaWarpSmem {
     uint32_t bm[kNBits / 32];               // 2 KiB: de-dup bitmap of the columns, then of the noise bits (= the flip mask)
-    uint32_t cols[kXColWt];                 // chosen columns in draw order, as offsets into H in 16-byte units (col * 64)
+    uint32_t cols[kXColWt];                 // chosen columns in draw order, as byte offsets into H (col * 1024)
     uint16_t cand[G * 2 * NH * 4];          // phase B output: [edge][label][4 NH]  (NH = 34: 136 candidates)
     union {
         uint32_t mid[G * 2][8];             // phase A output: SHA-256 state after block 0, per (edge, label)
@@ -84,7 +84,7 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint1
     for (int k = 0; k < 4; k++) {
         const bool win = !(old[k] & bit[k]);
         uint32_t b = __ballot_sync(0xffffffffu, win);
-        if (win && cols) cols[have + __popc(b & ((1u << lane) - 1))] = (uint32_t)c[k] * 64u;
+        if (win && cols) cols[have + __popc(b & ((1u << lane) - 1))] = (uint32_t)c[k] * 1024u;
         have += __popc(b);
     }
     if (have < kXColWt) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint1
                     uint32_t old = bm[v >> 5];
                     if (!(old & bit)) {
                         bm[v >> 5] = old | bit;
-                        if (cols) cols[have] = (uint32_t)v * 64u;
+                        if (cols) cols[have] = (uint32_t)v * 1024u;
                         have++;
                     }
                 }
@@ -126,11 +126,19 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint1
     __syncwarp();
 }
 
+// address of this lane's 16 bytes of a column: Hl + byte offset as ONE mad.wide on the FMA pipe (`one` is a run-time 1). Written as
+// pointer arithmetic it costs IADD3 + LEA + LEA.HI.X on the ALU pipe per column, and the ALU pipe is what bounds the kernel.
+__device__ __forceinline__ const uint4* col_ptr(const uint4* Hl, uint32_t byte_off, uint32_t one) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(byte_off), "r"(one), "l"(reinterpret_cast<uint64_t>(Hl)));
+    return reinterpret_cast<const uint4*>(r);
+}
+
 // phase C for one edge: ordered de-duplication of both labels, XOR-gather of the 128 chosen columns, noise flips, store.
 // gc = the edge's candidates [2][136] in shared memory; bm / cols / more = the warp's scratch.
 template <int EXP, int CPS, int NH>
 __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_t* more, const uint16_t* gc, const SigmaJobs& J, uint64_t canon, uint64_t job,
-                                           const uint4* Hl, int lane) {
+                                           const uint4* Hl, int lane, uint32_t one) {
     dedupe_label(bm, cols, more, gc, label_xseed(), J, canon, job, (uint32_t)kNBits, lane, NH);
     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
     // 8 column offsets per step, broadcast reads. The NEXT step's offsets are fetched right after this step's loads
@@ -145,14 +153,14 @@ __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_
             uint4 v[16];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const uint4* p = Hl + co[k];
+                const uint4* p = col_ptr(Hl, co[k], one);
                 if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
                 v[2 * k] = __ldcg(p);
                 v[2 * k + 1] = __ldcg(p + 32);
             }
             if (i == 0) {
                 // clear the bitmap again (every word that got a bit belongs to one of the chosen columns) -- under the first loads
-                for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 11] = 0;
+                for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 15] = 0;
             }
             if (i + 8 < kXColWt) {
                 c0 = *reinterpret_cast<const uint4*>(&cols[i + 8]);
@@ -172,13 +180,13 @@ __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_
             uint4 v[8];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint4* p = Hl + co[k];
+                const uint4* p = col_ptr(Hl, co[k], one);
                 if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
                 v[2 * k] = __ldcg(p);
                 v[2 * k + 1] = __ldcg(p + 32);
             }
             if (i == 0) {
-                for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 11] = 0;
+                for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 15] = 0;
             }
             if (i + 4 < kXColWt) c0 = *reinterpret_cast<const uint4*>(&cols[i + 4]);
 #pragma unroll
@@ -289,7 +297,7 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
         __syncwarp();
         // ---- phase C: de-duplicate, gather, flip, store
 #pragma unroll 1
-        for (int e = 0; e < ng; e++) sigma_edge<EXP, CPS, NH>(S.bm, S.cols, S.more, S.cand + e * 2 * (4 * NH), J, canon, job0 + e, Hl, lane);
+        for (int e = 0; e < ng; e++) sigma_edge<EXP, CPS, NH>(S.bm, S.cols, S.more, S.cand + e * 2 * (4 * NH), J, canon, job0 + e, Hl, lane, one);
         __syncwarp();
     }
 }
@@ -362,7 +370,8 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
         case 3: rc = sigma_launch<8, 4, 7, true, 0, 4>(ctx, J); break;    // 28 warps/SM but 217 KB shared: the slow L1 split
         case 4: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 0>(ctx, J); break;   // the default shape with fully unrolled compressions
         case 5: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 1>(ctx, J); break;   // rounds 0..15 unrolled + 3-trip loop (two copies of the round code)
-        case 6: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 3>(ctx, J); break;   // 4-trip loop for the midstates only
+        case 8: rc = sigma_launch<8, 4, 5, true, 0, 8>(ctx, J); break;    // 20 warps/SM, 16 loads in flight per lane
+        case 9: rc = sigma_launch<8, 4, 6, true, 0, 8>(ctx, J); break;    // 24 warps/SM, 16 loads in flight per lane
         case 21: rc = sigma_launch<6, 4, 7, true, 1, 4>(ctx, J); break;   // experiment: no gather loads (wrong results)
         case 22: rc = sigma_launch<6, 4, 7, true, 2, 4>(ctx, J); break;   // experiment: no hashing (wrong results)
     }

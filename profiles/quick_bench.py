@@ -47,6 +47,8 @@ if "sigma" in what:
     ms = pr['sigma'][0]
     print(f"sigma cfg={os.environ.get('PVACB_SIGMA_CFG', '0')} n={n}: fused {ms:.2f} ms ({ms*1e6/n:.2f} ns/edge, {n*131072/ms/1e9:.2f} TB/s L2 gather, "
           f"{n*68/ms/1e6:.2f} G SHA-256 compressions/s), wall {wall*1e3:.0f} ms", flush=True)
+    import hashlib
+    print("sigma rows digest", hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest()[:16], flush=True)
     print("l2 probe GB/s", eng.l2_gather_probe(3), flush=True)
 
 if "add" in what:

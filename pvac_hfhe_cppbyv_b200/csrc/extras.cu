@@ -60,7 +60,8 @@ __global__ void synth_sigma_kernel(uint64_t nwords, uint64_t seed, uint64_t* sig
 // L2 gather probe: the access pattern of sigma_gather_kernel (a warp XOR-reads pseudo-random 1 KiB columns of the 16 MiB
 // matrix H with 128-bit loads) with nothing else around it. U = columns in flight per warp. The best bandwidth over a
 // few (U, CTAs/SM) shapes is used as the practical ceiling of the sigma kernel.
-// LD: 0 ld.global.cg (what the sigma kernel uses), 1 plain ld.global, 2 ld.global.nc, 3 ld.global.cs  (PVACB_PROBE_LD)
+// LD: 0 ld.global.cg (what the sigma kernel uses), 1 plain ld.global, 2 ld.global.nc, 3 ld.global.cs, 4 one 256-bit ld.global.cg per
+// lane and column instead of two 128-bit ones  (PVACB_PROBE_LD; 5 = the 256-bit form with 4 columns in flight)
 template <int LD>
 __device__ __forceinline__ uint4 probe_load(const uint4* p) {
     if (LD == 1) return *p;
@@ -80,6 +81,14 @@ __global__ void __launch_bounds__(256) l2_gather_probe_kernel(const uint4* __res
         for (int k = 0; k < U; k++) {
             state = state * 1664525u + 1013904223u;
             uint32_t col = (state >> 10) & (kNBits - 1);
+            if (LD == 4) {
+                const uint4* p = H4 + (size_t)col * 64 + 2 * lane;
+                asm volatile("ld.global.cg.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(v[2 * k].x), "=r"(v[2 * k].y), "=r"(v[2 * k].z), "=r"(v[2 * k].w), "=r"(v[2 * k + 1].x), "=r"(v[2 * k + 1].y),
+                               "=r"(v[2 * k + 1].z), "=r"(v[2 * k + 1].w)
+                             : "l"(p));
+                continue;
+            }
             const uint4* p = H4 + (size_t)col * 64 + lane;
             v[2 * k] = probe_load<LD>(p);
             v[2 * k + 1] = probe_load<LD>(p + 32);
@@ -281,6 +290,8 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
             if (ld == 1) l2_gather_probe_kernel<8, 1><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (ld == 2) l2_gather_probe_kernel<8, 2><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (ld == 3) l2_gather_probe_kernel<8, 3><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (ld == 4) l2_gather_probe_kernel<8, 4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (ld == 5) l2_gather_probe_kernel<4, 4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (shape / 2 == 0) l2_gather_probe_kernel<4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (shape / 2 == 1) l2_gather_probe_kernel<8><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else l2_gather_probe_kernel<16><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);

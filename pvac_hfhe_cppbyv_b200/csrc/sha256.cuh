@@ -180,51 +180,6 @@ __device__ __forceinline__ void sha_compress_from_rolled4(const uint32_t* from, 
     out[0] = from[0] + a; out[1] = from[1] + b; out[2] = from[2] + c; out[3] = from[3] + d;
     out[4] = from[4] + e; out[5] = from[5] + f; out[6] = from[6] + g; out[7] = from[7] + h;
 }
-// N independent compressions interleaved in one instruction stream (rolled like sha_compress_from_rolled4): a single warp then
-// has N dependency chains in flight, which is what lets a few hasher warps keep the ALU pipe busy (sigma_ws2_kernel).
-template <int N>
-__device__ __forceinline__ void sha_compressN_from_rolled4(const uint32_t* const from[N], uint32_t w[N][16], uint32_t out[N][8], uint32_t one) {
-    uint32_t a[N], b[N], c[N], d[N], e[N], f[N], g[N], h[N];
-#pragma unroll
-    for (int n = 0; n < N; n++) {
-        a[n] = from[n][0]; b[n] = from[n][1]; c[n] = from[n][2]; d[n] = from[n][3];
-        e[n] = from[n][4]; f[n] = from[n][5]; g[n] = from[n][6]; h[n] = from[n][7];
-    }
-#pragma unroll 1
-    for (int it = 0; it < 64; it += 16) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const uint32_t k = c_shaK[it + j];
-#pragma unroll
-            for (int n = 0; n < N; n++) {
-                uint32_t S1 = sha_rotr(e[n], 6) ^ sha_rotr(e[n], 11) ^ sha_rotr(e[n], 25);
-                uint32_t S0 = sha_rotr(a[n], 2) ^ sha_rotr(a[n], 13) ^ sha_rotr(a[n], 22);
-                uint32_t ch = (e[n] & f[n]) ^ (~e[n] & g[n]), maj = (a[n] & b[n]) ^ (a[n] & c[n]) ^ (b[n] & c[n]);
-                uint32_t t1 = sha_add_fma(sha_add_fma(h[n], S1, one), sha_add_fma(ch, k + w[n][j], one), one);
-                uint32_t t2 = sha_add_fma(S0, maj, one);
-                h[n] = g[n]; g[n] = f[n]; f[n] = e[n]; e[n] = sha_add_fma(d[n], t1, one); d[n] = c[n]; c[n] = b[n]; b[n] = a[n];
-                a[n] = sha_add_fma(t1, t2, one);
-            }
-        }
-        if (it < 48) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-#pragma unroll
-                for (int n = 0; n < N; n++) {
-                    uint32_t w15 = w[n][(j + 1) & 15], w2 = w[n][(j + 14) & 15];
-                    uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
-                    uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
-                    w[n][j] = sha_add_fma(sha_add_fma(w[n][j], s0, one), sha_add_fma(w[n][(j + 9) & 15], s1, one), one);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int n = 0; n < N; n++) {
-        out[n][0] = from[n][0] + a[n]; out[n][1] = from[n][1] + b[n]; out[n][2] = from[n][2] + c[n]; out[n][3] = from[n][3] + d[n];
-        out[n][4] = from[n][4] + e[n]; out[n][5] = from[n][5] + f[n]; out[n][6] = from[n][6] + g[n]; out[n][7] = from[n][7] + h[n];
-    }
-}
 #endif
 
 // LE64 of 8 big-endian digest bytes held as two state words (what load_le64(digest + 8k) returns)

@@ -302,365 +302,6 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------------
-// Warp-specialised form of the same work. The L2 gather rate of an SM depends on HOW MANY WARPS are gathering, not on how many
-// loads each has in flight (pvacb_l2_gather_probe: 8 / 16 / 24 / 32 gathering warps -> 11.5 / 17.8 / 19.3 / 19.9 TB/s, the same for
-// 4, 8 or 16 columns in flight per warp). In the fused kernel about 17 of the 28 resident warps gather at any time. Here HW hasher
-// warps per CTA do phases A, B and the de-duplication and hand finished (columns, flip mask, row) items through a ring in shared
-// memory to GW gatherer warps that do nothing but gather, so ~24 warps per SM gather all the time. Ring slots are guarded by two
-// mbarriers each (full / empty), slot numbers are claimed in order from two shared counters.
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    const uint32_t a = smem_addr_u32(bar);
-    uint32_t ok = 0;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok)
-                     : "r"(a), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
-
-template <int G, int HW, int R, int NH = kCandHashes>
-struct __align__(16) SigmaWsSmem {
-    struct Hasher {
-        uint32_t bm[kNBits / 32];           // de-dup bitmap of the columns (cleared again through the column list)
-        uint16_t cand[G * 2 * NH * 4];
-        union {
-            uint32_t mid[G * 2][8];
-            uint16_t more[128];
-        };
-        uint64_t salt[G < 4 ? 4 : G];
-    } h[HW];
-    struct Slot {
-        uint32_t cols[kXColWt];             // byte offsets of the chosen columns
-        uint32_t mask[kMBits / 32];         // noise flip mask (the de-dup bitmap of the noise label); the gatherer zeroes it again
-        unsigned long long job;             // edge number, ~0 = no more work
-        unsigned long long pad;
-    } slot[R];
-    unsigned long long full[R], empty[R];
-    uint32_t iv[8];
-    unsigned int head, tail, done, pad;
-};
-
-template <int G, int HW, int GW, int MINB, int R, int EXP = 0, int NH = kCandHashes>
-__global__ void __launch_bounds__((HW + GW) * 32, MINB)
-sigma_ws_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, unsigned long long* __restrict__ work, uint32_t one, uint32_t sm_count) {
-    extern __shared__ __align__(16) unsigned char sigma_smem[];
-    auto& S = *reinterpret_cast<SigmaWsSmem<G, HW, R, NH>*>(sigma_smem);
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < R * (kMBits / 32); i += blockDim.x) S.slot[i / (kMBits / 32)].mask[i % (kMBits / 32)] = 0;
-    for (int i = threadIdx.x; i < HW * (kNBits / 32); i += blockDim.x) S.h[i / (kNBits / 32)].bm[i % (kNBits / 32)] = 0;
-    if (threadIdx.x < 8) S.iv[threadIdx.x] = kShaIv[threadIdx.x];
-    if (threadIdx.x == 0) {
-        for (int r = 0; r < R; r++) { mbar_init(&S.full[r], 1); mbar_init(&S.empty[r], 1); }
-        S.head = S.tail = S.done = 0;
-    }
-    __syncthreads();
-    // hashers sit on different sub-partitions in the CTAs that share an SM (warp w runs on sub-partition w % 4)
-    const int first_hasher = ((blockIdx.x / sm_count) * HW) % (HW + GW);
-    const int hid = (warp - first_hasher + (HW + GW)) % (HW + GW);
-    if (hid < HW) {
-        // ---------------- hasher: phases A and B per group of G edges, then one ring item per edge
-        auto& Hs = S.h[hid];
-        const uint64_t ngroups = (J.n + G - 1) / G;
-        for (;;) {
-            unsigned long long grp = 0;
-            if (lane == 0) grp = atomicAdd(work, 1ull);
-            grp = __shfl_sync(0xffffffffu, grp, 0);
-            if (grp >= ngroups) break;
-            const uint64_t job0 = grp * G;
-            const int ng = (int)(J.n - job0 < (uint64_t)G ? J.n - job0 : (uint64_t)G);
-            if (lane < 2 * ng) {
-                const LabelStream ls = (lane & 1) ? label_noise() : label_xseed();
-                uint64_t x[8];
-                load_words(J, canon, job0 + (lane >> 1), x);
-                uint64_t q[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) q[j] = stream_word(ls, x, 8, j, 0x80ull);
-                uint32_t w[16], d[8];
-                sha_block_from_le64(q, w);
-                sha_compress_from_rolled4(S.iv, w, d, one);
-#pragma unroll
-                for (int i = 0; i < 8; i++) Hs.mid[lane][i] = d[i];
-                if (!(lane & 1)) Hs.salt[lane >> 1] = x[6];
-            }
-            __syncwarp();
-            const int nh = ng * 2 * NH;
-            for (int h = lane; h < nh; h += 32) {
-                const int sl = h / NH;
-                const uint32_t ctr = (uint32_t)(h - sl * NH);
-                const int label = sl & 1;
-                const int sh = label ? 48 : 56;
-                const uint64_t q8 = (Hs.salt[sl >> 1] >> (64 - sh)) | ((uint64_t)ctr << sh);
-                uint32_t w[16], d[8];
-                w[0] = sha_bswap((uint32_t)q8);
-                w[1] = sha_bswap((uint32_t)(q8 >> 32));
-                w[2] = 0;
-                w[3] = label ? 0x00008000u : 0x00000080u;
-#pragma unroll
-                for (int i = 4; i < 15; i++) w[i] = 0;
-                w[15] = label ? 78u * 8u : 79u * 8u;
-                if (EXP == 2) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) d[i] = (uint32_t)(h * 8 + i) * 2654435761u + w[0];
-                } else sha_compress_from_rolled4(Hs.mid[sl], w, d, one);
-                const uint32_t N = label ? (uint32_t)kMBits : (uint32_t)kNBits;
-                uint2 pk;
-                pk.x = (uint32_t)cand_from_word(sha_le64_of(d[0], d[1]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[2], d[3]), N) << 16);
-                pk.y = (uint32_t)cand_from_word(sha_le64_of(d[4], d[5]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[6], d[7]), N) << 16);
-                reinterpret_cast<uint2*>(Hs.cand + sl * (4 * NH))[ctr] = pk;
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int e = 0; e < ng; e++) {
-                unsigned int p = 0;
-                if (lane == 0) p = atomicAdd(&S.tail, 1u);
-                p = __shfl_sync(0xffffffffu, p, 0);
-                const unsigned int sl = p % R, round = p / R;
-                mbar_wait(&S.empty[sl], (round & 1) ^ 1);
-                auto& T = S.slot[sl];
-                const uint16_t* gc = Hs.cand + e * 2 * (4 * NH);
-                dedupe_label(Hs.bm, T.cols, Hs.more, gc, label_xseed(), J, canon, job0 + e, (uint32_t)kNBits, lane, NH);
-                for (int q = lane; q < kXColWt; q += 32) Hs.bm[T.cols[q] >> 15] = 0;
-                dedupe_label(T.mask, nullptr, Hs.more, gc + 4 * NH, label_noise(), J, canon, job0 + e, (uint32_t)kMBits, lane, NH);
-                if (lane == 0) T.job = job0 + e;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.full[sl]);
-            }
-        }
-        unsigned int d = 0;
-        if (lane == 0) d = atomicAdd(&S.done, 1u);
-        d = __shfl_sync(0xffffffffu, d, 0);
-        if (d == HW - 1) {
-            // the last hasher of the CTA to run out of work retires the gatherers
-            for (int k = 0; k < GW; k++) {
-                unsigned int p = 0;
-                if (lane == 0) p = atomicAdd(&S.tail, 1u);
-                p = __shfl_sync(0xffffffffu, p, 0);
-                const unsigned int sl = p % R, round = p / R;
-                mbar_wait(&S.empty[sl], (round & 1) ^ 1);
-                if (lane == 0) { S.slot[sl].job = ~0ull; mbar_arrive(&S.full[sl]); }
-                __syncwarp();
-            }
-        }
-    } else {
-        // ---------------- gatherer
-        const uint4* const Hl = H4 + lane;
-        for (;;) {
-            unsigned int c = 0;
-            if (lane == 0) c = atomicAdd(&S.head, 1u);
-            c = __shfl_sync(0xffffffffu, c, 0);
-            const unsigned int sl = c % R, round = c / R;
-            mbar_wait(&S.full[sl], round & 1);
-            auto& T = S.slot[sl];
-            const unsigned long long job = T.job;
-            if (job == ~0ull) break;
-            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
-            uint4 c0 = *reinterpret_cast<const uint4*>(&T.cols[0]);
-#pragma unroll 1
-            for (int i = 0; i < kXColWt; i += 4) {
-                const uint32_t co[4] = {c0.x, c0.y, c0.z, c0.w};
-                uint4 v[8];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint4* p = col_ptr(Hl, co[k], one);
-                    if (EXP == 1) { v[2 * k] = make_uint4(co[k], i, k, lane); v[2 * k + 1] = make_uint4(k, co[k], lane, i); continue; }
-                    v[2 * k] = __ldcg(p);
-                    v[2 * k + 1] = __ldcg(p + 32);
-                }
-                if (i + 4 < kXColWt) c0 = *reinterpret_cast<const uint4*>(&T.cols[i + 4]);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
-                    a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
-                }
-            }
-            uint4* bn = reinterpret_cast<uint4*>(T.mask);
-            const uint4 n0 = bn[lane], n1 = bn[lane + 32];
-            bn[lane] = make_uint4(0, 0, 0, 0);
-            bn[lane + 32] = make_uint4(0, 0, 0, 0);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty[sl]);
-            a0.x ^= n0.x; a0.y ^= n0.y; a0.z ^= n0.z; a0.w ^= n0.w;
-            a1.x ^= n1.x; a1.y ^= n1.y; a1.z ^= n1.z; a1.w ^= n1.w;
-            const uint64_t row = J.out_row ? J.out_row[job] : job;
-            uint4* o = reinterpret_cast<uint4*>(row < J.out_split ? J.out + row * kMWords : J.out2 + (row - J.out_split) * kMWords);
-            __stcs(o + lane, a0);
-            __stcs(o + lane + 32, a1);
-        }
-    }
-}
-
-// Second form: ONE 1024-thread CTA per SM, the first HWG warpgroups hash with ILP independent compressions per lane and a larger
-// register budget (setmaxnreg), all other warps gather with a smaller one.
-template <int REGS>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
-template <int REGS>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
-
-template <int G, int HWG, int R, int ILP, int RH, int RG, int NH = kCandHashes>
-__global__ void __launch_bounds__(1024, 1)
-sigma_ws2_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, unsigned long long* __restrict__ work, uint32_t one) {
-    constexpr int HW = 4 * HWG, GW = 32 - HW;
-    extern __shared__ __align__(16) unsigned char sigma_smem[];
-    auto& S = *reinterpret_cast<SigmaWsSmem<G, HW, R, NH>*>(sigma_smem);
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < R * (kMBits / 32); i += blockDim.x) S.slot[i / (kMBits / 32)].mask[i % (kMBits / 32)] = 0;
-    for (int i = threadIdx.x; i < HW * (kNBits / 32); i += blockDim.x) S.h[i / (kNBits / 32)].bm[i % (kNBits / 32)] = 0;
-    if (threadIdx.x < 8) S.iv[threadIdx.x] = kShaIv[threadIdx.x];
-    if (threadIdx.x == 0) {
-        for (int r = 0; r < R; r++) { mbar_init(&S.full[r], 1); mbar_init(&S.empty[r], 1); }
-        S.head = S.tail = S.done = 0;
-    }
-    __syncthreads();
-    if (warp < HW) {
-        reg_inc<RH>();
-        auto& Hs = S.h[warp];
-        const uint64_t ngroups = (J.n + G - 1) / G;
-        for (;;) {
-            unsigned long long grp = 0;
-            if (lane == 0) grp = atomicAdd(work, 1ull);
-            grp = __shfl_sync(0xffffffffu, grp, 0);
-            if (grp >= ngroups) break;
-            const uint64_t job0 = grp * G;
-            const int ng = (int)(J.n - job0 < (uint64_t)G ? J.n - job0 : (uint64_t)G);
-            if (lane < 2 * ng) {
-                const LabelStream ls = (lane & 1) ? label_noise() : label_xseed();
-                uint64_t x[8];
-                load_words(J, canon, job0 + (lane >> 1), x);
-                uint64_t q[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) q[j] = stream_word(ls, x, 8, j, 0x80ull);
-                uint32_t w[16], d[8];
-                sha_block_from_le64(q, w);
-                sha_compress_from_rolled4(S.iv, w, d, one);
-#pragma unroll
-                for (int i = 0; i < 8; i++) Hs.mid[lane][i] = d[i];
-                if (!(lane & 1)) Hs.salt[lane >> 1] = x[6];
-            }
-            __syncwarp();
-            const int nh = ng * 2 * NH;
-#pragma unroll 1
-            for (int h0 = lane; h0 < nh; h0 += 32 * ILP) {
-                uint32_t w[ILP][16], d[ILP][8];
-                const uint32_t* from[ILP];
-                int sl[ILP];
-                uint32_t ctr[ILP];
-#pragma unroll
-                for (int n = 0; n < ILP; n++) {
-                    const int h = (h0 + 32 * n < nh) ? h0 + 32 * n : h0;        // past the end: repeat the lane's first hash
-                    sl[n] = h / NH;
-                    ctr[n] = (uint32_t)(h - sl[n] * NH);
-                    const int label = sl[n] & 1;
-                    const int sh = label ? 48 : 56;
-                    const uint64_t q8 = (Hs.salt[sl[n] >> 1] >> (64 - sh)) | ((uint64_t)ctr[n] << sh);
-                    w[n][0] = sha_bswap((uint32_t)q8);
-                    w[n][1] = sha_bswap((uint32_t)(q8 >> 32));
-                    w[n][2] = 0;
-                    w[n][3] = label ? 0x00008000u : 0x00000080u;
-#pragma unroll
-                    for (int i = 4; i < 15; i++) w[n][i] = 0;
-                    w[n][15] = label ? 78u * 8u : 79u * 8u;
-                    from[n] = Hs.mid[sl[n]];
-                }
-                sha_compressN_from_rolled4<ILP>(from, w, d, one);
-#pragma unroll
-                for (int n = 0; n < ILP; n++) {
-                    const uint32_t N = (sl[n] & 1) ? (uint32_t)kMBits : (uint32_t)kNBits;
-                    uint2 pk;
-                    pk.x = (uint32_t)cand_from_word(sha_le64_of(d[n][0], d[n][1]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[n][2], d[n][3]), N) << 16);
-                    pk.y = (uint32_t)cand_from_word(sha_le64_of(d[n][4], d[n][5]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[n][6], d[n][7]), N) << 16);
-                    reinterpret_cast<uint2*>(Hs.cand + sl[n] * (4 * NH))[ctr[n]] = pk;    // a repeated hash rewrites the same value
-                }
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int e = 0; e < ng; e++) {
-                unsigned int p = 0;
-                if (lane == 0) p = atomicAdd(&S.tail, 1u);
-                p = __shfl_sync(0xffffffffu, p, 0);
-                const unsigned int sl = p % R, round = p / R;
-                mbar_wait(&S.empty[sl], (round & 1) ^ 1);
-                auto& T = S.slot[sl];
-                const uint16_t* gc = Hs.cand + e * 2 * (4 * NH);
-                dedupe_label(Hs.bm, T.cols, Hs.more, gc, label_xseed(), J, canon, job0 + e, (uint32_t)kNBits, lane, NH);
-                for (int q = lane; q < kXColWt; q += 32) Hs.bm[T.cols[q] >> 15] = 0;
-                dedupe_label(T.mask, nullptr, Hs.more, gc + 4 * NH, label_noise(), J, canon, job0 + e, (uint32_t)kMBits, lane, NH);
-                if (lane == 0) T.job = job0 + e;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.full[sl]);
-            }
-        }
-        unsigned int d = 0;
-        if (lane == 0) d = atomicAdd(&S.done, 1u);
-        d = __shfl_sync(0xffffffffu, d, 0);
-        if (d == HW - 1) {
-            for (int k = 0; k < GW; k++) {
-                unsigned int p = 0;
-                if (lane == 0) p = atomicAdd(&S.tail, 1u);
-                p = __shfl_sync(0xffffffffu, p, 0);
-                const unsigned int sl = p % R, round = p / R;
-                mbar_wait(&S.empty[sl], (round & 1) ^ 1);
-                if (lane == 0) { S.slot[sl].job = ~0ull; mbar_arrive(&S.full[sl]); }
-                __syncwarp();
-            }
-        }
-    } else {
-        reg_dec<RG>();
-        const uint4* const Hl = H4 + lane;
-        for (;;) {
-            unsigned int c = 0;
-            if (lane == 0) c = atomicAdd(&S.head, 1u);
-            c = __shfl_sync(0xffffffffu, c, 0);
-            const unsigned int sl = c % R, round = c / R;
-            mbar_wait(&S.full[sl], round & 1);
-            auto& T = S.slot[sl];
-            const unsigned long long job = T.job;
-            if (job == ~0ull) break;
-            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
-            uint4 c0 = *reinterpret_cast<const uint4*>(&T.cols[0]);
-#pragma unroll 1
-            for (int i = 0; i < kXColWt; i += 4) {
-                const uint32_t co[4] = {c0.x, c0.y, c0.z, c0.w};
-                uint4 v[8];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint4* p = col_ptr(Hl, co[k], one);
-                    v[2 * k] = __ldcg(p);
-                    v[2 * k + 1] = __ldcg(p + 32);
-                }
-                if (i + 4 < kXColWt) c0 = *reinterpret_cast<const uint4*>(&T.cols[i + 4]);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;
-                    a1.x ^= v[2 * k + 1].x; a1.y ^= v[2 * k + 1].y; a1.z ^= v[2 * k + 1].z; a1.w ^= v[2 * k + 1].w;
-                }
-            }
-            uint4* bn = reinterpret_cast<uint4*>(T.mask);
-            const uint4 n0 = bn[lane], n1 = bn[lane + 32];
-            bn[lane] = make_uint4(0, 0, 0, 0);
-            bn[lane + 32] = make_uint4(0, 0, 0, 0);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty[sl]);
-            a0.x ^= n0.x; a0.y ^= n0.y; a0.z ^= n0.z; a0.w ^= n0.w;
-            a1.x ^= n1.x; a1.y ^= n1.y; a1.z ^= n1.z; a1.w ^= n1.w;
-            const uint64_t row = J.out_row ? J.out_row[job] : job;
-            uint4* o = reinterpret_cast<uint4*>(row < J.out_split ? J.out + row * kMWords : J.out2 + (row - J.out_split) * kMWords);
-            __stcs(o + lane, a0);
-            __stcs(o + lane + 32, a1);
-        }
-    }
-}
-
 // out[dst] ^= scratch row, for merged edges of enc_value (compact_edges XORs the sigmas, ops/encrypt.hpp:39-71).
 // Several pairs may share a destination, hence atomics.
 __global__ void sigma_xor_rows_kernel(uint64_t npairs, const uint2* __restrict__ pairs, uint64_t* __restrict__ out, uint64_t split,
@@ -708,48 +349,6 @@ static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
     return PV_OK;
 }
 
-template <int G, int HW, int GW, int MINB, int R, int EXP = 0>
-static int sigma_ws_launch(Ctx* ctx, const SigmaJobs& J) {
-    auto kern = sigma_ws_kernel<G, HW, GW, MINB, R, EXP>;
-    constexpr int smem = (int)sizeof(SigmaWsSmem<G, HW, R>);
-    const void* kid = reinterpret_cast<const void*>(kern);
-    bool attr_done = false;
-    for (const void* k : ctx->configured_kernels) attr_done |= (k == kid);
-    if (!attr_done) {
-        PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int carve = (int)(((size_t)MINB * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-        if (getenv("PVACB_SIGMA_CARVEOUT")) carve = atoi(getenv("PVACB_SIGMA_CARVEOUT"));
-        PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
-        ctx->configured_kernels.push_back(kid);
-    }
-    const uint64_t grid = (uint64_t)ctx->sm_count * MINB;     // persistent: hashers pull groups from the work counter
-    PV_CUDA(cudaMemsetAsync(ctx->d_work, 0, 8, ctx->stream));
-    ProfScope ps(ctx, PROF_SIGMA);
-    kern<<<(unsigned)grid, (HW + GW) * 32, smem, ctx->stream>>>(J, ctx->kv.canon_tag, reinterpret_cast<const uint4*>(ctx->kv.H), ctx->d_work, 1u,
-                                                                 (uint32_t)ctx->sm_count);
-    return PV_OK;
-}
-
-template <int G, int HWG, int R, int ILP, int RH, int RG>
-static int sigma_ws2_launch(Ctx* ctx, const SigmaJobs& J) {
-    auto kern = sigma_ws2_kernel<G, HWG, R, ILP, RH, RG>;
-    constexpr int smem = (int)sizeof(SigmaWsSmem<G, 4 * HWG, R>);
-    const void* kid = reinterpret_cast<const void*>(kern);
-    bool attr_done = false;
-    for (const void* k : ctx->configured_kernels) attr_done |= (k == kid);
-    if (!attr_done) {
-        PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int carve = (int)(((size_t)(smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-        if (getenv("PVACB_SIGMA_CARVEOUT")) carve = atoi(getenv("PVACB_SIGMA_CARVEOUT"));
-        PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
-        ctx->configured_kernels.push_back(kid);
-    }
-    PV_CUDA(cudaMemsetAsync(ctx->d_work, 0, 8, ctx->stream));
-    ProfScope ps(ctx, PROF_SIGMA);
-    kern<<<(unsigned)ctx->sm_count, 1024, smem, ctx->stream>>>(J, ctx->kv.canon_tag, reinterpret_cast<const uint4*>(ctx->kv.H), ctx->d_work, 1u);
-    return PV_OK;
-}
-
 int sigma_run(Ctx* ctx, const SigmaJobs& J) {
     if (J.n == 0) return PV_OK;
     int rc;
@@ -773,15 +372,6 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
         case 5: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 1>(ctx, J); break;   // rounds 0..15 unrolled + 3-trip loop (two copies of the round code)
         case 8: rc = sigma_launch<8, 4, 5, true, 0, 8>(ctx, J); break;    // 20 warps/SM, 16 loads in flight per lane
         case 9: rc = sigma_launch<8, 4, 6, true, 0, 8>(ctx, J); break;    // 24 warps/SM, 16 loads in flight per lane
-        case 30: rc = sigma_ws_launch<6, 2, 6, 4, 14>(ctx, J); break;    // warp-specialised: 8 hashers + 24 gatherers per SM
-        case 31: rc = sigma_ws_launch<6, 2, 6, 4, 14, 1>(ctx, J); break;  // experiment: no gather loads (wrong results)
-        case 32: rc = sigma_ws_launch<6, 2, 6, 4, 14, 2>(ctx, J); break;  // experiment: no hashing (wrong results)
-        case 33: rc = sigma_ws_launch<6, 1, 3, 8, 8>(ctx, J); break;      // same roles in 4-warp CTAs
-        case 34: rc = sigma_ws_launch<6, 2, 7, 4, 16>(ctx, J); break;     // 8 hashers + 28 gatherers (56 registers)
-        case 35: rc = sigma_ws2_launch<6, 2, 44, 2, 88, 56>(ctx, J); break;   // 8 hashers x 2 chains (88 registers) + 24 gatherers (56)
-        case 36: rc = sigma_ws2_launch<6, 1, 40, 3, 120, 56>(ctx, J); break;  // 4 hashers x 3 chains (120 registers) + 28 gatherers (56)
-        case 37: rc = sigma_ws2_launch<6, 1, 40, 2, 120, 56>(ctx, J); break;  // 4 hashers x 2 chains + 28 gatherers
-        case 38: rc = sigma_ws2_launch<6, 2, 44, 1, 88, 56>(ctx, J); break;   // 8 hashers x 1 chain + 24 gatherers, one CTA per SM
         case 21: rc = sigma_launch<6, 4, 7, true, 1, 4>(ctx, J); break;   // experiment: no gather loads (wrong results)
         case 22: rc = sigma_launch<6, 4, 7, true, 2, 4>(ctx, J); break;   // experiment: no hashing (wrong results)
     }

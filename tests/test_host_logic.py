@@ -43,6 +43,10 @@ def test_header_symbols_exported():
     out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert set(declared) <= exported
+    # INTEGRATION.md maps every entry point to the reference interface it replaces (or says what it is for)
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    undocumented = [s for s in declared if s not in integ]
+    assert not undocumented, undocumented
 
 
 def test_product_has_no_oracle_or_cpu_fallback():

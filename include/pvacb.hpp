@@ -123,6 +123,38 @@ public:
         for (size_t i = 0; i < n_msgs; i++) out[i].assign(reinterpret_cast<const char*>(buf.data()) + off[i], (size_t)(off[i + 1] - off[i]));
         return out;
     }
+    // riders (ops/encrypt.hpp:162,293): one-share encryptions of field elements, encryptions of zero
+    Ciphers enc_fp_depth(const std::vector<Fp>& v, int depth_hint, uint64_t batch_seed) {
+        pvacb_batch* o = nullptr;
+        ck(pvacb_enc_fp_depth(ctx_, reinterpret_cast<const uint64_t*>(v.data()), v.size(), depth_hint, batch_seed, nullptr, &o));
+        return Ciphers(o);
+    }
+    Ciphers enc_zero_depth(size_t n, int depth_hint, uint64_t batch_seed) {
+        pvacb_batch* o = nullptr;
+        ck(pvacb_enc_zero_depth(ctx_, n, depth_hint, batch_seed, nullptr, &o));
+        return Ciphers(o);
+    }
+    // ct_recrypt (ops/recrypt.hpp:26) with EvalKey::zero_pool held as a batch; sigma_density (ops/encrypt.hpp:29); ubk_apply (crypto/matrix.hpp:306)
+    Ciphers ct_recrypt(const Ciphers& c, const Ciphers& zero_pool, uint64_t batch_seed) {
+        pvacb_batch* o = nullptr;
+        ck(pvacb_ct_recrypt(ctx_, c.handle(), zero_pool.handle(), batch_seed, nullptr, &o));
+        return Ciphers(o);
+    }
+    std::vector<double> sigma_density(const Ciphers& c) {
+        std::vector<double> d(c.size());
+        ck(pvacb_sigma_density(ctx_, c.handle(), d.data()));
+        return d;
+    }
+    Ciphers ubk_apply(const Ciphers& c) { pvacb_batch* o = nullptr; ck(pvacb_ubk_apply(ctx_, c.handle(), &o)); return Ciphers(o); }
+    // batch plumbing
+    Ciphers slice(const Ciphers& c, size_t first, size_t count) { pvacb_batch* o = nullptr; ck(pvacb_batch_slice(ctx_, c.handle(), first, count, &o)); return Ciphers(o); }
+    Ciphers concat(const std::vector<const Ciphers*>& parts) {
+        std::vector<const pvacb_batch*> h;
+        for (const Ciphers* p : parts) h.push_back(p->handle());
+        pvacb_batch* o = nullptr;
+        ck(pvacb_batch_concat(ctx_, h.data(), h.size(), &o));
+        return Ciphers(o);
+    }
     // the reference's on-disk format (tests/bounty2_test.cpp:63-143)
     std::vector<uint8_t> to_wire(const Ciphers& c) {
         size_t n = 0, w = 0;

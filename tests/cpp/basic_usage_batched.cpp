@@ -202,6 +202,36 @@ int main() {
         check(eng.to_wire(back) == buf && dec(back) == dec(ca), "export -> import -> export is the identity");
     }
 
+    section("recrypt (tests/test_main.cpp:282-306)");
+    {
+        Ciphers pool = eng.enc_zero_depth(32, 3, g_seed++);            // make_evalkey(pk, sk, 32, 3): the zero pool
+        check(all_eq(dec(pool), std::vector<u128>(32, 0)), "the pool encrypts zeros");
+        Ciphers x = enc({7, 1000003});
+        Ciphers x3 = mul(mul(x, x), x);
+        Ciphers u = eng.ct_recrypt(x3, pool, g_seed++);
+        check(dec(u) == dec(x3), "recrypt keeps the plaintext");
+        auto d = eng.sigma_density(u);
+        check(d[0] > 0.45 && d[0] < 0.55 && d[1] > 0.45 && d[1] < 0.55, "sigma density stays near 1/2");
+        Ciphers chain = enc({2});
+        int rec = 0;
+        for (int i = 1; i < 10; i++) {
+            chain = mul(chain, enc({2}));
+            if (i % 3 == 0) { chain = eng.ct_recrypt(chain, pool, g_seed++); rec++; }
+        }
+        check(all_eq(dec(chain), {1024}) && rec == 3, "2^10 with three recrypts");
+    }
+
+    section("slices and concatenation");
+    {
+        Ciphers all = enc({1, 2, 3, 4, 5});
+        Ciphers lo = eng.slice(all, 0, 2), hi = eng.slice(all, 2, 3);
+        Ciphers back = eng.concat({&lo, &hi});
+        check(eng.to_wire(back) == eng.to_wire(all), "slice + concat is the identity");
+        const std::vector<pvacb::Fp> fv = {pvacb::Fp{5, 0}, pvacb::Fp{~0ull, 0x7FFFFFFFFFFFFFFEull}};
+        Ciphers z = eng.enc_fp_depth(fv, 2, g_seed++);
+        check(dec(z) == fv, "enc_fp_depth round trip");
+    }
+
     std::printf("\npassed %d/%d\n", g_pass, g_pass + g_fail);
     return g_fail ? 1 : 0;
 }

@@ -154,6 +154,14 @@ __device__ __forceinline__ void sha_compress_from_rolled(const uint32_t* from, u
 }
 // Fully rolled: four trips of (16 rounds, then the schedule of the next 16 words unless this was the last trip) -- ONE copy of
 // the round code (~10 KB of SASS instead of ~14 KB), same dynamic instruction count.
+// SPARSE: the caller guarantees w[2] = 0 and w[4..14] = 0 (block 1 of the counter hashes of prg_choose_k: tail of the salt, the
+// counter, 0x80, zeros, the bit length). Words 16..31 of the schedule then need 15 small sigmas instead of 32:
+//   W16 = s0(w1) + w0            W17 = s1(w15) + w1          W18 = s1(W16) + s0(w3)      W19 = s1(W17) + w3
+//   W20 = s1(W18)                W21 = s1(W19)               W22 = s1(W20) + w15         W23..W29 = s1(W[t-2]) + W[t-7]
+//   W30 = s1(W28) + W23 + s0(w15)                            W31 = s1(W29) + W24 + s0(W16) + w15
+__device__ __forceinline__ uint32_t sha_s0(uint32_t x) { return sha_rotr(x, 7) ^ sha_rotr(x, 18) ^ (x >> 3); }
+__device__ __forceinline__ uint32_t sha_s1(uint32_t x) { return sha_rotr(x, 17) ^ sha_rotr(x, 19) ^ (x >> 10); }
+template <bool SPARSE = false>
 __device__ __forceinline__ void sha_compress_from_rolled4(const uint32_t* from, uint32_t w[16], uint32_t out[8], uint32_t one) {
     uint32_t a = from[0], b = from[1], c = from[2], d = from[3], e = from[4], f = from[5], g = from[6], h = from[7];
 #pragma unroll 1
@@ -167,7 +175,20 @@ __device__ __forceinline__ void sha_compress_from_rolled4(const uint32_t* from, 
             uint32_t t2 = sha_add_fma(S0, maj, one);
             h = g; g = f; f = e; e = sha_add_fma(d, t1, one); d = c; c = b; b = a; a = sha_add_fma(t1, t2, one);
         }
-        if (it < 48) {
+        if (SPARSE && it == 0) {
+            const uint32_t w3 = w[3], w15 = w[15];
+            w[0] = sha_add_fma(sha_s0(w[1]), w[0], one);                                   // W16
+            w[1] = sha_add_fma(sha_s1(w15), w[1], one);                                    // W17
+            w[2] = sha_add_fma(sha_s1(w[0]), sha_s0(w3), one);                             // W18
+            w[3] = sha_add_fma(sha_s1(w[1]), w3, one);                                     // W19
+            w[4] = sha_s1(w[2]);                                                           // W20
+            w[5] = sha_s1(w[3]);                                                           // W21
+            w[6] = sha_add_fma(sha_s1(w[4]), w15, one);                                    // W22
+#pragma unroll
+            for (int j = 7; j < 14; j++) w[j] = sha_add_fma(sha_s1(w[j - 2]), w[j - 7], one);   // W23..W29
+            w[14] = sha_add_fma(sha_add_fma(sha_s1(w[12]), w[7], one), sha_s0(w15), one);  // W30
+            w[15] = sha_add_fma(sha_add_fma(sha_s1(w[13]), w[8], one), sha_add_fma(sha_s0(w[0]), w15, one), one);   // W31
+        } else if (it < 48) {
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 uint32_t w15 = w[(j + 1) & 15], w2 = w[(j + 14) & 15];

@@ -250,7 +250,7 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
             sha_block_from_le64(q, w);
             if (ROLLED) {
                 uint32_t d[8];
-                if (ROLLED >= 2) sha_compress_from_rolled4(kShaIv, w, d, one);
+                if (ROLLED >= 2) sha_compress_from_rolled4<false>(kShaIv, w, d, one);
                 else sha_compress_from_rolled(kShaIv, w, d, one);
 #pragma unroll
                 for (int i = 0; i < 8; i++) S.mid[lane][i] = d[i];
@@ -284,7 +284,7 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
             if (EXP == 2) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) d[i] = (uint32_t)(h * 8 + i) * 2654435761u + w[0];
-            } else if (ROLLED == 2) sha_compress_from_rolled4(S.mid[sl], w, d, one);
+            } else if (ROLLED == 2) sha_compress_from_rolled4<true>(S.mid[sl], w, d, one);
             else if (ROLLED) sha_compress_from_rolled(S.mid[sl], w, d, one);
             else if (FMA) sha_compress_from_fma(S.mid[sl], w, d, one);
             else sha_compress_from(S.mid[sl], w, d);

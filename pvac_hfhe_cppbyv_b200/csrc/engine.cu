@@ -133,10 +133,24 @@ static void derive_key_view(Ctx* ctx) {
     ctx->have_keys = true;
 }
 
+// The key blob must not straddle a 4 GiB boundary: the sigma kernel forms the addresses of the columns of H with 32-bit
+// arithmetic on the low word (one IMAD per column instead of a 64-bit add on the ALU pipe that bounds it).
 static int ensure_blob(Ctx* ctx) {
     if (ctx->d_blob) return PV_OK;
-    PV_CUDA(cudaMalloc((void**)&ctx->d_blob, kBlobBytes));
-    return PV_OK;
+    void* held[4] = {nullptr, nullptr, nullptr, nullptr};
+    int nheld = 0;
+    int rc = PV_OK;
+    for (;;) {
+        uint64_t* p = nullptr;
+        cudaError_t e = cudaMalloc((void**)&p, kBlobBytes);
+        if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); rc = PV_E_OOM; break; }
+        const uint64_t a = reinterpret_cast<uint64_t>(p);
+        if ((a >> 32) == ((a + kBlobBytes - 1) >> 32)) { ctx->d_blob = p; break; }
+        if (nheld == 4) { cudaFree(p); ctx->last_error = "key blob: no placement inside one 4 GiB window"; rc = PV_E_CUDA; break; }
+        held[nheld++] = p;                 // keep the straddling block allocated so that the next try lands elsewhere
+    }
+    for (int i = 0; i < nheld; i++) cudaFree(held[i]);
+    return rc;
 }
 
 static int keys_from_host_blob(Ctx* ctx, const uint64_t* blob) {

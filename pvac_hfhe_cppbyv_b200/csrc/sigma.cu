@@ -55,7 +55,7 @@ __device__ __noinline__ void prg_hash_words(const LabelStream ls, const uint64_t
 template <int G, int NH = kCandHashes>
 struct __align__(16) SigmaWarpSmem {
     uint32_t bm[kNBits / 32];               // 2 KiB: de-dup bitmap of the columns, then of the noise bits (= the flip mask)
-    uint32_t cols[kXColWt];                 // chosen columns in draw order, as byte offsets into H (col * 1024)
+    uint32_t cols[kXColWt + 4];             // chosen columns in draw order, as byte offsets into H (col * 1024); 4 entries of padding
     uint16_t cand[G * 2 * NH * 4];          // phase B output: [edge][label][4 NH]  (NH = 34: 136 candidates)
     union {
         uint32_t mid[G * 2][8];             // phase A output: SHA-256 state after block 0, per (edge, label)
@@ -126,11 +126,15 @@ __device__ __forceinline__ void dedupe_label(uint32_t* bm, uint32_t* cols, uint1
     __syncwarp();
 }
 
-// address of this lane's 16 bytes of a column: Hl + byte offset as ONE mad.wide on the FMA pipe (`one` is a run-time 1). Written as
-// pointer arithmetic it costs IADD3 + LEA + LEA.HI.X on the ALU pipe per column, and the ALU pipe is what bounds the kernel.
+// address of this lane's 16 bytes of a column = Hl + byte offset, formed on the FMA pipe: the low word as off * one + lo(Hl)
+// (`one` is a run-time 1), the high word is that of Hl -- the key blob never straddles a 4 GiB boundary (engine.cu: ensure_blob).
+// Written as pointer arithmetic it costs IADD3 + LEA + LEA.HI.X per column on the ALU pipe, which is what bounds the kernel.
 __device__ __forceinline__ const uint4* col_ptr(const uint4* Hl, uint32_t byte_off, uint32_t one) {
+    const uint64_t b = reinterpret_cast<uint64_t>(Hl);
+    uint32_t lo;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(byte_off), "r"(one), "r"((uint32_t)b));
     uint64_t r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(byte_off), "r"(one), "l"(reinterpret_cast<uint64_t>(Hl)));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"((uint32_t)(b >> 32)));
     return reinterpret_cast<const uint4*>(r);
 }
 
@@ -173,8 +177,11 @@ __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_
             }
         }
     } else {
+        // clear the bitmap again (every word that got a bit belongs to one of the chosen columns). The loop below is kept free of
+        // everything but loads and XORs: the kernel is bound by the ALU pipe, and a compare per step is 32 ALU instructions per edge.
+        for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 15] = 0;
         uint4 c0 = *reinterpret_cast<const uint4*>(&cols[0]);
-#pragma unroll 1
+#pragma unroll 2
         for (int i = 0; i < kXColWt; i += 4) {
             const uint32_t co[4] = {c0.x, c0.y, c0.z, c0.w};
             uint4 v[8];
@@ -185,10 +192,7 @@ __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_
                 v[2 * k] = __ldcg(p);
                 v[2 * k + 1] = __ldcg(p + 32);
             }
-            if (i == 0) {
-                for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 15] = 0;
-            }
-            if (i + 4 < kXColWt) c0 = *reinterpret_cast<const uint4*>(&cols[i + 4]);
+            c0 = *reinterpret_cast<const uint4*>(&cols[i + 4]);       // the last step reads the 4 padding entries
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 a0.x ^= v[2 * k].x; a0.y ^= v[2 * k].y; a0.z ^= v[2 * k].z; a0.w ^= v[2 * k].w;

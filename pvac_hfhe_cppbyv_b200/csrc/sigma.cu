@@ -181,7 +181,7 @@ __device__ __forceinline__ void sigma_edge(uint32_t* bm, uint32_t* cols, uint16_
         // everything but loads and XORs: the kernel is bound by the ALU pipe, and a compare per step is 32 ALU instructions per edge.
         for (int q = lane; q < kXColWt; q += 32) bm[cols[q] >> 15] = 0;
         uint4 c0 = *reinterpret_cast<const uint4*>(&cols[0]);
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < kXColWt; i += 4) {
             const uint32_t co[4] = {c0.x, c0.y, c0.z, c0.w};
             uint4 v[8];
@@ -288,14 +288,23 @@ sigma_fused_kernel(SigmaJobs J, uint64_t canon, const uint4* __restrict__ H4, un
             if (EXP == 2) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) d[i] = (uint32_t)(h * 8 + i) * 2654435761u + w[0];
-            } else if (ROLLED == 2) sha_compress_from_rolled4<true>(S.mid[sl], w, d, one);
+            } else if (ROLLED >= 2) sha_compress_from_rolled4<true>(S.mid[sl], w, d, one);
             else if (ROLLED) sha_compress_from_rolled(S.mid[sl], w, d, one);
             else if (FMA) sha_compress_from_fma(S.mid[sl], w, d, one);
             else sha_compress_from(S.mid[sl], w, d);
             const uint32_t N = label ? (uint32_t)kMBits : (uint32_t)kNBits;
+            // word k of the hash = LE64 of digest bytes 8k..8k+7, i.e. bswap(d[2k]) | bswap(d[2k+1]) << 32. N is a power of two below
+            // 2^16: the candidate is the low 16 bits masked (digest bytes 8k, 8k+1 = the top two bytes of d[2k]), and the word is only
+            // rejected when it exceeds 2^64 - N, which needs d[2k+1] == 0xFFFFFFFF: that (2^-30 per hash) takes the exact path.
             uint2 pk;
-            pk.x = (uint32_t)cand_from_word(sha_le64_of(d[0], d[1]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[2], d[3]), N) << 16);
-            pk.y = (uint32_t)cand_from_word(sha_le64_of(d[4], d[5]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[6], d[7]), N) << 16);
+            if (ROLLED != 3 && NH != 32 && max(max(d[1], d[3]), max(d[5], d[7])) != 0xFFFFFFFFu) {     // (the NH = 32 test shape always takes the exact path)
+                const uint32_t M = (N - 1) * 0x00010001u;
+                pk.x = __byte_perm(d[0], d[2], 0x6723) & M;
+                pk.y = __byte_perm(d[4], d[6], 0x6723) & M;
+            } else {
+                pk.x = (uint32_t)cand_from_word(sha_le64_of(d[0], d[1]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[2], d[3]), N) << 16);
+                pk.y = (uint32_t)cand_from_word(sha_le64_of(d[4], d[5]), N) | ((uint32_t)cand_from_word(sha_le64_of(d[6], d[7]), N) << 16);
+            }
             reinterpret_cast<uint2*>(S.cand + sl * (4 * NH))[ctr] = pk;
         }
         __syncwarp();
@@ -374,6 +383,7 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
         case 3: rc = sigma_launch<8, 4, 7, true, 0, 4>(ctx, J); break;    // 28 warps/SM but 217 KB shared: the slow L1 split
         case 4: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 0>(ctx, J); break;   // the default shape with fully unrolled compressions
         case 5: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 1>(ctx, J); break;   // rounds 0..15 unrolled + 3-trip loop (two copies of the round code)
+        case 6: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 3>(ctx, J); break;   // A/B: exact candidate packing only
         case 8: rc = sigma_launch<8, 4, 5, true, 0, 8>(ctx, J); break;    // 20 warps/SM, 16 loads in flight per lane
         case 9: rc = sigma_launch<8, 4, 6, true, 0, 8>(ctx, J); break;    // 24 warps/SM, 16 loads in flight per lane
         case 21: rc = sigma_launch<6, 4, 7, true, 1, 4>(ctx, J); break;   // experiment: no gather loads (wrong results)

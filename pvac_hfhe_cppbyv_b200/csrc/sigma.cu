@@ -366,28 +366,29 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
     if (J.n == 0) return PV_OK;
     int rc;
     // shape (G edges per warp-group, warps per CTA, CTAs per SM). G*68 hashes should fill whole 32-lane rounds (G = 8: 17
-    // rounds exactly, G = 6: 12.75); shared memory per warp = 2560 + 616 G bytes bounds the resident warps, and the total must
-    // stay under ~196 KB per SM or the L2 gather ceiling drops by 18 % (see sigma_launch). PVACB_SIGMA_CFG picks another
+    // rounds exactly, G = 5: 10.6); shared memory per warp = 2576 + 616 G bytes bounds the resident warps, and the total must
+    // stay under ~196 KB per SM or the L2 gather ceiling drops by 18 % (see sigma_launch). Since the ALU trimming of round 1 the
+    // kernel fits 64 registers without spills and 32 resident warps beat 28 (7.02 vs 7.15 ms per 2^20 edges). PVACB_SIGMA_CFG picks another
     // compiled shape for tuning runs. Small batches use groups of 2 edges so that more warps (and SMs) take part.
     static int cfg = -1;
     if (cfg < 0) {
         const char* e = getenv("PVACB_SIGMA_CFG");
         cfg = e ? atoi(e) : 0;
     }
-    if (cfg == 40) rc = sigma_launch<6, 4, 7, true, 0, 4, 32>(ctx, J);   // test shape: no spare candidates, the PRG continuation runs for ~3 of 4 edges
-    else if (J.n < (uint64_t)ctx->sm_count * 7 * 4 * 6) rc = sigma_launch<2, 4, 8, true, 0, 4>(ctx, J);
+    if (cfg == 40) rc = sigma_launch<5, 4, 8, true, 0, 4, 32>(ctx, J);   // test shape: no spare candidates, the PRG continuation runs for ~3 of 4 edges
+    else if (J.n < (uint64_t)ctx->sm_count * 8 * 4 * 5) rc = sigma_launch<2, 4, 8, true, 0, 4>(ctx, J);
     else switch (cfg) {
-        default: rc = sigma_launch<6, 4, 7, true, 0, 4>(ctx, J); break;   // 28 warps/SM, 182 KB of shared memory: L1 keeps 60 KB
+        default: rc = sigma_launch<5, 4, 8, true, 0, 4>(ctx, J); break;   // 32 warps/SM at 64 registers, 183 KB of shared memory: L1 keeps 45 KB
         case 1: rc = sigma_launch<8, 4, 6, true, 0, 4>(ctx, J); break;    // 24 warps/SM, exact 17-round groups
-        case 2: rc = sigma_launch<5, 4, 8, true, 0, 4>(ctx, J); break;    // 32 warps/SM
+        case 2: rc = sigma_launch<6, 4, 7, true, 0, 4>(ctx, J); break;    // 28 warps/SM at 72 registers (the default before the ALU trimming)
         case 3: rc = sigma_launch<8, 4, 7, true, 0, 4>(ctx, J); break;    // 28 warps/SM but 217 KB shared: the slow L1 split
-        case 4: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 0>(ctx, J); break;   // the default shape with fully unrolled compressions
-        case 5: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 1>(ctx, J); break;   // rounds 0..15 unrolled + 3-trip loop (two copies of the round code)
-        case 6: rc = sigma_launch<6, 4, 7, true, 0, 4, kCandHashes, 3>(ctx, J); break;   // A/B: exact candidate packing only
+        case 4: rc = sigma_launch<5, 4, 8, true, 0, 4, kCandHashes, 0>(ctx, J); break;   // the default shape with fully unrolled compressions
+        case 5: rc = sigma_launch<5, 4, 8, true, 0, 4, kCandHashes, 1>(ctx, J); break;   // rounds 0..15 unrolled + 3-trip loop (two copies of the round code)
+        case 6: rc = sigma_launch<5, 4, 8, true, 0, 4, kCandHashes, 3>(ctx, J); break;   // A/B: exact candidate packing only
         case 8: rc = sigma_launch<8, 4, 5, true, 0, 8>(ctx, J); break;    // 20 warps/SM, 16 loads in flight per lane
         case 9: rc = sigma_launch<8, 4, 6, true, 0, 8>(ctx, J); break;    // 24 warps/SM, 16 loads in flight per lane
-        case 21: rc = sigma_launch<6, 4, 7, true, 1, 4>(ctx, J); break;   // experiment: no gather loads (wrong results)
-        case 22: rc = sigma_launch<6, 4, 7, true, 2, 4>(ctx, J); break;   // experiment: no hashing (wrong results)
+        case 21: rc = sigma_launch<5, 4, 8, true, 1, 4>(ctx, J); break;   // experiment: no gather loads (wrong results)
+        case 22: rc = sigma_launch<5, 4, 8, true, 2, 4>(ctx, J); break;   // experiment: no hashing (wrong results)
     }
     if (rc) return rc;
     PV_CUDA(cudaGetLastError());

@@ -31,6 +31,7 @@ if ROOT not in sys.path:
 P127 = (1 << 127) - 1
 EDGE_WIRE_BYTES = 1052          # serialised edge (tests/bounty2_test.cpp:98-106): the byte convention of SURVEY 8d
 GATHER_BYTES_PER_EDGE = 128 * 1024
+WORKLOAD = "ct_mul fresh x fresh (2 layers, 39-40 edges each -> 8 layers, ~1200 edges), default Params"   # both arms
 SHA_PER_EDGE = 70               # 2 midstates + 2 x 34 counter hashes (csrc/sigma.cu)
 AES_LDS_PER_BLOCK = 197         # T-table lookups per AES-256 block after hoisting rounds 1-2 (csrc/aes256.cuh)
 ALU_LANE_OPS_PER_S = 18.55e12    # measured LOP3/SHF/PRMT rate of this GPU (profiles/micro/int_pipes.cu): 63.8 lanes/clk/SM
@@ -144,7 +145,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "ct_mul/s", "value": v, "unit": "ct_mul/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (GF(2^127-1) limbs, bitwise)",
-        "data": "synthetic", "config": {"workload": "ct_mul fresh x fresh (2 layers, 39-40 edges each), default Params, lpn_t=16384", "pairs_per_step": threads * iters},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "pairs_per_step": threads * iters, "note": "bounded sample of the same workload; the reference runs with its default Params (lpn_t = 16384)"},
         "cpu_baseline": {"value": v, "unit": "ct_mul/s", "cores": threads, "kind": "reference",
                          "sample": f"{args.steps} steps x {threads} threads x {iters} ct_mul each, unmodified reference headers, g++ -O2 -march=x86-64-v3 -maes -mpclmul"},
         "e2e": {"value": v, "unit": "ct_mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -487,7 +488,7 @@ def main():
             "metric": "ct_mul/s", "value": value, "unit": "ct_mul/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 (GF(2^127-1) limbs, bitwise)", "data": "synthetic",
-            "config": {"workload": "ct_mul fresh x fresh (2 layers, 39-40 edges each -> 8 layers, ~1200 edges), default Params",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_step_per_gpu": M, "out_edges_per_step_per_gpu": edges_per_step, "input_bytes_resident": in_bytes,
                        "l2": "inputs (%.0f MB) and outputs (%.1f GB per step) exceed the 126 MB L2; the 16 MiB matrix H is meant to be L2 resident" % (in_bytes / 1e6, edges_per_step * 1052 / 1e9),
                        "sharding": f"batch index, {world} rank(s), keys replicated by one NCCL broadcast, no steady-state collective", "prf_mode_for_inputs": "live"},

@@ -69,12 +69,15 @@ __device__ __forceinline__ uint4 probe_load(const uint4* p) {
     if (LD == 3) return __ldcs(p);
     return __ldcg(p);
 }
-template <int U, int LD = 0>
+// PIPE > 1 unrolls the column loop so that ptxas issues the next batch of loads before the last XORs of the current one, like
+// the gather loop of sigma_fused_kernel (16 columns per trip).
+template <int U, int LD = 0, int PIPE = 1>
 __global__ void __launch_bounds__(256) l2_gather_probe_kernel(const uint4* __restrict__ H4, uint32_t cols_per_warp, uint4* __restrict__ sink) {
     const int lane = threadIdx.x & 31;
     uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t state = w * 2654435761u + 12345u;
     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+#pragma unroll PIPE
     for (uint32_t i = 0; i < cols_per_warp; i += U) {
         uint4 v[2 * U];
 #pragma unroll
@@ -292,6 +295,7 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
             else if (ld == 3) l2_gather_probe_kernel<8, 3><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (ld == 4) l2_gather_probe_kernel<8, 4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (ld == 5) l2_gather_probe_kernel<4, 4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (shape / 2 == 0 && (sh & 1) == 0 && sh < 6) l2_gather_probe_kernel<4, 0, 4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (shape / 2 == 0) l2_gather_probe_kernel<4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (shape / 2 == 1) l2_gather_probe_kernel<8><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else l2_gather_probe_kernel<16><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
@@ -304,7 +308,7 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
             if (r > 1 && g > best) best = g;
             if (r > 1 && g > shape_best) shape_best = g;
         }
-        if (getenv("PVACB_PROBE_VERBOSE")) fprintf(stderr, "l2 gather probe: %d columns in flight per warp, %d warps/SM: %.0f GB/s\n", 4 << (shape / 2), ctas_per_sm * 8, shape_best);
+        if (getenv("PVACB_PROBE_VERBOSE")) fprintf(stderr, "l2 gather probe: %d columns in flight per warp%s, %d warps/SM: %.0f GB/s\n", 4 << (shape / 2), sh == 0 ? " (loop unrolled x4)" : "", ctas_per_sm * 8, shape_best);
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     dev_free(ctx, sink);

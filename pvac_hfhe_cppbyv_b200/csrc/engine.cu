@@ -685,6 +685,7 @@ int pvacb_batch_import_wire(pvacb_ctx* x, const void* buf, size_t bytes, pvacb_b
         off += nbytes;
         return true;
     };
+    auto truncated = [&]() { ctx->last_error = "ciphertext file ends inside a record"; return (int)PV_E_FORMAT; };
     uint32_t magic = 0, ver = 0;
     uint64_t cnt = 0;
     if (!get(&magic, 4) || !get(&ver, 4) || !get(&cnt, 8) || magic != kMagicCT || ver != kWireVer) { ctx->last_error = "bad CT header"; return PV_E_FORMAT; }
@@ -692,14 +693,14 @@ int pvacb_batch_import_wire(pvacb_ctx* x, const void* buf, size_t bytes, pvacb_b
     h.loff.push_back(0); h.eoff.push_back(0);
     for (uint64_t i = 0; i < cnt; i++) {
         uint32_t nl = 0, ne = 0;
-        if (!get(&nl, 4) || !get(&ne, 4)) return PV_E_FORMAT;
+        if (!get(&nl, 4) || !get(&ne, 4)) return truncated();
         for (uint32_t k = 0; k < nl; k++) {
             uint8_t r = 0;
             uint64_t a = 0, b = 0, c = 0;
             uint32_t pa = 0, pb = 0;
-            if (!get(&r, 1)) return PV_E_FORMAT;
-            if (r == 1) { if (!get(&pa, 4) || !get(&pb, 4)) return PV_E_FORMAT; }
-            else if (!get(&a, 8) || !get(&b, 8) || !get(&c, 8)) return PV_E_FORMAT;
+            if (!get(&r, 1)) return truncated();
+            if (r == 1) { if (!get(&pa, 4) || !get(&pb, 4)) return truncated(); }
+            else if (!get(&a, 8) || !get(&b, 8) || !get(&c, 8)) return truncated();
             h.rule.push_back(r); h.ztag.push_back(a); h.nlo.push_back(b); h.nhi.push_back(c); h.pa.push_back(pa); h.pb.push_back(pb);
         }
         for (uint32_t e = 0; e < ne; e++) {
@@ -707,16 +708,18 @@ int pvacb_batch_import_wire(pvacb_ctx* x, const void* buf, size_t bytes, pvacb_b
             uint16_t idx = 0;
             uint8_t ch = 0, pad = 0;
             uint64_t w[2];
-            if (!get(&lid, 4) || !get(&idx, 2) || !get(&ch, 1) || !get(&pad, 1) || !get(w, 16) || !get(&nbits, 4)) return PV_E_FORMAT;
+            if (!get(&lid, 4) || !get(&idx, 2) || !get(&ch, 1) || !get(&pad, 1) || !get(w, 16) || !get(&nbits, 4)) return truncated();
             if (nbits != kMBits) { ctx->last_error = "sigma length is not m_bits"; return PV_E_FORMAT; }
+            if (pad != 0) { ctx->last_error = "reserved edge byte is not zero"; return PV_E_FORMAT; }   // putEdge always writes 0 there
             size_t so = h.sigma.size();
             h.sigma.resize(so + kMWords);
-            if (!get(&h.sigma[so], kMWords * 8)) return PV_E_FORMAT;
+            if (!get(&h.sigma[so], kMWords * 8)) return truncated();
             h.lid.push_back(lid); h.idx.push_back(idx); h.ch.push_back(ch); h.w.push_back(w[0]); h.w.push_back(w[1]);
         }
         h.loff.push_back((uint32_t)h.rule.size());
         h.eoff.push_back((uint32_t)h.lid.size());
     }
+    if (off != bytes) { ctx->last_error = "trailing bytes after the last ciphertext"; return PV_E_FORMAT; }
     return pvacb_batch_import_soa(x, cnt, h.loff.data(), h.eoff.data(), h.rule.data(), h.ztag.data(), h.nlo.data(), h.nhi.data(), h.pa.data(),
                                   h.pb.data(), h.lid.data(), h.idx.data(), h.ch.data(), h.w.data(), h.sigma.data(), out);
 }

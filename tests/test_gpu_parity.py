@@ -703,3 +703,35 @@ def test_prg_continuation_path():
                        capture_output=True, text=True, env=env, cwd=root, timeout=800)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_wire_import_rejects_malformed_input(engine, api):
+    """the importer of the reference's file format (tests/bounty2_test.cpp:103-143 reads the same fields with range checks) never
+    crashes and never accepts a damaged file silently: truncations and corrupted counts give a status code; a mutation that
+    still parses must re-export to exactly the mutated bytes (so nothing was dropped or invented)"""
+    good = open(os.path.join(GOLDEN, "bounty2", "a.ct"), "rb").read()
+    assert engine.export_wire(engine.import_wire(good)) == good
+    rng = np.random.default_rng(99)
+    rejected = accepted = 0
+    cuts = [0, 1, 7, 8, 15, 16, 17, 24, 31, 32, 40, len(good) - 1, len(good) // 2] + list(rng.integers(0, len(good), 40))
+    for cut in cuts:
+        with pytest.raises(api.PvacbError):
+            engine.import_wire(good[: int(cut)])
+        rejected += 1
+    for trial in range(120):
+        bad = bytearray(good)
+        pos = int(rng.integers(0, 64)) if trial % 2 == 0 else int(rng.integers(0, len(good)))   # the header holds the counts
+        bad[pos] ^= int(rng.integers(1, 256))
+        try:
+            b = engine.import_wire(bytes(bad))
+        except api.PvacbError:
+            rejected += 1
+            continue
+        accepted += 1
+        assert engine.export_wire(b) == bytes(bad)
+    with pytest.raises(api.PvacbError):
+        engine.import_wire(good + b"\x00")               # trailing bytes
+    assert rejected > 50 and accepted > 0
+    # the context is still healthy afterwards
+    assert engine.export_wire(engine.import_wire(good)) == good

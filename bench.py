@@ -345,7 +345,7 @@ def main():
     pending = []
 
     def retire():
-        eng.export_wait()                            # the previous product is now complete in host memory
+        eng.export_wait_one()                        # the oldest product is now complete in host memory
         P0, d0 = pending.pop(0)
         d2h_list.append(sum(v.nbytes for v in d0.values() if isinstance(v, np.ndarray)))
         P0.free()
@@ -354,20 +354,22 @@ def main():
         X = eng.import_soa(in_a)                     # H2D from pinned host arrays
         Y = eng.import_soa(in_b)
         P = eng.ct_mul(X, Y, tape_states=item_states(3000 + k, g0, Me))
-        if pending:
-            retire()
-        pending.append((P, eng.export_soa_async(P, out_bufs[k & 1])))
+        pending.append((P, eng.export_soa_async(P, out_bufs[k & 1])))    # queued behind the previous export: the copy engine never idles
+        if len(pending) > 1:
+            retire()                                 # frees the other buffer set for step k + 1
         X.free(); Y.free()
 
     for k in range(args.warmup):
         step_e2e(k)
-    retire()
+    while pending:
+        retire()
     d2h_list.clear()
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         step_e2e(args.warmup + k)
-    retire()                                         # the last product's device->host read is inside the timed region
+    while pending:
+        retire()                                     # the last product's device->host read is inside the timed region
     torch.cuda.synchronize()
     e2e_secs = max_over_ranks(time.perf_counter() - t0)
     barrier()

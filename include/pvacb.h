@@ -175,7 +175,10 @@ int pvacb_batch_export_soa(pvacb_ctx* ctx, const pvacb_batch* b, uint32_t* layer
 int pvacb_batch_export_soa_async(pvacb_ctx* ctx, const pvacb_batch* b, uint32_t* layer_off, uint32_t* edge_off, uint8_t* rule,
                                  uint64_t* ztag, uint64_t* nonce_lo, uint64_t* nonce_hi, uint32_t* pa, uint32_t* pb,
                                  uint32_t* layer_id, uint16_t* idx, uint8_t* ch, uint64_t* w, uint64_t* sigma);
-int pvacb_export_wait(pvacb_ctx* ctx);
+int pvacb_export_wait(pvacb_ctx* ctx);            /* all asynchronous exports issued so far are complete */
+/* only the OLDEST outstanding asynchronous export is complete: with two sets of host buffers the next export can already be
+ * queued behind the one being waited for, so the copy engine never idles between them */
+int pvacb_export_wait_one(pvacb_ctx* ctx);
 int pvacb_batch_import_soa(pvacb_ctx* ctx, size_t n, const uint32_t* layer_off, const uint32_t* edge_off, const uint8_t* rule,
                            const uint64_t* ztag, const uint64_t* nonce_lo, const uint64_t* nonce_hi, const uint32_t* pa,
                            const uint32_t* pb, const uint32_t* layer_id, const uint16_t* idx, const uint8_t* ch,

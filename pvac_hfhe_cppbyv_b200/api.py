@@ -40,7 +40,7 @@ SYMBOLS = [
     "pvacb_batch_slice", "pvacb_batch_export_soa", "pvacb_batch_import_soa", "pvacb_batch_wire_size", "pvacb_batch_export_wire",
     "pvacb_batch_import_wire", "pvacb_batch_synthetic", "pvacb_prf", "pvacb_sigma_from_H", "pvacb_fp_op",
     "pvacb_profile_enable", "pvacb_profile_collect", "pvacb_keys_copy_blob_to", "pvacb_keys_adopt_blob_from", "pvacb_l2_gather_probe",
-    "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_compact_edges", "pvacb_batch_checksum", "pvacb_commit_ct",
+    "pvacb_batch_export_soa_async", "pvacb_export_wait", "pvacb_export_wait_one", "pvacb_compact_edges", "pvacb_batch_checksum", "pvacb_commit_ct",
     "pvacb_enc_value_depth", "pvacb_enc_zero_depth", "pvacb_plan_noise", "pvacb_ct_neg", "pvacb_ct_div_const", "pvacb_enc_fp_depth",
     "pvacb_enc_text", "pvacb_dec_text", "pvacb_batch_concat",
     "pvacb_ct_recrypt", "pvacb_sigma_density", "pvacb_ubk_apply", "pvacb_ubk_perm", "pvacb_batch_select",
@@ -112,6 +112,7 @@ def load_library():
         "pvacb_l2_gather_probe": (i32, [vp, i32, P(C.c_double)]),
         "pvacb_batch_export_soa_async": (i32, [vp, vp, P(u32), P(u32), P(u8), P(u64), P(u64), P(u64), P(u32), P(u32), P(u32), P(u16), P(u8), P(u64), P(u64)]),
         "pvacb_export_wait": (i32, [vp]),
+        "pvacb_export_wait_one": (i32, [vp]),
         "pvacb_compact_edges": (i32, [vp, vp, P(vp)]),
         "pvacb_batch_checksum": (i32, [vp, vp, P(u64)]),
         "pvacb_commit_ct": (i32, [vp, vp, P(u8)]),
@@ -482,6 +483,10 @@ class Engine:
 
     def export_wait(self):
         self._ck(self.L.pvacb_export_wait(self.h))
+
+    def export_wait_one(self):
+        """wait for the oldest outstanding export_soa_async only (later ones keep running)"""
+        self._ck(self.L.pvacb_export_wait_one(self.h))
 
     def import_soa(self, d):
         n = len(d["loff"]) - 1

@@ -231,6 +231,7 @@ void pvacb_ctx_destroy(pvacb_ctx* x) {
     Ctx* ctx = C(x);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t e : ctx->export_events) cudaEventDestroy(e);
     cudaFree(ctx->d_blob);
     cudaFree(ctx->d_aes);
     cudaFree(ctx->d_primes);
@@ -550,6 +551,10 @@ int pvacb_batch_export_soa_async(pvacb_ctx* x, const pvacb_batch* pb, uint32_t* 
     PV_CUDA(cp(ch, b->ch, b->nE));
     PV_CUDA(cp(w, b->w, b->nE * 16));
     PV_CUDA(cp(sigma, b->sigma, b->nE * (size_t)kMWords * 8));
+    cudaEvent_t done;
+    PV_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    PV_CUDA(cudaEventRecord(done, ctx->stream2));
+    ctx->export_events.push_back(done);
     return PV_OK;
 }
 
@@ -557,6 +562,20 @@ int pvacb_export_wait(pvacb_ctx* x) {
     Ctx* ctx = C(x);
     cudaSetDevice(ctx->device);
     PV_CUDA(cudaStreamSynchronize(ctx->stream2));
+    for (cudaEvent_t e : ctx->export_events) cudaEventDestroy(e);
+    ctx->export_events.clear();
+    return PV_OK;
+}
+
+int pvacb_export_wait_one(pvacb_ctx* x) {
+    Ctx* ctx = C(x);
+    cudaSetDevice(ctx->device);
+    if (ctx->export_events.empty()) return PV_OK;
+    cudaEvent_t e = ctx->export_events.front();
+    ctx->export_events.pop_front();
+    cudaError_t err = cudaEventSynchronize(e);
+    cudaEventDestroy(e);
+    PV_CUDA(err);
     return PV_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstddef>
 #include <vector>
+#include <deque>
 #include <string>
 
 #include "common.cuh"
@@ -43,6 +44,7 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;
+    std::deque<cudaEvent_t> export_events;   // one per pvacb_batch_export_soa_async still to be waited for, in issue order
     int sm_count = 148;
     bool have_keys = false;
     uint64_t* d_blob = nullptr;      // kBlobBytes

@@ -333,6 +333,19 @@ def test_async_export_equals_sync_export(engine):
     assert not np.array_equal(engine.export_soa(P2)["sigma"], ref["sigma"])      # different salts, different syndromes
     with pytest.raises(Exception):
         engine.export_soa_async(P1, dict(bufs, sigma=np.zeros((3, 128), np.uint64)))
+    # two exports in flight into two buffer sets, retired one at a time in issue order (pvacb_export_wait_one)
+    bufs2 = {k: np.zeros_like(v) for k, v in bufs.items()}
+    d1 = engine.export_soa_async(P1, bufs)
+    d2 = engine.export_soa_async(P2, bufs2)
+    engine.export_wait_one()
+    for k, v in ref.items():
+        assert np.array_equal(d1[k], v), k
+    engine.export_wait_one()
+    ref2 = engine.export_soa(P2)
+    for k, v in ref2.items():
+        assert np.array_equal(d2[k], v), k
+    engine.export_wait_one()                 # nothing outstanding: returns at once
+    engine.export_wait()
 
 
 def test_compact_edges_vs_oracle(engine, api, port, port_keys):

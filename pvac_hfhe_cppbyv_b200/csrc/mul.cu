@@ -17,6 +17,8 @@
 #include "engine.h"
 #include "sha256.cuh"
 
+#include <cstdlib>
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -43,7 +45,7 @@ __device__ __forceinline__ uint64_t next_bkt(const uint64_t* __restrict__ primes
 __global__ void mul_count_kernel(uint64_t n, const uint32_t* __restrict__ la, const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ea,
                                  const uint32_t* __restrict__ eb, const uint64_t* __restrict__ primes, int np, uint32_t* __restrict__ c_lpre,
                                  uint32_t* __restrict__ c_lp, uint32_t* __restrict__ c_keys, uint32_t* __restrict__ c_tbl, uint64_t* __restrict__ nb,
-                                 unsigned long long* __restrict__ max_pairs /*[0] max pairs, [1] sum keys, [2] sum table slots*/,
+                                 unsigned long long* __restrict__ max_pairs /*[0] max pairs, [1] sum keys, [2] sum table slots, [3] max keys*/,
                                  unsigned int* __restrict__ err) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -61,6 +63,7 @@ __global__ void mul_count_kernel(uint64_t n, const uint32_t* __restrict__ la, co
     atomicMax(max_pairs, (unsigned long long)pairs);
     atomicAdd(max_pairs + 1, (unsigned long long)keys);
     atomicAdd(max_pairs + 2, (unsigned long long)c_tbl[i]);
+    atomicMax(max_pairs + 3, (unsigned long long)keys);
 }
 
 // one CTA per pair
@@ -318,6 +321,43 @@ __global__ void mul_sortkey_kernel(uint32_t nkeys, const uint32_t* __restrict__ 
     sval[k] = k;
 }
 
+// The same order for batches whose ciphertext pairs have at most kBlockSortKeys keys each (fresh x fresh: 4 * 337 = 1 348): one
+// CTA per pair computes the keys and sorts them in shared memory (cub::BlockRadixSort, stable like the device-wide sort), so
+// the result is identical to sorting (item, key) globally -- without the 4-5 passes over all keys of the batch.
+constexpr int kBlockSortThreads = 256, kBlockSortItems = 8, kBlockSortKeys = kBlockSortThreads * kBlockSortItems;
+__global__ void __launch_bounds__(kBlockSortThreads)
+mul_sort_block_kernel(const uint32_t* __restrict__ koff, const uint32_t* __restrict__ toff, const uint64_t* __restrict__ nb, const uint32_t* __restrict__ k_tins,
+                      const unsigned long long* __restrict__ t_key, const uint32_t* __restrict__ t_val, int pbits, uint32_t* __restrict__ sval) {
+    using Sort = cub::BlockRadixSort<uint32_t, kBlockSortThreads, kBlockSortItems, uint32_t>;
+    __shared__ typename Sort::TempStorage tmp;
+    const uint32_t i = blockIdx.x;
+    const uint32_t k0 = koff[i], nk = koff[i + 1] - k0;
+    const uint32_t pmax = (1u << pbits) - 1;
+    const uint32_t size = toff[i + 1] - toff[i];
+    const uint64_t nbi = nb[i];
+    uint32_t key[kBlockSortItems], val[kBlockSortItems];
+#pragma unroll
+    for (int j = 0; j < kBlockSortItems; j++) {
+        const uint32_t rel = threadIdx.x * kBlockSortItems + j;          // blocked arrangement keeps the original order of equal keys
+        val[j] = k0 + rel;
+        if (rel >= nk) { key[j] = (1u << (2 * pbits)) | (pmax << pbits) | pmax; continue; }      // padding: after every real key
+        const uint32_t t = k_tins[k0 + rel];
+        if (t == kNone) { key[j] = (pmax << pbits) | pmax; continue; }
+        const uint64_t hk = ((uint64_t)(rel / kB) << 32) | (rel % kB);
+        const uint64_t bkt = (hk * 0x9E3779B97F4A7C15ull) % nbi;
+        uint32_t h = (uint32_t)(mix64(bkt) & (size - 1));
+        while (t_key[toff[i] + h] != bkt) h = (h + 1) & (size - 1);
+        const uint32_t tb = t_val[toff[i] + h];
+        key[j] = ((pmax - (tb + 1)) << pbits) | (pmax - (t + 1));
+    }
+    Sort(tmp).Sort(key, val, 0, 2 * pbits + 1);
+#pragma unroll
+    for (int j = 0; j < kBlockSortItems; j++) {
+        const uint32_t r = threadIdx.x * kBlockSortItems + j;
+        if (r < nk) sval[k0 + r] = val[j];
+    }
+}
+
 // per sorted position: number of edges emitted (P if ip && wp != 0, M if im && wm != 0; ops/arithmetic.hpp:96-101)
 __global__ void mul_emit_count_kernel(uint32_t nkeys, const uint32_t* __restrict__ sval, const uint8_t* __restrict__ k_flags, const Fp* __restrict__ k_wp,
                                       const Fp* __restrict__ k_wm, const uint32_t* __restrict__ k_tins, uint32_t* __restrict__ cnt) {
@@ -396,13 +436,13 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
     unsigned int* err;
     MUL_ALLOC(c_lpre, n * 4); MUL_ALLOC(c_lp, n * 4); MUL_ALLOC(c_keys, n * 4); MUL_ALLOC(c_tbl, n * 4);
     MUL_ALLOC(loP, (n + 1) * 4); MUL_ALLOC(lpoff, (n + 1) * 4); MUL_ALLOC(koff, (n + 1) * 4); MUL_ALLOC(toff, (n + 1) * 4);
-    MUL_ALLOC(nb, n * 8); MUL_ALLOC(max_pairs, 24); MUL_ALLOC(err, 4);
+    MUL_ALLOC(nb, n * 8); MUL_ALLOC(max_pairs, 32); MUL_ALLOC(err, 4);
     uint64_t* d_states = nullptr;
     if (h_states) {
         MUL_ALLOC(d_states, n * 8);
         PV_CUDA(cudaMemcpyAsync(d_states, h_states, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
-    PV_CUDA(cudaMemsetAsync(max_pairs, 0, 24, ctx->stream));
+    PV_CUDA(cudaMemsetAsync(max_pairs, 0, 32, ctx->stream));
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
     mul_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, A->loff, B->loff, A->eoff, B->eoff, ctx->d_primes, ctx->n_primes, c_lpre, c_lp,
                                                                            c_keys, c_tbl, nb, max_pairs, err);
@@ -410,12 +450,12 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
     if ((rc = scan_u32(ctx, n, c_lpre, loP)) || (rc = scan_u32(ctx, n, c_lp, lpoff)) || (rc = scan_u32(ctx, n, c_keys, koff)) ||
         (rc = scan_u32(ctx, n, c_tbl, toff))) { cleanup(); return rc; }
     uint32_t tot[4];
-    unsigned long long h_stats[3] = {0, 0, 0};
+    unsigned long long h_stats[4] = {0, 0, 0, 0};
     unsigned int h_err = 0;
     {
         SmallRead sr;
         sr.add(&tot[0], loP + n, 4); sr.add(&tot[1], lpoff + n, 4); sr.add(&tot[2], koff + n, 4); sr.add(&tot[3], toff + n, 4);
-        sr.add(h_stats, max_pairs, 24); sr.add(&h_err, err, 4);
+        sr.add(h_stats, max_pairs, 32); sr.add(&h_err, err, 4);
         if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
     }
     if (h_err) { cleanup(); ctx->last_error = "ct_mul: operand too large for the batched path (layer pairs / keys / edge pairs overflow)"; return PV_E_SHAPE; }
@@ -463,17 +503,25 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
         int ibits = 1;
         while ((1ull << ibits) < n) ibits++;
         if (2 * pbits + ibits > 64) { cleanup(); ctx->last_error = "ct_mul: sort key does not fit 64 bits (batch too large for these operand sizes)"; return PV_E_SHAPE; }
-        uint64_t *skey, *skey2; uint32_t *sval, *sval2, *ecnt, *epos;
-        MUL_ALLOC(skey, (size_t)nKeys * 8); MUL_ALLOC(skey2, (size_t)nKeys * 8); MUL_ALLOC(sval, (size_t)nKeys * 4); MUL_ALLOC(sval2, (size_t)nKeys * 4);
-        MUL_ALLOC(ecnt, (size_t)nKeys * 4); MUL_ALLOC(epos, (size_t)nKeys * 4);
-        mul_sortkey_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, koff, toff, nb, k_tins, k_item, t_key, t_val, pbits, skey, sval);
+        uint64_t *skey = nullptr, *skey2 = nullptr; uint32_t *sval = nullptr, *sval2, *ecnt, *epos;
+        MUL_ALLOC(sval2, (size_t)nKeys * 4); MUL_ALLOC(ecnt, (size_t)nKeys * 4); MUL_ALLOC(epos, (size_t)nKeys * 4);
         size_t tmp_bytes = 0, tmp2 = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, skey, skey2, sval, sval2, (int)nKeys, 0, 2 * pbits + ibits, ctx->stream);
         cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ecnt, epos, (int)nKeys, ctx->stream);
-        if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+        static const bool force_device_sort = getenv("PVACB_MUL_DEVICE_SORT") != nullptr;      // A/B switch for tuning runs and tests
+        const bool block_sort = !force_device_sort && h_stats[3] <= (unsigned long long)kBlockSortKeys && 2 * pbits + 1 <= 32;
         void* tmp;
-        MUL_ALLOC(tmp, tmp_bytes);
-        PV_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, skey, skey2, sval, sval2, (int)nKeys, 0, 2 * pbits + ibits, ctx->stream));
+        if (block_sort) {
+            tmp_bytes = tmp2;
+            MUL_ALLOC(tmp, tmp_bytes);
+            mul_sort_block_kernel<<<(unsigned)n, kBlockSortThreads, 0, ctx->stream>>>(koff, toff, nb, k_tins, t_key, t_val, pbits, sval2);
+        } else {
+            MUL_ALLOC(skey, (size_t)nKeys * 8); MUL_ALLOC(skey2, (size_t)nKeys * 8); MUL_ALLOC(sval, (size_t)nKeys * 4);
+            mul_sortkey_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, koff, toff, nb, k_tins, k_item, t_key, t_val, pbits, skey, sval);
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, skey, skey2, sval, sval2, (int)nKeys, 0, 2 * pbits + ibits, ctx->stream);
+            if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+            MUL_ALLOC(tmp, tmp_bytes);
+            PV_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, skey, skey2, sval, sval2, (int)nKeys, 0, 2 * pbits + ibits, ctx->stream));
+        }
         mul_emit_count_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, sval2, k_flags, k_wp, k_wm, k_tins, ecnt);
         PV_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ecnt, epos, (int)nKeys, ctx->stream));
         uint32_t last[2] = {0, 0};
@@ -483,7 +531,7 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
             if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
         }
         // pairs, bucket_insert, sortkey, emit_count + cub: radix sort (histogram, exclusive sum, one onesweep pass per 8 key bits) and scan (init + scan)
-        ctx->stat_kernel_launches += 4 + 2 + (uint64_t)((2 * pbits + ibits + 7) / 8) + 2;
+        ctx->stat_kernel_launches += block_sort ? 3 + 1 + 2 : 4 + 2 + (uint64_t)((2 * pbits + ibits + 7) / 8) + 2;
         if (h_err) {
             cleanup();
             if (h_err & 2) { ctx->last_error = "ct_mul: edge layer id out of range"; return PV_E_FORMAT; }

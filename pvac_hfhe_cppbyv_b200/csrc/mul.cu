@@ -11,6 +11,7 @@
 //                       output residue s accumulates sum_{ea} w_a * w_b[(s - idx_a) mod B] and the first insertion time
 //   mul_bucket_*        first-occupation time of every hash bucket (open-addressing table, atomicMin)
 //   radix sort          keys of each pair ordered by (bucket time desc, insertion time desc) = libstdc++ iteration order
+//                       (one CTA per pair in shared memory when a pair has <= 2048 keys, else one device-wide sort)
 //   mul_emit_*          P / M edges, salts from the tape in emission order
 //   sigma_run           one sigma_from_H per output edge (sigma.cu) -- > 99% of the time
 //   compact_layers_batch

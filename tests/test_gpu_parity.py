@@ -748,3 +748,32 @@ def test_wire_import_rejects_malformed_input(engine, api):
     assert rejected > 50 and accepted > 0
     # the context is still healthy afterwards
     assert engine.export_wire(engine.import_wire(good)) == good
+
+
+@pytest.mark.gpu
+def test_no_device_memory_growth(engine):
+    """steady-state loops do not leak device memory: after a few warm-up rounds the free memory reported by the driver stays
+    put while batches are created and freed (scratch and batches come from the stream-ordered pool and go back to it)"""
+    import torch
+    va = np.arange(1, 65, dtype=np.uint64)
+
+    def one_round(k):
+        A, B = engine.enc_value(va, 9100 + k), engine.enc_value(va[::-1].copy(), 9200 + k)
+        S = engine.ct_add(A, B)
+        P = engine.ct_mul(A, B, 9300 + k)
+        Q = engine.ct_sub(P, S)
+        d = engine.dec_value(Q)
+        assert (int(d[0][0]) | (int(d[0][1]) << 64)) == (1 * 64 - (1 + 64)) % ((1 << 127) - 1)
+        engine.commit_ct(Q)
+        for b in (A, B, S, P, Q):
+            b.free()
+
+    for k in range(6):
+        one_round(k)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for k in range(6, 40):
+        one_round(k)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, (free0, free1)

@@ -46,7 +46,7 @@ __device__ __forceinline__ uint64_t next_bkt(const uint64_t* __restrict__ primes
 __global__ void mul_count_kernel(uint64_t n, const uint32_t* __restrict__ la, const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ea,
                                  const uint32_t* __restrict__ eb, const uint64_t* __restrict__ primes, int np, uint32_t* __restrict__ c_lpre,
                                  uint32_t* __restrict__ c_lp, uint32_t* __restrict__ c_keys, uint32_t* __restrict__ c_tbl, uint64_t* __restrict__ nb,
-                                 unsigned long long* __restrict__ max_pairs /*[0] max pairs, [1] sum keys, [2] sum table slots, [3] max keys*/,
+                                 unsigned long long* __restrict__ max_pairs /*[0] max pairs, [1] sum keys, [2] sum table slots, [3] max keys, [4] max buckets*/,
                                  unsigned int* __restrict__ err) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -65,6 +65,7 @@ __global__ void mul_count_kernel(uint64_t n, const uint32_t* __restrict__ la, co
     atomicAdd(max_pairs + 1, (unsigned long long)keys);
     atomicAdd(max_pairs + 2, (unsigned long long)c_tbl[i]);
     atomicMax(max_pairs + 3, (unsigned long long)keys);
+    atomicMax(max_pairs + 4, (unsigned long long)nb[i]);
 }
 
 // one CTA per pair
@@ -326,30 +327,56 @@ __global__ void mul_sortkey_kernel(uint32_t nkeys, const uint32_t* __restrict__ 
 // CTA per pair computes the keys and sorts them in shared memory (cub::BlockRadixSort, stable like the device-wide sort), so
 // the result is identical to sorting (item, key) globally -- without the 4-5 passes over all keys of the batch.
 constexpr int kBlockSortThreads = 256, kBlockSortItems = 8, kBlockSortKeys = kBlockSortThreads * kBlockSortItems;
+constexpr uint32_t kSmemBuckets = 4096;     // SMEM_TABLE: the pair's bucket table (first-occupation time per bucket) lives in shared memory
+template <bool SMEM_TABLE>
 __global__ void __launch_bounds__(kBlockSortThreads)
 mul_sort_block_kernel(const uint32_t* __restrict__ koff, const uint32_t* __restrict__ toff, const uint64_t* __restrict__ nb, const uint32_t* __restrict__ k_tins,
-                      const unsigned long long* __restrict__ t_key, const uint32_t* __restrict__ t_val, int pbits, uint32_t* __restrict__ sval) {
+                      const unsigned long long* __restrict__ t_key, const uint32_t* __restrict__ t_val, int pbits, uint32_t* __restrict__ sval,
+                      uint32_t* __restrict__ k_item) {
     using Sort = cub::BlockRadixSort<uint32_t, kBlockSortThreads, kBlockSortItems, uint32_t>;
     __shared__ typename Sort::TempStorage tmp;
+    __shared__ uint32_t s_tb[SMEM_TABLE ? kSmemBuckets : 1];
     const uint32_t i = blockIdx.x;
     const uint32_t k0 = koff[i], nk = koff[i + 1] - k0;
     const uint32_t pmax = (1u << pbits) - 1;
-    const uint32_t size = toff[i + 1] - toff[i];
     const uint64_t nbi = nb[i];
-    uint32_t key[kBlockSortItems], val[kBlockSortItems];
+    uint32_t key[kBlockSortItems], val[kBlockSortItems], tin[kBlockSortItems], bk[kBlockSortItems];
+    if (SMEM_TABLE) {
+        for (uint32_t b = threadIdx.x; b < (uint32_t)nbi; b += kBlockSortThreads) s_tb[b] = kNone;
+        __syncthreads();
+    }
 #pragma unroll
     for (int j = 0; j < kBlockSortItems; j++) {
         const uint32_t rel = threadIdx.x * kBlockSortItems + j;          // blocked arrangement keeps the original order of equal keys
         val[j] = k0 + rel;
-        if (rel >= nk) { key[j] = (1u << (2 * pbits)) | (pmax << pbits) | pmax; continue; }      // padding: after every real key
-        const uint32_t t = k_tins[k0 + rel];
-        if (t == kNone) { key[j] = (pmax << pbits) | pmax; continue; }
+        tin[j] = kNone;
+        bk[j] = 0;
+        if (rel >= nk) continue;
+        if (SMEM_TABLE) k_item[k0 + rel] = i;
+        tin[j] = k_tins[k0 + rel];
+        if (tin[j] == kNone) continue;
         const uint64_t hk = ((uint64_t)(rel / kB) << 32) | (rel % kB);
-        const uint64_t bkt = (hk * 0x9E3779B97F4A7C15ull) % nbi;
-        uint32_t h = (uint32_t)(mix64(bkt) & (size - 1));
-        while (t_key[toff[i] + h] != bkt) h = (h + 1) & (size - 1);
-        const uint32_t tb = t_val[toff[i] + h];
-        key[j] = ((pmax - (tb + 1)) << pbits) | (pmax - (t + 1));
+        const uint64_t bkt = (hk * 0x9E3779B97F4A7C15ull) % nbi;         // struct H, ops/arithmetic.hpp:73
+        if (SMEM_TABLE) {
+            bk[j] = (uint32_t)bkt;
+            atomicMin(&s_tb[bk[j]], tin[j]);
+        } else {
+            const uint32_t size = toff[i + 1] - toff[i];
+            uint32_t h = (uint32_t)(mix64(bkt) & (size - 1));
+            while (t_key[toff[i] + h] != bkt) h = (h + 1) & (size - 1);
+            bk[j] = t_val[toff[i] + h];                                  // the bucket's first-occupation time itself
+        }
+    }
+    if (SMEM_TABLE) __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kBlockSortItems; j++) {
+        const uint32_t rel = threadIdx.x * kBlockSortItems + j;
+        if (rel >= nk) key[j] = (1u << (2 * pbits)) | (pmax << pbits) | pmax;          // padding: after every real key
+        else if (tin[j] == kNone) key[j] = (pmax << pbits) | pmax;
+        else {
+            const uint32_t tb = SMEM_TABLE ? s_tb[bk[j]] : bk[j];
+            key[j] = ((pmax - (tb + 1)) << pbits) | (pmax - (tin[j] + 1));
+        }
     }
     Sort(tmp).Sort(key, val, 0, 2 * pbits + 1);
 #pragma unroll
@@ -437,13 +464,13 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
     unsigned int* err;
     MUL_ALLOC(c_lpre, n * 4); MUL_ALLOC(c_lp, n * 4); MUL_ALLOC(c_keys, n * 4); MUL_ALLOC(c_tbl, n * 4);
     MUL_ALLOC(loP, (n + 1) * 4); MUL_ALLOC(lpoff, (n + 1) * 4); MUL_ALLOC(koff, (n + 1) * 4); MUL_ALLOC(toff, (n + 1) * 4);
-    MUL_ALLOC(nb, n * 8); MUL_ALLOC(max_pairs, 32); MUL_ALLOC(err, 4);
+    MUL_ALLOC(nb, n * 8); MUL_ALLOC(max_pairs, 40); MUL_ALLOC(err, 4);
     uint64_t* d_states = nullptr;
     if (h_states) {
         MUL_ALLOC(d_states, n * 8);
         PV_CUDA(cudaMemcpyAsync(d_states, h_states, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
-    PV_CUDA(cudaMemsetAsync(max_pairs, 0, 32, ctx->stream));
+    PV_CUDA(cudaMemsetAsync(max_pairs, 0, 40, ctx->stream));
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
     mul_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, A->loff, B->loff, A->eoff, B->eoff, ctx->d_primes, ctx->n_primes, c_lpre, c_lp,
                                                                            c_keys, c_tbl, nb, max_pairs, err);
@@ -451,12 +478,12 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
     if ((rc = scan_u32(ctx, n, c_lpre, loP)) || (rc = scan_u32(ctx, n, c_lp, lpoff)) || (rc = scan_u32(ctx, n, c_keys, koff)) ||
         (rc = scan_u32(ctx, n, c_tbl, toff))) { cleanup(); return rc; }
     uint32_t tot[4];
-    unsigned long long h_stats[4] = {0, 0, 0, 0};
+    unsigned long long h_stats[5] = {0, 0, 0, 0, 0};
     unsigned int h_err = 0;
     {
         SmallRead sr;
         sr.add(&tot[0], loP + n, 4); sr.add(&tot[1], lpoff + n, 4); sr.add(&tot[2], koff + n, 4); sr.add(&tot[3], toff + n, 4);
-        sr.add(h_stats, max_pairs, 32); sr.add(&h_err, err, 4);
+        sr.add(h_stats, max_pairs, 40); sr.add(&h_err, err, 4);
         if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
     }
     if (h_err) { cleanup(); ctx->last_error = "ct_mul: operand too large for the batched path (layer pairs / keys / edge pairs overflow)"; return PV_E_SHAPE; }
@@ -494,10 +521,7 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
         EdgeView VA{A->loff, A->eoff, A->idx, A->ch, A->w, lsA, lcA, ordA};
         EdgeView VB{B->loff, B->eoff, B->idx, B->ch, B->w, lsB, lcB, ordB};
         mul_pairs_kernel<<<nLP, kPairThreads, 0, ctx->stream>>>(VA, VB, lp_item, lpoff, koff, k_wp, k_wm, k_flags, k_tins, err);
-        PV_CUDA(cudaMemsetAsync(t_key, 0xFF, (size_t)(nTbl ? nTbl : 1) * 8, ctx->stream));
-        PV_CUDA(cudaMemsetAsync(t_val, 0xFF, (size_t)(nTbl ? nTbl : 1) * 4, ctx->stream));
         const unsigned kb = (nKeys + 255) / 256;
-        mul_bucket_insert_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, (uint32_t)n, koff, toff, nb, k_tins, k_item, t_key, t_val);
         // ---- libstdc++ iteration order by radix sort
         int pbits = 1;
         while ((1ull << pbits) - 1 < h_maxpairs + 1) pbits++;
@@ -508,13 +532,22 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
         MUL_ALLOC(sval2, (size_t)nKeys * 4); MUL_ALLOC(ecnt, (size_t)nKeys * 4); MUL_ALLOC(epos, (size_t)nKeys * 4);
         size_t tmp_bytes = 0, tmp2 = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ecnt, epos, (int)nKeys, ctx->stream);
-        static const bool force_device_sort = getenv("PVACB_MUL_DEVICE_SORT") != nullptr;      // A/B switch for tuning runs and tests
+        static const bool force_device_sort = getenv("PVACB_MUL_DEVICE_SORT") != nullptr;      // A/B switches for tuning runs and tests
+        static const bool force_global_table = getenv("PVACB_MUL_GLOBAL_TABLE") != nullptr;
         const bool block_sort = !force_device_sort && h_stats[3] <= (unsigned long long)kBlockSortKeys && 2 * pbits + 1 <= 32;
+        const bool smem_table = block_sort && !force_global_table && h_stats[4] <= (unsigned long long)kSmemBuckets;
+        if (!smem_table) {
+            // first-occupation time of every hash bucket in an open-addressing table in global memory
+            PV_CUDA(cudaMemsetAsync(t_key, 0xFF, (size_t)(nTbl ? nTbl : 1) * 8, ctx->stream));
+            PV_CUDA(cudaMemsetAsync(t_val, 0xFF, (size_t)(nTbl ? nTbl : 1) * 4, ctx->stream));
+            mul_bucket_insert_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, (uint32_t)n, koff, toff, nb, k_tins, k_item, t_key, t_val);
+        }
         void* tmp;
         if (block_sort) {
             tmp_bytes = tmp2;
             MUL_ALLOC(tmp, tmp_bytes);
-            mul_sort_block_kernel<<<(unsigned)n, kBlockSortThreads, 0, ctx->stream>>>(koff, toff, nb, k_tins, t_key, t_val, pbits, sval2);
+            if (smem_table) mul_sort_block_kernel<true><<<(unsigned)n, kBlockSortThreads, 0, ctx->stream>>>(koff, toff, nb, k_tins, t_key, t_val, pbits, sval2, k_item);
+            else mul_sort_block_kernel<false><<<(unsigned)n, kBlockSortThreads, 0, ctx->stream>>>(koff, toff, nb, k_tins, t_key, t_val, pbits, sval2, k_item);
         } else {
             MUL_ALLOC(skey, (size_t)nKeys * 8); MUL_ALLOC(skey2, (size_t)nKeys * 8); MUL_ALLOC(sval, (size_t)nKeys * 4);
             mul_sortkey_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, koff, toff, nb, k_tins, k_item, t_key, t_val, pbits, skey, sval);
@@ -531,8 +564,9 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
             sr.add(&last[0], epos + (nKeys - 1), 4); sr.add(&last[1], ecnt + (nKeys - 1), 4); sr.add(&h_err, err, 4);
             if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
         }
-        // pairs, bucket_insert, sortkey, emit_count + cub: radix sort (histogram, exclusive sum, one onesweep pass per 8 key bits) and scan (init + scan)
-        ctx->stat_kernel_launches += block_sort ? 3 + 1 + 2 : 4 + 2 + (uint64_t)((2 * pbits + ibits + 7) / 8) + 2;
+        // pairs, [bucket_insert], sort (block kernel, or sortkey + cub histogram, exclusive sum, one onesweep pass per 8 key bits), emit_count, cub scan (init + scan)
+        ctx->stat_kernel_launches += 1 /* pairs */ + (smem_table ? 0 : 1) /* bucket_insert */ + 1 /* emit_count */ + 2 /* cub scan */ +
+                                     (block_sort ? 1 : 1 + 2 + (uint64_t)((2 * pbits + ibits + 7) / 8)) /* block sort | sortkey + cub radix sort */;
         if (h_err) {
             cleanup();
             if (h_err & 2) { ctx->last_error = "ct_mul: edge layer id out of range"; return PV_E_FORMAT; }

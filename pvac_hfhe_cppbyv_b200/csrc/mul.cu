@@ -9,7 +9,8 @@
 //   mul_bylayer_kernel  edges of A and B grouped by layer (counting sort per ciphertext)
 //   mul_pairs_kernel    one CTA per (pair, la, lb): B's layer as a dense (idx, sign) table in shared memory, one thread per
 //                       output residue s accumulates sum_{ea} w_a * w_b[(s - idx_a) mod B] and the first insertion time
-//   mul_bucket_*        first-occupation time of every hash bucket (open-addressing table, atomicMin)
+//   mul_bucket_*        first-occupation time of every hash bucket (open-addressing table, atomicMin); for pairs with at most
+//                       4096 buckets the table lives in shared memory inside the sort kernel instead
 //   radix sort          keys of each pair ordered by (bucket time desc, insertion time desc) = libstdc++ iteration order
 //                       (one CTA per pair in shared memory when a pair has <= 2048 keys, else one device-wide sort)
 //   mul_emit_*          P / M edges, salts from the tape in emission order

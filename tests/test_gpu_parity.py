@@ -777,3 +777,21 @@ def test_no_device_memory_growth(engine):
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 64 << 20, (free0, free1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("switch", ["PVACB_MUL_DEVICE_SORT", "PVACB_MUL_GLOBAL_TABLE"])
+def test_mul_planning_fallback_paths(switch):
+    """ct_mul orders the keys of a ciphertext pair (libstdc++'s unordered_map iteration order) inside one CTA when the pair is small
+    -- keys and bucket table in shared memory -- and with a device-wide radix sort / a global bucket table otherwise. Fresh
+    operands never reach the fallbacks, so the golden / oracle ct_mul cases are run again with each fallback forced (the
+    switches are read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **{switch: "1"})
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k",
+                        "mul_golden or mul_chain_golden or mul_vs_oracle_batch or ct_fuzz_random_circuits"],
+                       capture_output=True, text=True, env=env, cwd=root, timeout=800)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout

@@ -529,7 +529,12 @@ def test_ct_fuzz_random_circuits(engine, api, port, port_keys):
     """tests/test_ct_fuzz.cpp on batches: random 3-6 step add / sub / mul chains (at most two multiplications) over a pool of
     encrypted values; each of the 16 lanes of a batch runs the same circuit on different plaintexts. Every decrypt equals the
     plain evaluation mod p; for one trial lane 0 is replayed on the oracle and compared bit for bit."""
-    rng = np.random.default_rng(20261018)
+    for extra in range(1 + int(os.environ.get("PVACB_FUZZ_EXTRA_SEEDS", "0"))):      # more seeds on demand (each ~10 s)
+        _fuzz_one_seed(engine, api, port, port_keys, 20261018 + extra)
+
+
+def _fuzz_one_seed(engine, api, port, port_keys, seed0):
+    rng = np.random.default_rng(seed0)
     lanes, K = 16, 6
     vals = rng.integers(0, 2**64, (K, lanes), dtype=np.uint64)
     enc = [engine.enc_value(vals[k], 9100 + k) for k in range(K)]

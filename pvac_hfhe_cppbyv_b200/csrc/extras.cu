@@ -61,7 +61,8 @@ __global__ void synth_sigma_kernel(uint64_t nwords, uint64_t seed, uint64_t* sig
 // matrix H with 128-bit loads) with nothing else around it. U = columns in flight per warp. The best bandwidth over a
 // few (U, CTAs/SM) shapes is used as the practical ceiling of the sigma kernel.
 // LD: 0 ld.global.cg (what the sigma kernel uses), 1 plain ld.global, 2 ld.global.nc, 3 ld.global.cs, 4 one 256-bit ld.global.cg per
-// lane and column instead of two 128-bit ones  (PVACB_PROBE_LD; 5 = the 256-bit form with 4 columns in flight)
+// lane and column instead of two 128-bit ones  (PVACB_PROBE_LD; 5 = the 256-bit form with 4 columns in flight; 6 / 7 / 8 = the TMA
+// form below with 4 / 8 / 16 KiB in flight per warp)
 template <int LD>
 __device__ __forceinline__ uint4 probe_load(const uint4* p) {
     if (LD == 1) return *p;
@@ -104,6 +105,54 @@ __global__ void __launch_bounds__(256) l2_gather_probe_kernel(const uint4* __res
     }
     a0.x ^= a1.x; a0.y ^= a1.y; a0.z ^= a1.z; a0.w ^= a1.w;
     if ((a0.x ^ a0.y ^ a0.z ^ a0.w) == 0x9E3779B9u && cols_per_warp == 0xFFFFFFFFu) sink[w] = a0;   // keeps the loads alive
+}
+
+// The same gather through the TMA engine: every column is one 1 KiB bulk copy (cp.async.bulk, global -> shared memory, completion on an
+// mbarrier) into a per-warp ring of R slots, then two 128-bit shared-memory loads per lane and the XORs. Measures whether staging
+// the columns through shared memory moves the ceiling (it does not: profiles/r01_notes.md).
+template <int R>
+__global__ void __launch_bounds__(256) l2_gather_probe_tma_kernel(const uint4* __restrict__ H4, uint32_t cols_per_warp, uint4* __restrict__ sink) {
+    extern __shared__ __align__(128) unsigned char probe_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* ring = reinterpret_cast<uint4*>(probe_smem) + (size_t)warp * R * 64;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(probe_smem + (size_t)8 * R * 1024) + warp * R;
+    auto s32 = [](const void* q) { return (uint32_t)__cvta_generic_to_shared(q); };
+    if (lane == 0)
+        for (int r = 0; r < R; r++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bars[r])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t state = w * 2654435761u + 12345u;
+    auto issue = [&](int slot) {
+        state = state * 1664525u + 1013904223u;
+        const uint32_t col = (state >> 10) & (kNBits - 1);
+        const uint32_t bar = s32(&bars[slot]), dst = s32(ring + slot * 64);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 1024;" ::"r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 1024, [%2];" ::"r"(dst),
+                     "l"(H4 + (size_t)col * 64), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0)
+        for (int r = 0; r < R; r++) issue(r);
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    for (uint32_t i = 0; i < cols_per_warp; i++) {
+        const int slot = i % R;
+        const uint32_t parity = (i / R) & 1, bar = s32(&bars[slot]);
+        uint32_t ok = 0;
+        do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        } while (!ok);
+        const uint4 v0 = ring[slot * 64 + lane], v1 = ring[slot * 64 + 32 + lane];
+        a0.x ^= v0.x; a0.y ^= v0.y; a0.z ^= v0.z; a0.w ^= v0.w;
+        a1.x ^= v1.x; a1.y ^= v1.y; a1.z ^= v1.z; a1.w ^= v1.w;
+        __syncwarp();
+        if (lane == 0 && i + R < cols_per_warp) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the slot was read through the generic proxy
+            issue(slot);
+        }
+    }
+    a0.x ^= a1.x; a0.y ^= a1.y; a0.z ^= a1.z; a0.w ^= a1.w;
+    if ((a0.x ^ a0.y ^ a0.z ^ a0.w) == 0x9E3779B9u && cols_per_warp == 0xFFFFFFFFu) sink[w] = a0;
 }
 
 // order-independent checksums of a whole batch (parity checks at sizes that cannot be exported):
@@ -276,6 +325,8 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
         cudaFuncSetAttribute(l2_gather_probe_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(l2_gather_probe_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
+    cudaFuncSetAttribute(l2_gather_probe_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * 1024 + 8 * 8 * 8);
+    cudaFuncSetAttribute(l2_gather_probe_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16 * 1024 + 8 * 16 * 8);
     if (probe_smem > 48 * 1024) {
         cudaFuncSetAttribute(l2_gather_probe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, probe_smem);
         cudaFuncSetAttribute(l2_gather_probe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, probe_smem);
@@ -295,6 +346,9 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
             else if (ld == 3) l2_gather_probe_kernel<8, 3><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (ld == 4) l2_gather_probe_kernel<8, 4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (ld == 5) l2_gather_probe_kernel<4, 4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (ld == 6) l2_gather_probe_tma_kernel<4><<<grid, 256, 8 * 4 * 1024 + 8 * 4 * 8, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (ld == 7) l2_gather_probe_tma_kernel<8><<<grid, 256, 8 * 8 * 1024 + 8 * 8 * 8, ctx->stream>>>(H4, cols_per_warp, sink);
+            else if (ld == 8) l2_gather_probe_tma_kernel<16><<<grid, 256, 8 * 16 * 1024 + 8 * 16 * 8, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (shape / 2 == 0 && (sh & 1) == 0 && sh < 6) l2_gather_probe_kernel<4, 0, 4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (shape / 2 == 0) l2_gather_probe_kernel<4><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (shape / 2 == 1) l2_gather_probe_kernel<8><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);

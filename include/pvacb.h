@@ -10,11 +10,19 @@
  * returns a new batch that the caller frees with pvacb_batch_free; where the reference calls std::abort() the batched
  * call returns a non-zero status instead (pvacb_last_error gives text). A context is single-caller (one host thread).
  *
- * RNG tape. The reference draws 64-bit words from the OS CSPRNG with no seed hook (core/random.hpp:106-110). Here the
- * caller passes a 64-bit batch_seed; item i of a batch consumes the SplitMix64 stream
- *     state0 = mix64(batch_seed + 0xD1342543DE82EF95 * (i + 1)),  word k = mix64(state0 + (k + 1) * 0x9E3779B97F4A7C15)
- * in exactly the order the reference would call csprng_u64() for that item. With the same words the outputs are
- * bit-identical to the reference (compiled with g++ 13 / libstdc++), including edge order.
+ * RNG tape. The reference draws 64-bit words from the OS CSPRNG with no seed hook (core/random.hpp:106-110). Here every item
+ * of a call consumes its own word stream in exactly the order the reference would call csprng_u64() for that item; with the
+ * same words the outputs are bit-identical to the reference (compiled with g++ 13 / libstdc++), including edge order.
+ * The stream of item i (global index = item base + i) under the three tape kinds of a context (pvacb_set_tape):
+ *   PVACB_TAPE_CHACHA20 (default; key = 256 bits from getrandom() at pvacb_ctx_create, or given by the caller):
+ *       word k = little-endian 64-bit word (k mod 8) of ChaCha20 block (k div 8), block input words 12..15 =
+ *       (block index, lane, stream id lo, stream id hi); from a batch_seed: stream id = batch_seed, lane = global index + 1;
+ *       from an explicit per-item tape_states[i]: stream id = tape_states[i], lane = 0. Only keystream ever reaches a ciphertext.
+ *       NEVER use one (key, batch_seed) or one (key, tape state) twice: pvacb_fresh_seed hands out seeds that do not repeat.
+ *   PVACB_TAPE_SPLITMIX (parity tests and the committed golden vectors ONLY -- not secret-keeping: the generator is an unkeyed
+ *       bijection of a 64-bit state and tape words are published as nonces):
+ *       state0 = tape_states[i] or mix64(batch_seed + 0xD1342543DE82EF95 * (global index + 1)), word k = mix64(state0 + (k + 1) * 0x9E3779B97F4A7C15)
+ *   PVACB_TAPE_WORDS: the caller supplies every word (pvacb_set_tape_words), e.g. straight from its own CSPRNG.
  */
 #ifndef PVACB_H
 #define PVACB_H
@@ -37,8 +45,8 @@ enum {
     PVACB_E_NOKEYS = 4,
     PVACB_E_EDGE_BUDGET = 5, /* reserved (results over Params::edge_budget are compacted like the reference's guard_budget does) */
     PVACB_E_LAYER_GRAPH = 6, /* reference: std::abort() in layer_R_cached (ops/decrypt.hpp:23,36) */
-    PVACB_E_RARE_PATH = 7,   /* AesCtr256::bounded rejected a word (p = 2^-61 per LPN row, crypto/lpn.hpp:141-148) */
-    PVACB_E_DUP_EDGE = 8,    /* ct_mul input with two edges of equal (layer, idx, sign) */
+    PVACB_E_RESERVED7 = 7,   /* (round 1: rare rejection branches; both now run on the device) */
+    PVACB_E_RESERVED8 = 8,   /* (round 1: ct_mul operands with repeated (layer, idx, sign); now summed like the reference does) */
     PVACB_E_FORMAT = 9,
     PVACB_E_SHAPE = 10
 };
@@ -52,7 +60,25 @@ enum { PVACB_PRF_FAITHFUL = 0, PVACB_PRF_LIVE = 1 };
 #define PVACB_M_WORDS 128      /* sigma: m_bits/64 */
 #define PVACB_N_COLS 16384     /* columns of H */
 #define PVACB_LPN_WORDS 64
-#define PVACB_KEY_BLOB_BYTES ((size_t)(748 + 16384 * 128) * 8)
+#define PVACB_KEY_BLOB_BYTES ((size_t)(752 + 16384 * 128) * 8)
+
+/* RNG tape kinds (see the header comment) */
+enum { PVACB_TAPE_SPLITMIX = 0, PVACB_TAPE_CHACHA20 = 1, PVACB_TAPE_WORDS = 2 };
+
+/* struct Params, core/types.hpp:36-70, field for field. The kernels are built for the shapes of the default set: B, m_bits, n_bits,
+ * h_col_wt, x_col_wt, err_wt, lpn_n and lpn_tau must keep their defaults (anything else is refused with PVACB_E_ARG and a
+ * message naming the field); noise_entropy_bits, tuple2_fraction, depth_slope_bits, edge_budget (4096..2^32-1), lpn_t (127..16384:
+ * every value in that range gives identical ciphertexts, 16384 evaluates all rows like the reference, less evaluates the live
+ * rows) and the recrypt fields (which the reference never reads either) are run-time values. */
+typedef struct pvacb_params {
+    int32_t B, m_bits, n_bits, h_col_wt, x_col_wt, err_wt;
+    double noise_entropy_bits, tuple2_fraction, depth_slope_bits;
+    uint64_t edge_budget;
+    int32_t lpn_n, lpn_t, lpn_tau_num, lpn_tau_den;
+    double recrypt_lo, recrypt_hi;
+    int32_t recrypt_rounds;
+} pvacb_params;
+void pvacb_params_default(pvacb_params* p);
 
 /* ---- context ------------------------------------------------------------------------------------------------- */
 int pvacb_ctx_create(int device, pvacb_ctx** out);
@@ -65,16 +91,43 @@ int pvacb_sync(pvacb_ctx* ctx);
 /* counters since the last reset: kernels launched, AES-256 blocks computed, sigma_from_H evaluations */
 void pvacb_stats(const pvacb_ctx* ctx, uint64_t* kernel_launches, uint64_t* aes_blocks, uint64_t* sigma_edges);
 void pvacb_stats_reset(pvacb_ctx* ctx);
-/* optional per-kernel timing with CUDA events on the context's stream. Tags: 0 prf_lpn, 1 unused, 2 sigma (fused sigma_from_H kernel),
- * 3 concat (ct_add/ct_sub), 4 dec_edges, 5 mul planning. collect() synchronises, sums ms and launch counts per tag. */
+/* RNG tape of the context. key: 32 bytes for PVACB_TAPE_CHACHA20 (NULL = fresh from the OS CSPRNG), ignored otherwise. */
+int pvacb_set_tape(pvacb_ctx* ctx, int kind, const uint8_t key[32]);
+int pvacb_get_tape(const pvacb_ctx* ctx);
+/* PVACB_TAPE_WORDS: words[(global item index) * words_per_item + k] is word k of that item. A call that needs more words than
+ * supplied fails with PVACB_E_ARG (an enc_value item draws about 214, a ct_mul item 2 per new layer + 1 per output edge). */
+int pvacb_set_tape_words(pvacb_ctx* ctx, const uint64_t* words, size_t n_items, size_t words_per_item);
+/* global index of item 0 of the following calls (default 0): a shard of a larger batch keeps the streams of the whole batch, so
+ * an N-GPU run returns the same bytes as a 1-GPU run */
+int pvacb_set_item_base(pvacb_ctx* ctx, uint64_t base);
+/* a batch_seed this context has not handed out before (a counter): for callers that have no use for reproducible seeds */
+uint64_t pvacb_fresh_seed(pvacb_ctx* ctx);
+/* test hooks, all bit-exact: what = 0: ct_mul planning takes the device-wide sort (a = 1) / the global bucket table (b = 1) even
+ * for small pairs; what = 1: keystream word a of every PRF core is OR-ed with b (a = ~0: off), which reaches the rejection branch
+ * of AesCtr256::bounded (crypto/lpn.hpp:141-148); what = 2: sigma kernel shape without spare PRG candidates (a = 1) */
+int pvacb_debug_set(pvacb_ctx* ctx, int what, uint64_t a, uint64_t b);
+/* optional per-kernel timing with CUDA events on the context's stream. Tags: 0 prf_lpn, 1 mul_pairs (weight products of ct_mul),
+ * 2 sigma (fused sigma_from_H kernel), 3 concat (ct_add/ct_sub), 4 dec_edges, 5 commit, 6 compact_edges sort + merge. collect() synchronises,
+ * sums ms and launch counts per tag. */
 int pvacb_profile_enable(pvacb_ctx* ctx, int on);
 /* microbenchmark: achieved GB/s of warp-wide 1 KiB gathers from the L2-resident matrix H (ceiling of the sigma kernel) */
 int pvacb_l2_gather_probe(pvacb_ctx* ctx, int reps, double* gbps_out);
 int pvacb_profile_collect(pvacb_ctx* ctx, float ms_out[8], uint32_t launches_out[8]);
 
 /* ---- keys: replaces keygen(const Params&, PubKey&, SecKey&), crypto/keygen.hpp:35 ---------------------------------- */
-/* keygen with default Params; consumes the tape stream with initial state `tape_state` exactly like the reference. */
+/* keygen(prm, pk, sk): prm == NULL means the default Params; every word comes from ChaCha20 keyed by seed[32] (NULL = 32 fresh
+ * bytes from the OS CSPRNG) in the reference's draw order. The run-time Params fields become those of the context. */
+int pvacb_keygen_params(pvacb_ctx* ctx, const pvacb_params* prm, const uint8_t seed[32]);
+int pvacb_set_params(pvacb_ctx* ctx, const pvacb_params* prm);     /* for keys that were imported as raw arrays */
+int pvacb_get_params(const pvacb_ctx* ctx, pvacb_params* prm);
+/* PARITY / TEST ONLY: keygen with default Params from the SplitMix64 stream of a 64-bit state (the committed golden keys). */
 int pvacb_keygen(pvacb_ctx* ctx, uint64_t tape_state);
+/* the reference's key files (savePk / loadPk / saveSk / loadSk, tests/bounty2_test.cpp:145-236; magics 0x06660666 / 0x66666999),
+ * byte for byte. Either path may be NULL on export; on import sk_path == NULL gives a public-key-only context (ct_add / ct_sub /
+ * ct_mul / commit_ct / ct_recrypt work, enc_* and dec_* return PVACB_E_NOKEYS). The Params stored in the pk file are checked like
+ * pvacb_keygen_params checks them, and ubk.perm / ubk.inv must be the permutation canon_tag derives. */
+int pvacb_keys_export_file(pvacb_ctx* ctx, const char* pk_path, const char* sk_path);
+int pvacb_keys_import_file(pvacb_ctx* ctx, const char* pk_path, const char* sk_path);
 /* PubKey/SecKey fields as raw arrays (core/types.hpp:121-134): H[16384][128], powg_B[337][2] (lo,hi), prf_k[4], lpn_s[64] */
 int pvacb_keys_import_raw(pvacb_ctx* ctx, uint64_t canon_tag, const uint8_t h_digest[32], const uint64_t* H,
                           const uint64_t* powg_B, const uint64_t prf_k[4], const uint64_t* lpn_s);
@@ -96,7 +149,7 @@ int pvacb_enc_value(pvacb_ctx* ctx, const uint64_t* values, size_t n, uint64_t b
  * tape_states == NULL falls back to the batch_seed derivation above. */
 int pvacb_enc_value_ex(pvacb_ctx* ctx, const uint64_t* values, size_t n, uint64_t batch_seed, const uint64_t* tape_states,
                        pvacb_batch** out);
-/* Cipher enc_value_depth(pk, sk, v, depth_hint)            ops/encrypt.hpp:281  (plan_noise(depth_hint) noise groups; depth_hint 0..23)
+/* Cipher enc_value_depth(pk, sk, v, depth_hint)            ops/encrypt.hpp:281  (plan_noise(depth_hint) noise groups; any depth_hint >= 0)
  * Cipher enc_zero_depth(pk, sk, depth_hint)                ops/encrypt.hpp:293  (identical draws to enc_value_depth(0, depth_hint)) */
 int pvacb_enc_value_depth(pvacb_ctx* ctx, const uint64_t* values, size_t n, int depth_hint, uint64_t batch_seed, const uint64_t* tape_states,
                           pvacb_batch** out);
@@ -104,7 +157,7 @@ int pvacb_enc_zero_depth(pvacb_ctx* ctx, size_t n, int depth_hint, uint64_t batc
 /* Cipher enc_fp_depth(pk, sk, Fp v, depth_hint)             ops/encrypt.hpp:162  (one share: 1 BASE layer; fp_values = n x (lo, hi), canonical) */
 int pvacb_enc_fp_depth(pvacb_ctx* ctx, const uint64_t* fp_values, size_t n, int depth_hint, uint64_t batch_seed, const uint64_t* tape_states,
                        pvacb_batch** out);
-/* std::pair<int,int> plan_noise(pk, depth_hint)            ops/encrypt.hpp:16 */
+/* std::pair<int,int> plan_noise(pk, depth_hint)            ops/encrypt.hpp:16  (default Params) */
 int pvacb_plan_noise(int depth_hint, int* z2, int* z3);
 /* Cipher ct_add / ct_sub(pk, A, B)                        ops/arithmetic.hpp:12,43 */
 int pvacb_ct_add(pvacb_ctx* ctx, const pvacb_batch* a, const pvacb_batch* b, pvacb_batch** out);
@@ -128,7 +181,7 @@ int pvacb_dec_value(pvacb_ctx* ctx, const pvacb_batch* c, uint64_t* out);
 int pvacb_commit_ct(pvacb_ctx* ctx, const pvacb_batch* c, uint8_t* out);
 
 /* std::vector<Cipher> enc_text(pk, sk, msg) / std::string dec_text(pk, sk, cts)     utils/text.hpp:39,63
- * for n messages at once: bytes = all messages back to back, msg_off[n+1] their byte ranges (<= 330 bytes each). Message m
+ * for n messages at once: bytes = all messages back to back, msg_off[n+1] their byte ranges (any length: block j is encrypted with depth_hint 2 + j like the reference does). Message m
  * draws from ONE tape stream (tape_states[m] or the batch_seed derivation) exactly like the reference: enc_value(length), then
  * enc_fp_depth(15-byte block j, depth_hint 2 + j). The result batch is WAVE-MAJOR: the n length ciphertexts in message
  * order, then block 0 of every message that has one (message order), then block 1, ... pvacb_dec_text expects that order. */
@@ -184,6 +237,19 @@ int pvacb_batch_import_soa(pvacb_ctx* ctx, size_t n, const uint32_t* layer_off, 
                            const uint32_t* pb, const uint32_t* layer_id, const uint16_t* idx, const uint8_t* ch,
                            const uint64_t* w, const uint64_t* sigma, pvacb_batch** out);
 
+/* the whole device image of a batch with ONE copy (a batch is one allocation; the 13 arrays above sit at the offsets
+ * pvacb_blob_layout gives for the counts of pvacb_batch_blob_info: off[0..12] = layer_off, edge_off, rule, ztag, nonce_lo,
+ * nonce_hi, pa, pb, layer_id, idx, ch, w, sigma; off[13] = image size). Asynchronous like pvacb_batch_export_soa_async
+ * (pvacb_export_wait / _wait_one); `host` should be pinned. */
+int pvacb_blob_layout(uint64_t n, uint64_t n_layers, uint64_t n_edges, uint64_t off[14]);
+int pvacb_batch_blob_info(const pvacb_batch* b, uint64_t* n, uint64_t* layout_layers, uint64_t* layout_edges, uint64_t* bytes);
+int pvacb_batch_export_blob_async(pvacb_ctx* ctx, const pvacb_batch* b, void* host, size_t cap);
+int pvacb_batch_import_blob(pvacb_ctx* ctx, size_t n, uint64_t layout_layers, uint64_t layout_edges, const void* host, size_t bytes, pvacb_batch** out);
+/* Route the blob exports of this context through ANOTHER GPU's host link: the image crosses NVLink into a staging buffer on
+ * relay_device and leaves from there (-1 = direct, the default). For boxes whose GPUs do not all reach host memory equally fast
+ * (profiles/r02_hostlink_probe.txt: four of eight GPUs share 70 GB/s while the other four reach 176 GB/s together). */
+int pvacb_set_export_relay(pvacb_ctx* ctx, int relay_device);
+
 /* the reference's on-disk ciphertext format (tests/bounty2_test.cpp:17-143: magic 0x66699666, ver 1, u64 count, then per
  * cipher u32 nL, u32 nE, layers, edges). PROD-layer seeds are not part of that format. */
 int pvacb_batch_wire_size(pvacb_ctx* ctx, const pvacb_batch* b, size_t* bytes);
@@ -193,6 +259,37 @@ int pvacb_batch_import_wire(pvacb_ctx* ctx, const void* buf, size_t bytes, pvacb
 /* synthetic fresh-shaped ciphertexts for benchmarks: 2 BASE layers, edges_per_layer edges each,
  * uniform idx/ch/w/sigma from batch_seed. Not decryptable; exercises the bandwidth-bound ops. */
 int pvacb_batch_synthetic(pvacb_ctx* ctx, size_t n, int edges_per_layer, uint64_t batch_seed, pvacb_batch** out);
+
+/* ---- several GPUs of one box: N contexts of this process, one per device, one host thread per device while a
+ * call runs. A batch is split into contiguous index ranges (item i -> member floor(i N / n)); every item keeps the RNG stream of
+ * its GLOBAL index, so the result bytes do not depend on N; keys are replicated once by peer copies over NVLink; there is no
+ * collective in the steady state. The reference has no counterpart (it is single-threaded); semantics per item are those of the
+ * single-device calls above. */
+typedef struct pvacb_group pvacb_group;
+typedef struct pvacb_gbatch pvacb_gbatch;   /* a batch sharded over the members */
+int pvacb_group_create(const int* devices, int n, pvacb_group** out);     /* one ChaCha20 tape key (from the OS) shared by all members */
+void pvacb_group_destroy(pvacb_group* g);
+int pvacb_group_size(const pvacb_group* g);
+pvacb_ctx* pvacb_group_ctx(pvacb_group* g, int member);                   /* e.g. for pvacb_set_prf_mode / pvacb_stats per device */
+const char* pvacb_group_last_error(const pvacb_group* g);
+int pvacb_group_keygen_params(pvacb_group* g, const pvacb_params* prm, const uint8_t seed[32]);   /* keygen on member 0, then replicate */
+int pvacb_group_keys_import_file(pvacb_group* g, const char* pk_path, const char* sk_path);
+int pvacb_group_replicate_keys(pvacb_group* g);                           /* member 0's keys (however they got there) -> all members */
+int pvacb_group_set_tape(pvacb_group* g, int kind, const uint8_t key[32]);
+int pvacb_group_enc_value(pvacb_group* g, const uint64_t* values, size_t n, uint64_t batch_seed, pvacb_gbatch** out);
+int pvacb_group_ct_add(pvacb_group* g, const pvacb_gbatch* a, const pvacb_gbatch* b, pvacb_gbatch** out);
+int pvacb_group_ct_sub(pvacb_group* g, const pvacb_gbatch* a, const pvacb_gbatch* b, pvacb_gbatch** out);
+int pvacb_group_ct_mul(pvacb_group* g, const pvacb_gbatch* a, const pvacb_gbatch* b, uint64_t batch_seed, pvacb_gbatch** out);
+int pvacb_group_dec_value(pvacb_group* g, const pvacb_gbatch* c, uint64_t* out /* n x (lo,hi), global order */);
+int pvacb_group_commit_ct(pvacb_group* g, const pvacb_gbatch* c, uint8_t* out /* n x 32, global order */);
+void pvacb_group_batch_free(pvacb_gbatch* b);
+size_t pvacb_group_batch_count(const pvacb_gbatch* b);
+pvacb_batch* pvacb_group_batch_part(pvacb_gbatch* b, int member);         /* the member's slice (owned by the gbatch) */
+/* every member exports the image of its slice into host_bufs[member] (pinned) at the same time; returns when all are complete */
+int pvacb_group_export_blobs(pvacb_group* g, const pvacb_gbatch* c, void* const* host_bufs, const size_t* caps);
+/* measures the simultaneous export bandwidth of the members (GB/s), direct and -- if their host links are unequal -- with the
+ * slower half relayed through the faster half over NVLink; keeps the better routing for later exports */
+int pvacb_group_tune_export(pvacb_group* g, double* direct_gbs, double* relay_gbs);
 
 /* ---- building blocks exposed for parity tests (device kernels, not CPU code) ------------------------------------- */
 /* prf_R (family 0) / prf_R_noise (family 1) of n seeds, crypto/lpn.hpp:263-275. ybits (optional) receives every

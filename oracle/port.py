@@ -40,6 +40,11 @@ def lib():
     sig = {
         "orc_item_stream_state": (u64, [u64, u64]),
         "orc_tape_word": (u64, [P(u64)]),
+        "orc_set_tape": (None, [i32, P(u8)]),
+        "orc_set_tape_lane": (None, [u32]),
+        "orc_set_tape_words": (None, [P(u64), u64]),
+        "orc_set_prf_patch": (None, [u64, u64]),
+        "orc_chacha20_block": (None, [P(u32), P(u32), P(u32)]),
         "orc_keygen": (vp, [u64]),
         "orc_keys_from_raw": (vp, [u64, P(u8), P(u64), P(u64), P(u64), P(u64)]),
         "orc_keys_free": (None, [vp]),
@@ -98,6 +103,30 @@ def lib():
 
 
 _last_draws = 0
+_tape_words_keep = None
+
+
+def set_tape(kind, key=None, lane=0, words=None):
+    """tape kind of the oracle (process-wide): 0 SplitMix64 (default), 1 ChaCha20 under key (32 bytes) with `lane`, 2 explicit words.
+    The tape_state argument of enc_* / ct_mul / ... is the SplitMix state resp. the ChaCha20 stream id."""
+    global _tape_words_keep
+    k = np.frombuffer(bytes(key), np.uint8).copy() if key is not None else None
+    lib().orc_set_tape(kind, _p(k, C.c_uint8) if k is not None else None)
+    lib().orc_set_tape_lane(lane)
+    if words is not None:
+        _tape_words_keep = np.ascontiguousarray(words, np.uint64)
+        lib().orc_set_tape_words(_p(_tape_words_keep, C.c_uint64), len(_tape_words_keep))
+
+
+def set_prf_patch(word=2**64 - 1, or_mask=0):
+    """test hook: keystream word `word` of every LPN stream is OR-ed with or_mask (word = 2^64-1: off)"""
+    lib().orc_set_prf_patch(word, or_mask)
+
+
+def chacha20_block(key_words, c4):
+    k, c, o = np.asarray(key_words, np.uint32), np.asarray(c4, np.uint32), np.zeros(16, np.uint32)
+    lib().orc_chacha20_block(_p(k, C.c_uint32), _p(c, C.c_uint32), _p(o, C.c_uint32))
+    return o
 
 
 def tape_draws():

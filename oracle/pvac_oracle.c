@@ -46,11 +46,44 @@ static uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
+/* Tape kinds (same definitions as pvac_hfhe_cppbyv_b200/csrc/common.cuh): 0 SplitMix64 of a 64-bit state; 1 ChaCha20 -- word k =
+ * 64-bit little-endian word (k mod 8) of block (k div 8) under a 256-bit key, block input words 12..15 = (block index, lane,
+ * stream id lo, stream id hi), the stream id being the `tape_state` argument of the entry points below; 2 explicit words.
+ * The kind, key, lane and words are process-wide settings of this test library (orc_set_tape / _lane / _words). */
+static int g_tape_kind = 0;
+static uint32_t g_tape_key[8];
+static uint32_t g_tape_lane = 0;
+static const uint64_t* g_tape_words = 0;
+static uint64_t g_tape_nwords = 0;
+void orc_set_tape(int kind, const uint8_t* key32) {
+    g_tape_kind = kind;
+    if (key32) for (int i = 0; i < 8; i++) g_tape_key[i] = (uint32_t)key32[4 * i] | ((uint32_t)key32[4 * i + 1] << 8) | ((uint32_t)key32[4 * i + 2] << 16) | ((uint32_t)key32[4 * i + 3] << 24);
+}
+void orc_set_tape_lane(uint32_t lane) { g_tape_lane = lane; }
+void orc_set_tape_words(const uint64_t* words, uint64_t n) { g_tape_words = words; g_tape_nwords = n; }
+static uint32_t rotl32c(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+#define ORC_QR(a, b, c, d) a += b; d ^= a; d = rotl32c(d, 16); c += d; b ^= c; b = rotl32c(b, 12); a += b; d ^= a; d = rotl32c(d, 8); c += d; b ^= c; b = rotl32c(b, 7);
+/* the ChaCha20 block function (D. J. Bernstein; RFC 8439 section 2.3): 20 rounds over constants | key | words 12..15 */
+void orc_chacha20_block(const uint32_t key[8], const uint32_t c[4], uint32_t out[16]) {
+    uint32_t in[16] = { 0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7], c[0], c[1], c[2], c[3] };
+    uint32_t x[16];
+    memcpy(x, in, sizeof x);
+    for (int r = 0; r < 10; r++) {
+        ORC_QR(x[0], x[4], x[8], x[12]) ORC_QR(x[1], x[5], x[9], x[13]) ORC_QR(x[2], x[6], x[10], x[14]) ORC_QR(x[3], x[7], x[11], x[15])
+        ORC_QR(x[0], x[5], x[10], x[15]) ORC_QR(x[1], x[6], x[11], x[12]) ORC_QR(x[2], x[7], x[8], x[13]) ORC_QR(x[3], x[4], x[9], x[14])
+    }
+    for (int i = 0; i < 16; i++) out[i] = x[i] + in[i];
+}
 typedef struct { uint64_t state; uint64_t draws; } tape_t;
 static uint64_t tape_u64(tape_t* t) {
-    t->state += 0x9E3779B97F4A7C15ull;
-    t->draws++;
-    return mix64(t->state);
+    const uint64_t k = t->draws++;
+    if (g_tape_kind == 1) {
+        uint32_t c[4] = { (uint32_t)(k >> 3), g_tape_lane ^ (uint32_t)((k >> 3) >> 32), (uint32_t)t->state, (uint32_t)(t->state >> 32) }, o[16];
+        orc_chacha20_block(g_tape_key, c, o);
+        return (uint64_t)o[2 * (k & 7)] | ((uint64_t)o[2 * (k & 7) + 1] << 32);
+    }
+    if (g_tape_kind == 2) return k < g_tape_nwords ? g_tape_words[k] : 0;
+    return mix64(t->state + (k + 1) * 0x9E3779B97F4A7C15ull);
 }
 uint64_t orc_item_stream_state(uint64_t batch_seed, uint64_t item) {
     return mix64(batch_seed + 0xD1342543DE82EF95ull * (item + 1));
@@ -223,7 +256,11 @@ static void aes_tables(void) {
     aes_ready = 1;
 }
 static uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
-typedef struct { uint32_t rk[60]; uint64_t ctr; uint64_t buf[2]; int has_buf; } aesctr_t;
+typedef struct { uint32_t rk[60]; uint64_t ctr; uint64_t buf[2]; int has_buf; uint64_t nout; int patched; } aesctr_t;
+/* test hook (the engine's pvacb_debug_set(ctx, 1, word, or_mask)): keystream word `word` of every LPN stream is OR-ed with or_mask, which
+ * lets a test reach the rejection branch of bounded() (crypto/lpn.hpp:141-148, p = 2^-61 per row) */
+static uint64_t g_patch_word = ~0ull, g_patch_or = 0;
+void orc_set_prf_patch(uint64_t word, uint64_t or_mask) { g_patch_word = word; g_patch_or = or_mask; }
 static uint32_t subword(uint32_t w) {
     return (uint32_t)AES_SBOX[w & 0xff] | ((uint32_t)AES_SBOX[(w >> 8) & 0xff] << 8) | ((uint32_t)AES_SBOX[(w >> 16) & 0xff] << 16) | ((uint32_t)AES_SBOX[w >> 24] << 24);
 }
@@ -238,7 +275,7 @@ static void aesctr_init(aesctr_t* a, const uint8_t key[32], uint64_t nonce) {
         else if (i % 8 == 4) t = subword(t);
         a->rk[i] = a->rk[i - 8] ^ t;
     }
-    a->ctr = nonce; a->has_buf = 0;
+    a->ctr = nonce; a->has_buf = 0; a->nout = 0; a->patched = 0;
 }
 /* one block: input = LE64(ctr) || 0^8 (counter in the low lane only, crypto/lpn.hpp:84,104) */
 static void aesctr_block(aesctr_t* a, uint64_t out[2]) {
@@ -262,10 +299,12 @@ static void aesctr_block(aesctr_t* a, uint64_t out[2]) {
 }
 /* word FIFO: word w of the stream = half (w&1) of block (w>>1)  (crypto/lpn.hpp:108-139) */
 static uint64_t aesctr_next(aesctr_t* a) {
-    if (a->has_buf) { a->has_buf = 0; return a->buf[1]; }
-    aesctr_block(a, a->buf);
-    a->has_buf = 1;
-    return a->buf[0];
+    uint64_t x;
+    if (a->has_buf) { a->has_buf = 0; x = a->buf[1]; }
+    else { aesctr_block(a, a->buf); a->has_buf = 1; x = a->buf[0]; }
+    if (a->patched && a->nout == g_patch_word) x |= g_patch_or;
+    a->nout++;
+    return x;
 }
 /* crypto/lpn.hpp:141-148 -- strict '<' acceptance */
 static uint64_t aesctr_bounded(aesctr_t* a, uint64_t M) {
@@ -313,6 +352,7 @@ void orc_lpn_make_ybits(const orc_keys* k, uint64_t ztag, uint64_t nlo, uint64_t
     uint8_t key[32]; uint64_t nonce;
     orc_derive_aes_key(k, ztag, nlo, nhi, dom, key, &nonce);
     aesctr_t prg; aesctr_init(&prg, key, nonce);
+    prg.patched = 1;
     memset(ybits, 0, (size_t)((rows + 63) / 64) * 8);
     for (int r = 0; r < rows; r++) {
         uint64_t acc = 0;
@@ -1028,4 +1068,4 @@ void orc_prf_R_core(const orc_keys* k, uint64_t ztag, uint64_t nlo, uint64_t nhi
 void orc_prf_R(const orc_keys* k, uint64_t ztag, uint64_t nlo, uint64_t nhi, uint64_t* o) { fp_t r = prf_R(k, ztag, nlo, nhi); o[0] = r.lo; o[1] = r.hi; }
 void orc_prf_R_noise(const orc_keys* k, uint64_t ztag, uint64_t nlo, uint64_t nhi, uint64_t* o) { fp_t r = prf_R_noise(k, ztag, nlo, nhi); o[0] = r.lo; o[1] = r.hi; }
 void orc_prf_noise_delta(const orc_keys* k, uint64_t ztag, uint64_t nlo, uint64_t nhi, uint32_t gid, uint8_t kind, uint64_t* o) { fp_t r = prf_noise_delta(k, ztag, nlo, nhi, gid, kind); o[0] = r.lo; o[1] = r.hi; }
-uint64_t orc_tape_word(uint64_t* state) { tape_t t = { *state, 0 }; uint64_t x = tape_u64(&t); *state = t.state; return x; }
+uint64_t orc_tape_word(uint64_t* state) { *state += 0x9E3779B97F4A7C15ull; return mix64(*state); }   /* SplitMix64 stepping, for the tests */

@@ -42,6 +42,11 @@ def lib():
         "ref_seed": (None, [u64]),
         "ref_tape_draws": (u64, []),
         "ref_tape_word": (u64, []),
+        "ref_set_tape": (None, [i32, P(u8)]),
+        "ref_set_tape_lane": (None, [u32]),
+        "ref_set_tape_words": (None, [P(u64), u64]),
+        "ref_keys_omega": (None, [vp, P(u64)]),
+        "ref_keys_save": (i32, [vp, C.c_char_p, C.c_char_p]),
         "ref_item_stream_state": (u64, [u64, u64]),
         "ref_keygen": (vp, [u64]),
         "ref_keys_from_raw": (vp, [u64, P(u8), P(u64), P(u64), P(u64), P(u64)]),
@@ -103,6 +108,20 @@ def lib():
     L.ref_init()
     _lib = L
     return L
+
+
+_tape_words_keep = None
+
+
+def set_tape(kind, key=None, lane=0, words=None):
+    """tape kind behind the reference's getrandom(): 0 SplitMix64 (default), 1 ChaCha20 under key with `lane`, 2 explicit words"""
+    global _tape_words_keep
+    k = np.frombuffer(bytes(key), np.uint8).copy() if key is not None else None
+    lib().ref_set_tape(kind, _p(k, C.c_uint8) if k is not None else None)
+    lib().ref_set_tape_lane(lane)
+    if words is not None:
+        _tape_words_keep = np.ascontiguousarray(words, np.uint64)
+        lib().ref_set_tape_words(_p(_tape_words_keep, C.c_uint64), len(_tape_words_keep))
 
 
 def _fp2(fn, *vals):
@@ -174,6 +193,16 @@ class Keys:
 
     def set_lpn_t(self, t):
         lib().ref_keys_set_lpn_t(self.h, t)
+
+    def omega_B(self):
+        o = np.zeros(2, np.uint64)
+        lib().ref_keys_omega(self.h, _p(o, C.c_uint64))
+        return o
+
+    def save(self, pk_path=None, sk_path=None):
+        """the reference's key files (layout of savePk / saveSk, tests/bounty2_test.cpp:145-192) written from the reference's own objects"""
+        rc = lib().ref_keys_save(self.h, pk_path.encode() if pk_path else None, sk_path.encode() if sk_path else None)
+        assert rc == 0
 
     def export(self, with_H=True):
         ct = C.c_uint64()

@@ -17,15 +17,41 @@
 #include <sys/random.h>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
 
 static thread_local uint64_t g_tape_state = 0;
 static thread_local uint64_t g_tape_draws = 0;
+// tape kinds as in pvac_hfhe_cppbyv_b200/csrc/common.cuh: 0 SplitMix64, 1 ChaCha20 (stream id = the seeded state, plus a lane), 2 explicit words
+static int g_tape_kind = 0;
+static uint32_t g_tape_key[8];
+static uint32_t g_tape_lane = 0;
+static const uint64_t* g_tape_words = nullptr;
+static uint64_t g_tape_nwords = 0;
+
+static inline uint32_t rotl32c(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+static void chacha_block(const uint32_t key[8], const uint32_t c[4], uint32_t out[16]) {      // RFC 8439 section 2.3, 20 rounds
+    uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7], c[0], c[1], c[2], c[3]};
+    uint32_t x[16];
+    std::memcpy(x, in, sizeof x);
+    auto qr = [&](int a, int b, int cc, int d) {
+        x[a] += x[b]; x[d] ^= x[a]; x[d] = rotl32c(x[d], 16); x[cc] += x[d]; x[b] ^= x[cc]; x[b] = rotl32c(x[b], 12);
+        x[a] += x[b]; x[d] ^= x[a]; x[d] = rotl32c(x[d], 8); x[cc] += x[d]; x[b] ^= x[cc]; x[b] = rotl32c(x[b], 7);
+    };
+    for (int r = 0; r < 10; r++) { qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15); qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14); }
+    for (int i = 0; i < 16; i++) out[i] = x[i] + in[i];
+}
 
 static inline uint64_t tape_next() {
-    uint64_t z = (g_tape_state += 0x9E3779B97F4A7C15ull);
+    const uint64_t k = g_tape_draws++;
+    if (g_tape_kind == 1) {
+        uint32_t c[4] = {(uint32_t)(k >> 3), g_tape_lane ^ (uint32_t)((k >> 3) >> 32), (uint32_t)g_tape_state, (uint32_t)(g_tape_state >> 32)}, o[16];
+        chacha_block(g_tape_key, c, o);
+        return (uint64_t)o[2 * (k & 7)] | ((uint64_t)o[2 * (k & 7) + 1] << 32);
+    }
+    if (g_tape_kind == 2) return k < g_tape_nwords ? g_tape_words[k] : 0;
+    uint64_t z = g_tape_state + (k + 1) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    g_tape_draws++;
     return z ^ (z >> 31);
 }
 
@@ -73,12 +99,18 @@ extern "C" {
 
 void ref_init() {
     set_debug_level(0);
-    uint64_t save = g_tape_state;
+    uint64_t save = g_tape_state, save_draws = g_tape_draws;
     select_toeplitz();
-    g_tape_state = save;
+    g_tape_state = save; g_tape_draws = save_draws;
 }
 
 void ref_seed(uint64_t state) { g_tape_state = state; g_tape_draws = 0; }
+void ref_set_tape(int kind, const uint8_t* key32) {
+    g_tape_kind = kind;
+    if (key32) for (int i = 0; i < 8; i++) g_tape_key[i] = (uint32_t)key32[4 * i] | ((uint32_t)key32[4 * i + 1] << 8) | ((uint32_t)key32[4 * i + 2] << 16) | ((uint32_t)key32[4 * i + 3] << 24);
+}
+void ref_set_tape_lane(uint32_t lane) { g_tape_lane = lane; }
+void ref_set_tape_words(const uint64_t* words, uint64_t n) { g_tape_words = words; g_tape_nwords = n; }
 uint64_t ref_tape_draws() { return g_tape_draws; }
 uint64_t ref_tape_word() { return tape_next(); }
 uint64_t ref_item_stream_state(uint64_t batch_seed, uint64_t item) { return item_stream_state(batch_seed, item); }
@@ -115,6 +147,49 @@ void* ref_keys_from_raw(uint64_t canon_tag, const uint8_t* h_digest, const uint6
 }
 
 void ref_keys_free(void* h) { delete (Keys*)h; }
+
+void ref_keys_omega(void* h, uint64_t* out2) { Keys* k = (Keys*)h; out2[0] = k->pk.omega_B.lo; out2[1] = k->pk.omega_B.hi; }
+
+// The reference's key files. Its writers are lambdas inside tests/bounty2_test.cpp (:145-192), not part of the headers, so the byte
+// layout is restated here field by field OVER THE REFERENCE'S OWN PubKey / SecKey objects (ubk, omega_B and the Params it generated).
+int ref_keys_save(void* h, const char* pk_path, const char* sk_path) {
+    Keys* k = (Keys*)h;
+    auto put32 = [](FILE* f, uint32_t x) { fwrite(&x, 4, 1, f); };
+    auto put64 = [](FILE* f, uint64_t x) { fwrite(&x, 8, 1, f); };
+    if (sk_path) {
+        FILE* f = fopen(sk_path, "wb");
+        if (!f) return 1;
+        put32(f, 0x66666999u); put32(f, 1);
+        for (int j = 0; j < 4; j++) put64(f, k->sk.prf_k[j]);
+        put64(f, k->sk.lpn_s_bits.size());
+        for (auto w : k->sk.lpn_s_bits) put64(f, w);
+        fclose(f);
+    }
+    if (pk_path) {
+        FILE* f = fopen(pk_path, "wb");
+        if (!f) return 1;
+        const PubKey& pk = k->pk;
+        put32(f, 0x06660666u); put32(f, 1);
+        put32(f, pk.prm.m_bits); put32(f, pk.prm.B); put32(f, pk.prm.lpn_t); put32(f, pk.prm.lpn_n); put32(f, pk.prm.lpn_tau_num); put32(f, pk.prm.lpn_tau_den);
+        put32(f, (uint32_t)pk.prm.noise_entropy_bits); put32(f, (uint32_t)pk.prm.depth_slope_bits);
+        uint64_t t2; std::memcpy(&t2, &pk.prm.tuple2_fraction, 8);
+        put64(f, t2);
+        put32(f, (uint32_t)pk.prm.edge_budget);
+        put64(f, pk.canon_tag);
+        fwrite(pk.H_digest.data(), 1, 32, f);
+        put64(f, pk.H.size());
+        for (const auto& b : pk.H) { put32(f, (uint32_t)b.nbits); for (size_t i = 0; i < (b.nbits + 63) / 64; ++i) put64(f, b.w[i]); }
+        put64(f, pk.ubk.perm.size());
+        for (auto v : pk.ubk.perm) put32(f, v);
+        put64(f, pk.ubk.inv.size());
+        for (auto v : pk.ubk.inv) put32(f, v);
+        put64(f, pk.omega_B.lo); put64(f, pk.omega_B.hi);
+        put64(f, pk.powg_B.size());
+        for (const auto& x : pk.powg_B) { put64(f, x.lo); put64(f, x.hi); }
+        fclose(f);
+    }
+    return 0;
+}
 
 void ref_keys_set_lpn_t(void* h, int t) { ((Keys*)h)->pk.prm.lpn_t = t; }
 

@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from pvac_hfhe_cppbyv_b200 import api, shard
-eng = api.Engine(0, prf_mode=api.PRF_LIVE); eng.keygen(1)
+eng = api.Engine(0, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX); eng.keygen(1)
 Me = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 rng = np.random.default_rng(1)
 va, vb = rng.integers(0, 2**64, Me, dtype=np.uint64), rng.integers(0, 2**64, Me, dtype=np.uint64)

@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from pvac_hfhe_cppbyv_b200 import api
-eng = api.Engine(0, prf_mode=api.PRF_LIVE); eng.keygen(1)
+eng = api.Engine(0, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX); eng.keygen(1)
 rng = np.random.default_rng(1)
 N = 4096
 va, vb = rng.integers(0, 2**64, N, dtype=np.uint64), rng.integers(0, 2**64, N, dtype=np.uint64)

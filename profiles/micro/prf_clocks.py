@@ -3,7 +3,7 @@ import os, sys, subprocess, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from pvac_hfhe_cppbyv_b200 import api
-eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL); eng.keygen(1)
+eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL, tape=api.TAPE_SPLITMIX); eng.keygen(1)
 rng = np.random.default_rng(1)
 n = 4096
 z, lo, hi = (rng.integers(0, 2**64, n, dtype=np.uint64) for _ in range(3))

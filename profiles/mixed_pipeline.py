@@ -21,7 +21,7 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 if sh.world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-eng = api.Engine(device=local, prf_mode=api.PRF_LIVE)
+eng = api.Engine(device=local, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX)
 blob = torch.empty(api.KEY_BLOB_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
 if sh.rank == 0:
     eng.keygen(1)

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from pvac_hfhe_cppbyv_b200 import api
-eng = api.Engine(0, prf_mode=api.PRF_LIVE)
+eng = api.Engine(0, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX)
 eng.keygen(1)
 rng = np.random.default_rng(1)
 n = 32768

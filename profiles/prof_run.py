@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from pvac_hfhe_cppbyv_b200 import api
 
-eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL)
+eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL, tape=api.TAPE_SPLITMIX)
 eng.keygen(1)
 rng = np.random.default_rng(1)
 v = rng.integers(0, 2**64, 128, dtype=np.uint64)

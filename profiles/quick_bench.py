@@ -5,7 +5,7 @@ import numpy as np
 from pvac_hfhe_cppbyv_b200 import api
 
 what = set(sys.argv[1:]) or {"prf", "sigma", "add", "check"}
-eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL)
+eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL, tape=api.TAPE_SPLITMIX)
 eng.keygen(1)
 rng = np.random.default_rng(1)
 eng.profile_enable(True)

@@ -25,11 +25,27 @@ B = 337
 M_WORDS = 128
 N_COLS = 16384
 LPN_WORDS = 64
-KEY_BLOB_BYTES = (748 + 16384 * 128) * 8
+KEY_BLOB_BYTES = (752 + 16384 * 128) * 8
 PRF_FAITHFUL, PRF_LIVE = 0, 1
 
-STATUS = {0: "OK", 1: "E_ARG", 2: "E_CUDA", 3: "E_OOM", 4: "E_NOKEYS", 5: "E_EDGE_BUDGET", 6: "E_LAYER_GRAPH", 7: "E_RARE_PATH",
-          8: "E_DUP_EDGE", 9: "E_FORMAT", 10: "E_SHAPE"}
+TAPE_SPLITMIX, TAPE_CHACHA20, TAPE_WORDS = 0, 1, 2
+
+STATUS = {0: "OK", 1: "E_ARG", 2: "E_CUDA", 3: "E_OOM", 4: "E_NOKEYS", 5: "E_EDGE_BUDGET", 6: "E_LAYER_GRAPH", 7: "E_RESERVED7",
+          8: "E_RESERVED8", 9: "E_FORMAT", 10: "E_SHAPE"}
+
+
+class Params(C.Structure):
+    """struct pvacb_params = pvac::Params (core/types.hpp:36-70)"""
+    _fields_ = [("B", C.c_int32), ("m_bits", C.c_int32), ("n_bits", C.c_int32), ("h_col_wt", C.c_int32), ("x_col_wt", C.c_int32), ("err_wt", C.c_int32),
+                ("noise_entropy_bits", C.c_double), ("tuple2_fraction", C.c_double), ("depth_slope_bits", C.c_double), ("edge_budget", C.c_uint64),
+                ("lpn_n", C.c_int32), ("lpn_t", C.c_int32), ("lpn_tau_num", C.c_int32), ("lpn_tau_den", C.c_int32),
+                ("recrypt_lo", C.c_double), ("recrypt_hi", C.c_double), ("recrypt_rounds", C.c_int32)]
+
+    @classmethod
+    def default(cls):
+        p = cls()
+        load_library().pvacb_params_default(C.byref(p))
+        return p
 
 # every symbol include/pvacb.h declares
 SYMBOLS = [
@@ -44,6 +60,13 @@ SYMBOLS = [
     "pvacb_enc_value_depth", "pvacb_enc_zero_depth", "pvacb_plan_noise", "pvacb_ct_neg", "pvacb_ct_div_const", "pvacb_enc_fp_depth",
     "pvacb_enc_text", "pvacb_dec_text", "pvacb_batch_concat",
     "pvacb_ct_recrypt", "pvacb_sigma_density", "pvacb_ubk_apply", "pvacb_ubk_perm", "pvacb_batch_select",
+    "pvacb_params_default", "pvacb_keygen_params", "pvacb_set_params", "pvacb_get_params", "pvacb_keys_export_file", "pvacb_keys_import_file",
+    "pvacb_set_tape", "pvacb_get_tape", "pvacb_set_tape_words", "pvacb_set_item_base", "pvacb_fresh_seed", "pvacb_debug_set",
+    "pvacb_blob_layout", "pvacb_batch_blob_info", "pvacb_batch_export_blob_async", "pvacb_batch_import_blob", "pvacb_set_export_relay",
+    "pvacb_group_create", "pvacb_group_destroy", "pvacb_group_size", "pvacb_group_ctx", "pvacb_group_last_error", "pvacb_group_keygen_params",
+    "pvacb_group_keys_import_file", "pvacb_group_replicate_keys", "pvacb_group_set_tape", "pvacb_group_enc_value", "pvacb_group_ct_add", "pvacb_group_ct_sub",
+    "pvacb_group_ct_mul", "pvacb_group_dec_value", "pvacb_group_commit_ct", "pvacb_group_batch_free", "pvacb_group_batch_count", "pvacb_group_batch_part",
+    "pvacb_group_tune_export", "pvacb_group_export_blobs",
 ]
 
 
@@ -130,6 +153,43 @@ def load_library():
         "pvacb_plan_noise": (i32, [i32, P(i32), P(i32)]),
         "pvacb_ct_neg": (i32, [vp, vp, P(vp)]),
         "pvacb_ct_div_const": (i32, [vp, vp, P(u64), P(vp)]),
+        "pvacb_params_default": (None, [P(Params)]),
+        "pvacb_keygen_params": (i32, [vp, P(Params), P(u8)]),
+        "pvacb_set_params": (i32, [vp, P(Params)]),
+        "pvacb_get_params": (i32, [vp, P(Params)]),
+        "pvacb_keys_export_file": (i32, [vp, C.c_char_p, C.c_char_p]),
+        "pvacb_keys_import_file": (i32, [vp, C.c_char_p, C.c_char_p]),
+        "pvacb_set_tape": (i32, [vp, i32, P(u8)]),
+        "pvacb_get_tape": (i32, [vp]),
+        "pvacb_set_tape_words": (i32, [vp, P(u64), sz, sz]),
+        "pvacb_set_item_base": (i32, [vp, u64]),
+        "pvacb_fresh_seed": (u64, [vp]),
+        "pvacb_debug_set": (i32, [vp, i32, u64, u64]),
+        "pvacb_blob_layout": (i32, [u64, u64, u64, P(u64)]),
+        "pvacb_batch_blob_info": (i32, [vp, P(u64), P(u64), P(u64), P(u64)]),
+        "pvacb_batch_export_blob_async": (i32, [vp, vp, vp, sz]),
+        "pvacb_batch_import_blob": (i32, [vp, sz, u64, u64, vp, sz, P(vp)]),
+        "pvacb_set_export_relay": (i32, [vp, i32]),
+        "pvacb_group_create": (i32, [P(i32), i32, P(vp)]),
+        "pvacb_group_destroy": (None, [vp]),
+        "pvacb_group_size": (i32, [vp]),
+        "pvacb_group_ctx": (vp, [vp, i32]),
+        "pvacb_group_last_error": (C.c_char_p, [vp]),
+        "pvacb_group_keygen_params": (i32, [vp, P(Params), P(u8)]),
+        "pvacb_group_keys_import_file": (i32, [vp, C.c_char_p, C.c_char_p]),
+        "pvacb_group_replicate_keys": (i32, [vp]),
+        "pvacb_group_set_tape": (i32, [vp, i32, P(u8)]),
+        "pvacb_group_enc_value": (i32, [vp, P(u64), sz, u64, P(vp)]),
+        "pvacb_group_ct_add": (i32, [vp, vp, vp, P(vp)]),
+        "pvacb_group_ct_sub": (i32, [vp, vp, vp, P(vp)]),
+        "pvacb_group_ct_mul": (i32, [vp, vp, vp, u64, P(vp)]),
+        "pvacb_group_dec_value": (i32, [vp, vp, P(u64)]),
+        "pvacb_group_commit_ct": (i32, [vp, vp, P(u8)]),
+        "pvacb_group_batch_free": (None, [vp]),
+        "pvacb_group_batch_count": (sz, [vp]),
+        "pvacb_group_batch_part": (vp, [vp, i32]),
+        "pvacb_group_tune_export": (i32, [vp, P(C.c_double), P(C.c_double)]),
+        "pvacb_group_export_blobs": (i32, [vp, vp, P(vp), P(sz)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -182,7 +242,9 @@ class Batch:
 class Engine:
     """One B200: context + replicated keys. Mirrors the reference's free functions as methods over batches."""
 
-    def __init__(self, device=0, prf_mode=PRF_FAITHFUL):
+    def __init__(self, device=0, prf_mode=PRF_FAITHFUL, tape=TAPE_CHACHA20, tape_key=None):
+        """tape: RNG tape kind of the context (include/pvacb.h). The default draws every random word from ChaCha20 under a key taken
+        from the OS (or tape_key, 32 bytes); TAPE_SPLITMIX is for parity tests against the committed golden vectors only."""
         L = load_library()
         h = C.c_void_p()
         rc = L.pvacb_ctx_create(device, C.byref(h))
@@ -191,6 +253,35 @@ class Engine:
         self.L, self.h, self.device = L, h, device
         self._batches = weakref.WeakSet()
         self.set_prf_mode(prf_mode)
+        if tape != TAPE_CHACHA20 or tape_key is not None:
+            self.set_tape(tape, tape_key)
+
+    # ---- RNG tape
+    def set_tape(self, kind, key=None):
+        k = np.frombuffer(bytes(key), np.uint8).copy() if key is not None else None
+        if k is not None and len(k) != 32:
+            raise PvacbError(1, "tape key must be 32 bytes")
+        self._ck(self.L.pvacb_set_tape(self.h, kind, _p(k, C.c_uint8)))
+
+    def set_tape_words(self, words):
+        """words: (n_items, words_per_item) uint64 -- every random word of every item (tape kind TAPE_WORDS)"""
+        w = np.ascontiguousarray(words, np.uint64)
+        self._ck(self.L.pvacb_set_tape_words(self.h, _p(w, C.c_uint64), w.shape[0], w.shape[1]))
+
+    def set_item_base(self, base):
+        self._ck(self.L.pvacb_set_item_base(self.h, int(base)))
+
+    def fresh_seed(self):
+        return int(self.L.pvacb_fresh_seed(self.h))
+
+    def _seed(self, batch_seed, tape_states):
+        """a repeated seed repeats nonces, masks and salts: with neither a seed nor explicit states the context hands out a fresh one"""
+        if batch_seed is None:
+            return 0 if tape_states is not None else self.fresh_seed()
+        return int(batch_seed)
+
+    def debug_set(self, what, a=0, b=0):
+        self._ck(self.L.pvacb_debug_set(self.h, what, int(a) & (2**64 - 1), int(b) & (2**64 - 1)))
 
     def close(self):
         if self.h:
@@ -230,7 +321,28 @@ class Engine:
 
     # ---- keys (crypto/keygen.hpp:35)
     def keygen(self, tape_state):
+        """PARITY / TEST ONLY (SplitMix64 from a 64-bit state, the committed golden keys); use keygen_params for real keys"""
         self._ck(self.L.pvacb_keygen(self.h, tape_state))
+
+    def keygen_params(self, params=None, seed=None):
+        """keygen(prm, pk, sk) of the reference (crypto/keygen.hpp:35); seed: 32 bytes or None = OS CSPRNG"""
+        sd = np.frombuffer(bytes(seed), np.uint8).copy() if seed is not None else None
+        self._ck(self.L.pvacb_keygen_params(self.h, C.byref(params) if params is not None else None, _p(sd, C.c_uint8)))
+
+    def set_params(self, params):
+        self._ck(self.L.pvacb_set_params(self.h, C.byref(params)))
+
+    def get_params(self):
+        p = Params()
+        self._ck(self.L.pvacb_get_params(self.h, C.byref(p)))
+        return p
+
+    def export_key_files(self, pk_path=None, sk_path=None):
+        """savePk / saveSk of the reference's programs (tests/bounty2_test.cpp:145-192), byte for byte"""
+        self._ck(self.L.pvacb_keys_export_file(self.h, pk_path.encode() if pk_path else None, sk_path.encode() if sk_path else None))
+
+    def import_key_files(self, pk_path, sk_path=None):
+        self._ck(self.L.pvacb_keys_import_file(self.h, pk_path.encode(), sk_path.encode() if sk_path else None))
 
     def import_keys(self, canon_tag, H_digest, H, powg, prf_k, lpn_s):
         hd = np.ascontiguousarray(H_digest, np.uint8)
@@ -268,7 +380,7 @@ class Engine:
     def adopt_key_blob_from(self, device_ptr):
         self._ck(self.L.pvacb_keys_adopt_blob_from(self.h, device_ptr))
 
-    PROF_TAGS = ("prf_lpn", "t1", "sigma", "concat", "dec_edges", "mul_plan", "t6", "t7")
+    PROF_TAGS = ("prf_lpn", "mul_pairs", "sigma", "concat", "dec_edges", "commit", "compact", "t7")
 
     def l2_gather_probe(self, reps=5):
         g = C.c_double()
@@ -286,11 +398,11 @@ class Engine:
         return {t: (float(ms[i]), int(cnt[i])) for i, t in enumerate(self.PROF_TAGS)}
 
     # ---- hot path
-    def enc_value(self, values, batch_seed=0, tape_states=None):
+    def enc_value(self, values, batch_seed=None, tape_states=None):
         v = _u64(values)
         out = C.c_void_p()
         st = _u64(tape_states) if tape_states is not None else None
-        self._ck(self.L.pvacb_enc_value_ex(self.h, _p(v, C.c_uint64), len(v), batch_seed, _p(st, C.c_uint64), C.byref(out)))
+        self._ck(self.L.pvacb_enc_value_ex(self.h, _p(v, C.c_uint64), len(v), self._seed(batch_seed, tape_states), _p(st, C.c_uint64), C.byref(out)))
         return Batch(self, out)
 
     def ct_add(self, a, b):
@@ -309,25 +421,25 @@ class Engine:
         self._ck(self.L.pvacb_ct_scale(self.h, a.h, _p(ss, C.c_uint64), C.byref(out)))
         return Batch(self, out)
 
-    def enc_value_depth(self, values, depth_hint, batch_seed=0, tape_states=None):
+    def enc_value_depth(self, values, depth_hint, batch_seed=None, tape_states=None):
         v = _u64(values)
         st = _u64(tape_states) if tape_states is not None else None
         out = C.c_void_p()
-        self._ck(self.L.pvacb_enc_value_depth(self.h, _p(v, C.c_uint64), len(v), depth_hint, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        self._ck(self.L.pvacb_enc_value_depth(self.h, _p(v, C.c_uint64), len(v), depth_hint, self._seed(batch_seed, tape_states), _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
         return Batch(self, out)
 
-    def enc_fp_depth(self, fp_values, depth_hint=0, batch_seed=0, tape_states=None):
+    def enc_fp_depth(self, fp_values, depth_hint=0, batch_seed=None, tape_states=None):
         """fp_values: (n, 2) uint64 canonical field elements -> one-share ciphertexts (enc_fp_depth, ops/encrypt.hpp:162)"""
         v = np.ascontiguousarray(fp_values, np.uint64).reshape(-1, 2)
         st = _u64(tape_states) if tape_states is not None else None
         out = C.c_void_p()
-        self._ck(self.L.pvacb_enc_fp_depth(self.h, _p(v, C.c_uint64), len(v), depth_hint, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        self._ck(self.L.pvacb_enc_fp_depth(self.h, _p(v, C.c_uint64), len(v), depth_hint, self._seed(batch_seed, tape_states), _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
         return Batch(self, out)
 
-    def enc_zero_depth(self, n, depth_hint, batch_seed=0, tape_states=None):
+    def enc_zero_depth(self, n, depth_hint, batch_seed=None, tape_states=None):
         st = _u64(tape_states) if tape_states is not None else None
         out = C.c_void_p()
-        self._ck(self.L.pvacb_enc_zero_depth(self.h, n, depth_hint, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        self._ck(self.L.pvacb_enc_zero_depth(self.h, n, depth_hint, self._seed(batch_seed, tape_states), _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
         return Batch(self, out)
 
     def plan_noise(self, depth_hint):
@@ -346,7 +458,7 @@ class Engine:
         self._ck(self.L.pvacb_ct_div_const(self.h, a.h, _p(kk, C.c_uint64), C.byref(out)))
         return Batch(self, out)
 
-    def enc_text(self, msgs, batch_seed=0, tape_states=None):
+    def enc_text(self, msgs, batch_seed=None, tape_states=None):
         """msgs: list of bytes -> one WAVE-MAJOR batch (lengths, then block 0 of every message, then block 1, ...)"""
         off = np.zeros(len(msgs) + 1, np.uint64)
         for i, m in enumerate(msgs):
@@ -354,7 +466,7 @@ class Engine:
         flat = np.frombuffer(b"".join(msgs) or b"\0", np.uint8).copy()
         st = _u64(tape_states) if tape_states is not None else None
         out = C.c_void_p()
-        self._ck(self.L.pvacb_enc_text(self.h, _p(flat, C.c_uint8), _p(off, C.c_uint64), len(msgs), batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        self._ck(self.L.pvacb_enc_text(self.h, _p(flat, C.c_uint8), _p(off, C.c_uint64), len(msgs), self._seed(batch_seed, tape_states), _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
         return Batch(self, out)
 
     def dec_text(self, c, n_msgs):
@@ -370,15 +482,16 @@ class Engine:
         self._ck(self.L.pvacb_batch_concat(self.h, arr, len(parts), C.byref(out)))
         return Batch(self, out)
 
-    def ct_recrypt(self, c, zero_pool, batch_seed=0, tape_states=None):
+    def ct_recrypt(self, c, zero_pool, batch_seed=None, tape_states=None):
         st = _u64(tape_states) if tape_states is not None else None
         out = C.c_void_p()
-        self._ck(self.L.pvacb_ct_recrypt(self.h, c.h, zero_pool.h, batch_seed, _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
+        self._ck(self.L.pvacb_ct_recrypt(self.h, c.h, zero_pool.h, self._seed(batch_seed, tape_states), _p(st, C.c_uint64) if st is not None else None, C.byref(out)))
         return Batch(self, out)
 
-    def make_evalkey(self, pool_size, depth_hint, batch_seed):
-        """EvalKey of the reference (ops/recrypt.hpp:12): (zero_pool batch, enc_one batch); every entry on its own tape stream"""
-        return self.enc_zero_depth(pool_size, depth_hint, batch_seed), self.enc_value(np.array([1], np.uint64), batch_seed + 1)
+    def make_evalkey(self, pool_size, depth_hint, batch_seed=None, one_seed=None):
+        """EvalKey of the reference (ops/recrypt.hpp:12): (zero_pool batch, enc_one batch); every entry on its own tape stream.
+        The two seeds must differ (and differ from every other seed used under this key); None = fresh seeds from the context."""
+        return self.enc_zero_depth(pool_size, depth_hint, batch_seed), self.enc_value(np.array([1], np.uint64), one_seed)
 
     def sigma_density(self, c):
         out = np.zeros(len(c), np.float64)
@@ -407,10 +520,10 @@ class Engine:
         self._ck(self.L.pvacb_compact_edges(self.h, a.h, C.byref(out)))
         return Batch(self, out)
 
-    def ct_mul(self, a, b, batch_seed=0, tape_states=None):
+    def ct_mul(self, a, b, batch_seed=None, tape_states=None):
         out = C.c_void_p()
         st = _u64(tape_states) if tape_states is not None else None
-        self._ck(self.L.pvacb_ct_mul_ex(self.h, a.h, b.h, batch_seed, _p(st, C.c_uint64), C.byref(out)))
+        self._ck(self.L.pvacb_ct_mul_ex(self.h, a.h, b.h, self._seed(batch_seed, tape_states), _p(st, C.c_uint64), C.byref(out)))
         return Batch(self, out)
 
     def dec_value(self, c):
@@ -481,6 +594,27 @@ class Engine:
             ptr("w", C.c_uint64), ptr("sigma", C.c_uint64)))
         return d
 
+    # ---- whole-batch image: one copy per batch (and, optionally, out through another GPU's host link)
+    def blob_info(self, b):
+        """-> (n, layout_layers, layout_edges, bytes) of the batch's device image"""
+        n, nl, ne, by = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.L.pvacb_batch_blob_info(b.h, C.byref(n), C.byref(nl), C.byref(ne), C.byref(by)))
+        return int(n.value), int(nl.value), int(ne.value), int(by.value)
+
+    def export_blob_async(self, b, host_u8):
+        """queue ONE device->host copy of the batch image into host_u8 (pinned uint8 array, large enough); wait with export_wait[_one];
+        blob_views(host_u8, *blob_info(b)[:3]) then gives the arrays"""
+        self._ck(self.L.pvacb_batch_export_blob_async(self.h, b.h, host_u8.ctypes.data_as(C.c_void_p), host_u8.nbytes))
+
+    def import_blob(self, host_u8, n, layout_layers, layout_edges):
+        out = C.c_void_p()
+        off = blob_layout(n, layout_layers, layout_edges)
+        self._ck(self.L.pvacb_batch_import_blob(self.h, n, layout_layers, layout_edges, host_u8.ctypes.data_as(C.c_void_p), off[13], C.byref(out)))
+        return Batch(self, out)
+
+    def set_export_relay(self, device):
+        self._ck(self.L.pvacb_set_export_relay(self.h, device))
+
     def export_wait(self):
         self._ck(self.L.pvacb_export_wait(self.h))
 
@@ -544,6 +678,44 @@ class Engine:
         out = np.zeros_like(aa)
         self._ck(self.L.pvacb_fp_op(self.h, op, len(aa), _p(aa, C.c_uint64), _p(bb, C.c_uint64), _p(out, C.c_uint64)))
         return out
+
+
+def blob_layout(n, n_layers, n_edges):
+    off = (C.c_uint64 * 14)()
+    load_library().pvacb_blob_layout(n, n_layers, n_edges, off)
+    return [int(x) for x in off]
+
+
+_BLOB_FIELDS = (("loff", np.uint32, 1), ("eoff", np.uint32, 1), ("rule", np.uint8, 1), ("ztag", np.uint64, 1), ("nlo", np.uint64, 1), ("nhi", np.uint64, 1),
+                ("pa", np.uint32, 1), ("pb", np.uint32, 1), ("lid", np.uint32, 1), ("idx", np.uint16, 1), ("ch", np.uint8, 1), ("w", np.uint64, 2), ("sigma", np.uint64, M_WORDS))
+
+
+def blob_views(host_u8, n, layout_layers, layout_edges):
+    """numpy views (no copy) of the 13 arrays inside a batch image; the layer arrays are trimmed to the logical layer count loff[n]"""
+    off = blob_layout(n, layout_layers, layout_edges)
+    d = {}
+    for k, (name, dt, width) in enumerate(_BLOB_FIELDS):
+        cnt = n + 1 if k < 2 else layout_layers if k < 8 else layout_edges
+        a = host_u8[off[k]: off[k] + cnt * width * np.dtype(dt).itemsize].view(dt)
+        d[name] = a.reshape(cnt, width) if width > 1 else a
+    nl = int(d["loff"][n])
+    for name in ("rule", "ztag", "nlo", "nhi", "pa", "pb"):
+        d[name] = d[name][:nl]
+    return d
+
+
+def pack_blob(d, out_u8=None):
+    """the image of an SoA dict (export_soa layout) -> (uint8 array, n, layers, edges), for import_blob"""
+    n, nl, ne = len(d["loff"]) - 1, len(d["rule"]), len(d["lid"])
+    off = blob_layout(n, nl, ne)
+    buf = out_u8 if out_u8 is not None else np.zeros(off[13], np.uint8)
+    for k, (name, dt, width) in enumerate(_BLOB_FIELDS):
+        v = d.get(name)
+        if v is None:
+            continue
+        raw = np.ascontiguousarray(v, dt).reshape(-1).view(np.uint8)
+        buf[off[k]: off[k] + raw.size] = raw
+    return buf, n, nl, ne
 
 
 def checksum_of_soa(d):

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libpvacb.so")
 
-SOURCES = ["engine.cu", "prf.cu", "sigma.cu", "enc.cu", "arith.cu", "mul.cu", "compact.cu", "commit.cu", "text.cu", "recrypt.cu", "dec.cu", "extras.cu", "keygen.cpp"]
+SOURCES = ["engine.cu", "boundary.cu", "group.cu", "prf.cu", "sigma.cu", "enc.cu", "arith.cu", "mul.cu", "compact.cu", "commit.cu", "text.cu", "recrypt.cu", "dec.cu", "extras.cu", "keygen.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -49,7 +49,13 @@ def _compile(nvcc, src, obj, log):
     return src
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, tuning=False):
+    """tuning=True builds libpvacb_tuning.so with -DPVACB_TUNING: the experiment shapes of the sigma kernel and the probe's
+    load flavours behind environment switches (profiles/README.md). The product library has none of them."""
+    global OBJ, LIB, NVCC_FLAGS
+    if tuning:
+        OBJ, LIB = os.path.join(HERE, "_build_tuning"), os.path.join(HERE, "libpvacb_tuning.so")
+        NVCC_FLAGS = NVCC_FLAGS + ["-DPVACB_TUNING"]
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "pvacb.h"))
@@ -85,4 +91,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, tuning="--tuning" in sys.argv))

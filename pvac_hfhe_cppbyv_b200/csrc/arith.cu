@@ -9,14 +9,14 @@
 namespace pvacb {
 
 __global__ void concat_offsets_kernel(uint64_t n, const uint32_t* __restrict__ la, const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ea,
-                                      const uint32_t* __restrict__ eb, uint32_t* __restrict__ lo, uint32_t* __restrict__ eo, unsigned int* __restrict__ err) {
+                                      const uint32_t* __restrict__ eb, uint32_t* __restrict__ lo, uint32_t* __restrict__ eo, uint32_t budget, unsigned int* __restrict__ err) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     lo[i] = la[i] + lb[i];
     eo[i] = ea[i] + eb[i];
     if (i < n) {
         uint32_t ne = (ea[i + 1] - ea[i]) + (eb[i + 1] - eb[i]);
-        if (ne > kEdgeBudget) atomicOr(err, 1u);   // guard_budget (ops/encrypt.hpp:106-111)
+        if (ne > budget) atomicOr(err, 1u);   // guard_budget (ops/encrypt.hpp:106-111)
     }
 }
 
@@ -114,7 +114,7 @@ int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode, Batch** out) {
     if ((rc = scratch.alloc(err, 4))) { batch_free(o); return rc; }
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
     uint64_t n = A->n;
-    concat_offsets_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->loff, B->loff, A->eoff, B->eoff, o->loff, o->eoff, err);
+    concat_offsets_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, A->loff, B->loff, A->eoff, B->eoff, o->loff, o->eoff, ctx->edge_budget, err);
     if (n) {
         uint64_t avg = (o->nE + n - 1) / n;
         unsigned ych = (unsigned)std::min<uint64_t>(std::max<uint64_t>((avg + kConcatChunk - 1) / kConcatChunk, 1), 4096);
@@ -129,7 +129,7 @@ int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode, Batch** out) {
     unsigned int h_err = 0;
     { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) { batch_free(o); return rc; } }
     if (h_err) {       // guard_budget(pk, C, "add") -> compact_edges, ops/arithmetic.hpp:28
-        if ((rc = guard_budget_batch(ctx, &o))) { batch_free(o); return rc; }
+        if ((rc = guard_budget_batch(ctx, &o, ctx->edge_budget))) { batch_free(o); return rc; }
     }
     rc = compact_layers_batch(ctx, o);
     if (rc) { batch_free(o); return rc; }
@@ -253,8 +253,11 @@ layers_remap_kernel(const uint32_t* __restrict__ loff, const uint32_t* __restric
 }
 
 // compact_layers of every ciphertext of b, in place (layer arrays shrink; edge arrays keep their place).
-int compact_layers_batch(Ctx* ctx, Batch* b) {
-    if (b->n == 0 || b->nL == 0) return PV_OK;
+int compact_layers_batch(Ctx* ctx, Batch* b, const unsigned int* d_err, unsigned int* h_err) {
+    if (b->n == 0 || b->nL == 0) {
+        if (d_err) { SmallRead sr; sr.add(h_err, d_err, 4); return read_small_sync(ctx, sr); }
+        return PV_OK;
+    }
     Scratch scratch(ctx);
     uint8_t* used = nullptr;
     uint32_t *cnt = nullptr, *noff = nullptr;
@@ -266,7 +269,7 @@ int compact_layers_batch(Ctx* ctx, Batch* b) {
     layers_mark_kernel<<<(unsigned)b->n, 128, 0, ctx->stream>>>(b->n, b->loff, b->eoff, b->rule, b->pa, b->pb, b->lid, used, cnt, nullptr);
     if ((rc = scan_u32(ctx, b->n, cnt, noff))) return rc;
     uint32_t total = 0;
-    { SmallRead sr; sr.add(&total, noff + b->n, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
+    { SmallRead sr; sr.add(&total, noff + b->n, 4); if (d_err) sr.add(h_err, d_err, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
     ctx->stat_kernel_launches += 1;
     if (total != b->nL) {
         uint32_t* remap = nullptr;

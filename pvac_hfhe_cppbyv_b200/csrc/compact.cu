@@ -138,6 +138,7 @@ int guard_budget_batch(Ctx* ctx, Batch** pb, uint32_t budget) {
     const uint64_t n = b->n;
     if (n == 0) return PV_OK;
     if (n >= (1ull << 24)) { ctx->last_error = "guard_budget: batch too large"; return PV_E_SHAPE; }
+    if (b->nL >= (1ull << 30)) { ctx->last_error = "compact_edges: layer ids need more than the 30 bits of the sort key"; return PV_E_SHAPE; }
     int rc;
     std::vector<void*> scratch;
     auto cleanup = [&]() { for (void* p : scratch) dev_free(ctx, p); scratch.clear(); };

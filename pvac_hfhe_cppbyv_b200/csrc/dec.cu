@@ -130,6 +130,7 @@ __global__ void dec_alias_copy_kernel(uint64_t nL, const uint32_t* __restrict__ 
 
 int op_dec_value(Ctx* ctx, const Batch* Cb, uint64_t* h_out) {
     if (Cb->n == 0) return PV_OK;
+    if (!ctx->have_sk) { ctx->last_error = "this context holds a public key only"; return PV_E_NOKEYS; }
     Scratch scratch(ctx);
     int rc;
     uint8_t* flags = nullptr;

@@ -59,7 +59,7 @@ int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out) {
         return PV_E_SHAPE;
     }
     Batch* b = new Batch();
-    b->ctx = ctx; b->n = n; b->nL = nL; b->nE = nE;
+    b->ctx = ctx; b->n = n; b->nL = nL; b->nE = nE; b->nL_alloc = nL;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 1); return o; };
     size_t o_loff = take((n + 1) * 4), o_eoff = take((n + 1) * 4);
@@ -108,7 +108,7 @@ void batch_free(Batch* b) {
 }
 
 // ------------------------------------------------------------------ keys
-static void derive_key_view(Ctx* ctx) {
+static int derive_key_view(Ctx* ctx) {
     const uint64_t* h = ctx->h_hdr.data();
     KeyView& kv = ctx->kv;
     kv.canon_tag = h[0];
@@ -128,9 +128,11 @@ static void derive_key_view(Ctx* ctx) {
     lpn_masks_from_secret(&h[9], ctx->lpn_m);
     ctx->h_ubk_perm.resize(kMBits);
     gen_ubk_perm_host(kv.canon_tag, ctx->h_ubk_perm.data());
-    if (!ctx->d_ubk_perm) cudaMalloc((void**)&ctx->d_ubk_perm, kMBits * 2);
-    cudaMemcpy(ctx->d_ubk_perm, ctx->h_ubk_perm.data(), kMBits * 2, cudaMemcpyHostToDevice);
+    if (!ctx->d_ubk_perm) PV_CUDA(cudaMalloc((void**)&ctx->d_ubk_perm, kMBits * 2));
+    PV_CUDA(cudaMemcpy(ctx->d_ubk_perm, ctx->h_ubk_perm.data(), kMBits * 2, cudaMemcpyHostToDevice));
     ctx->have_keys = true;
+    ctx->have_sk = true;
+    return PV_OK;
 }
 
 // The key blob must not straddle a 4 GiB boundary: the sigma kernel forms the addresses of the columns of H with 32-bit
@@ -153,14 +155,14 @@ static int ensure_blob(Ctx* ctx) {
     return rc;
 }
 
-static int keys_from_host_blob(Ctx* ctx, const uint64_t* blob) {
+int keys_from_host_blob(Ctx* ctx, const uint64_t* blob) {
+    cudaSetDevice(ctx->device);
     int rc = ensure_blob(ctx);
     if (rc) return rc;
     PV_CUDA(cudaMemcpyAsync(ctx->d_blob, blob, kBlobBytes, cudaMemcpyHostToDevice, ctx->stream));
     PV_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->h_hdr.assign(blob, blob + kBlobHdrWords);
-    derive_key_view(ctx);
-    return PV_OK;
+    return derive_key_view(ctx);
 }
 
 // libstdc++ bucket counts: every value _Prime_rehash_policy::_M_next_bkt can return, ascending.
@@ -203,8 +205,13 @@ int pvacb_ctx_create(int device, pvacb_ctx** out) {
     Ctx* ctx = new Ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PV_E_CUDA; }
-    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    auto fail = [&](const char* what) {
+        fprintf(stderr, "pvacb_ctx_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
+        pvacb_ctx_destroy(reinterpret_cast<pvacb_ctx*>(ctx));
+        return (int)PV_E_CUDA;
+    };
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) return fail("second stream");
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
@@ -212,16 +219,22 @@ int pvacb_ctx_create(int device, pvacb_ctx** out) {
     }
     AesTables t;
     aes_make_tables(t);
-    if (cudaMalloc((void**)&ctx->d_aes, sizeof(AesTables)) != cudaSuccess) { delete ctx; return PV_E_CUDA; }
-    cudaMemcpy(ctx->d_aes, &t, sizeof t, cudaMemcpyHostToDevice);
+    if (cudaMalloc((void**)&ctx->d_aes, sizeof(AesTables)) != cudaSuccess) return fail("cudaMalloc(AES tables)");
+    if (cudaMemcpy(ctx->d_aes, &t, sizeof t, cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy(AES tables)");
     std::vector<uint64_t> primes;
     build_prime_table(primes);
     ctx->n_primes = (int)primes.size();
-    cudaMalloc((void**)&ctx->d_primes, primes.size() * 8);
-    cudaMemcpy(ctx->d_primes, primes.data(), primes.size() * 8, cudaMemcpyHostToDevice);
-    cudaMalloc((void**)&ctx->d_work, 64);
+    if (cudaMalloc((void**)&ctx->d_primes, primes.size() * 8) != cudaSuccess) return fail("cudaMalloc(bucket-count table)");
+    if (cudaMemcpy(ctx->d_primes, primes.data(), primes.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return fail("cudaMemcpy(bucket-count table)");
+    if (cudaMalloc((void**)&ctx->d_work, 64) != cudaSuccess) return fail("cudaMalloc(work counter)");
     if (cudaHostAlloc((void**)&ctx->h_mail, SmallRead::kMaxWords * 4, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostGetDevicePointer((void**)&ctx->d_mail, ctx->h_mail, 0) != cudaSuccess) { delete ctx; return PV_E_CUDA; }
+        cudaHostGetDevicePointer((void**)&ctx->d_mail, ctx->h_mail, 0) != cudaSuccess) return fail("mapped mailbox");
+    // RNG tape: ChaCha20 under 256 fresh bits from the OS (pvacb_set_tape replaces kind / key)
+    if (pvacb_set_tape(reinterpret_cast<pvacb_ctx*>(ctx), PVACB_TAPE_CHACHA20, nullptr) != PV_OK) {
+        fprintf(stderr, "pvacb_ctx_create: the OS CSPRNG (getrandom) failed\n");
+        pvacb_ctx_destroy(reinterpret_cast<pvacb_ctx*>(ctx));
+        return PV_E_CUDA;
+    }
     *out = reinterpret_cast<pvacb_ctx*>(ctx);
     return PV_OK;
 }
@@ -230,15 +243,26 @@ void pvacb_ctx_destroy(pvacb_ctx* x) {
     if (!x) return;
     Ctx* ctx = C(x);
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->relay.device >= 0) {
+        cudaSetDevice(ctx->relay.device);
+        for (int s = 0; s < 2; s++) {
+            if (ctx->relay.stream[s]) { cudaStreamSynchronize(ctx->relay.stream[s]); cudaStreamDestroy(ctx->relay.stream[s]); }
+            if (ctx->relay.stage[s]) cudaFree(ctx->relay.stage[s]);
+        }
+        cudaSetDevice(ctx->device);
+    }
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);      // asynchronous exports still in flight
     for (cudaEvent_t e : ctx->export_events) cudaEventDestroy(e);
+    memset(ctx->tape_key, 0, sizeof ctx->tape_key);
+    cudaFree(ctx->d_tape_words);
     cudaFree(ctx->d_blob);
     cudaFree(ctx->d_aes);
     cudaFree(ctx->d_primes);
     cudaFree(ctx->d_work);
     cudaFree(ctx->d_ubk_perm);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
@@ -363,8 +387,7 @@ int pvacb_keys_adopt_blob(pvacb_ctx* x) {
     if (!ctx->d_blob) return PV_E_NOKEYS;
     ctx->h_hdr.resize(kBlobHdrWords);
     PV_CUDA(cudaMemcpy(ctx->h_hdr.data(), ctx->d_blob, kBlobHdrWords * 8, cudaMemcpyDeviceToHost));
-    derive_key_view(ctx);
-    return PV_OK;
+    return derive_key_view(ctx);
 }
 
 // ---- ops
@@ -413,7 +436,7 @@ int pvacb_enc_zero_depth(pvacb_ctx* x, size_t n, int depth_hint, uint64_t seed, 
 }
 int pvacb_plan_noise(int depth_hint, int* z2, int* z3) {
     if (!z2 || !z3) return PV_E_ARG;
-    plan_noise_host(depth_hint, *z2, *z3);
+    plan_noise_host(nullptr, depth_hint, *z2, *z3);
     return PV_OK;
 }
 static int binop(pvacb_ctx* x, const pvacb_batch* a, const pvacb_batch* b, int mode, pvacb_batch** out) {
@@ -587,40 +610,27 @@ int pvacb_batch_import_soa(pvacb_ctx* x, size_t n, const uint32_t* loff, const u
     cudaSetDevice(ctx->device);
     uint64_t nL = loff[n], nE = eoff[n];
     if (loff[0] != 0 || eoff[0] != 0) return PV_E_FORMAT;
-    // validation the kernels rely on (the reference would index out of bounds instead)
-    for (size_t i = 0; i < n; i++) {
+    for (size_t i = 0; i < n; i++)
         if (loff[i + 1] < loff[i] || eoff[i + 1] < eoff[i]) { ctx->last_error = "offsets not monotone"; return PV_E_FORMAT; }
-        uint32_t l = loff[i + 1] - loff[i];
-        for (uint32_t e = eoff[i]; e < eoff[i + 1]; e++) {
-            if (lid[e] >= l || idx[e] >= kB || ch[e] > 1) { ctx->last_error = "edge field out of range"; return PV_E_FORMAT; }
-            uint64_t hi = w[2 * e + 1], lo = w[2 * e];
-            if ((hi >> 63) || (hi == kMask63 && lo == ~0ull)) { ctx->last_error = "edge weight not canonical"; return PV_E_FORMAT; }
-        }
-        for (uint32_t k = loff[i]; k < loff[i + 1]; k++)
-            if (rule[k] > 1) { ctx->last_error = "unknown layer rule"; return PV_E_FORMAT; }
+    if ((nL && (!rule || !ztag || !nlo || !nhi)) || (nE && (!lid || !idx || !ch || !w))) {
+        ctx->last_error = "import_soa: a layer / edge array is NULL although the batch has layers / edges (only pa, pb and sigma may be omitted)";
+        return PV_E_ARG;
     }
     Batch* b = nullptr;
     int rc = batch_alloc(ctx, n, nL, nE, &b);
     if (rc) return rc;
-    auto cp = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
-        if (!bytes) return cudaSuccess;
-        if (!src) return cudaMemsetAsync(dst, 0, bytes, ctx->stream);
-        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t ce = cudaSuccess;
+    auto cp = [&](void* dst, const void* src, size_t bytes) {
+        if (!bytes || ce != cudaSuccess) return;
+        ce = src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaMemsetAsync(dst, 0, bytes, ctx->stream);
     };
-    PV_CUDA(cp(b->loff, loff, (n + 1) * 4));
-    PV_CUDA(cp(b->eoff, eoff, (n + 1) * 4));
-    PV_CUDA(cp(b->rule, rule, nL));
-    PV_CUDA(cp(b->ztag, ztag, nL * 8));
-    PV_CUDA(cp(b->nlo, nlo, nL * 8));
-    PV_CUDA(cp(b->nhi, nhi, nL * 8));
-    PV_CUDA(cp(b->pa, pa, nL * 4));
-    PV_CUDA(cp(b->pb, pbb, nL * 4));
-    PV_CUDA(cp(b->lid, lid, nE * 4));
-    PV_CUDA(cp(b->idx, idx, nE * 2));
-    PV_CUDA(cp(b->ch, ch, nE));
-    PV_CUDA(cp(b->w, w, nE * 16));
-    PV_CUDA(cp(b->sigma, sigma, nE * (size_t)kMWords * 8));
-    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    cp(b->loff, loff, (n + 1) * 4); cp(b->eoff, eoff, (n + 1) * 4);
+    cp(b->rule, rule, nL); cp(b->ztag, ztag, nL * 8); cp(b->nlo, nlo, nL * 8); cp(b->nhi, nhi, nL * 8); cp(b->pa, pa, nL * 4); cp(b->pb, pbb, nL * 4);
+    cp(b->lid, lid, nE * 4); cp(b->idx, idx, nE * 2); cp(b->ch, ch, nE); cp(b->w, w, nE * 16); cp(b->sigma, sigma, nE * (size_t)kMWords * 8);
+    if (ce != cudaSuccess) { batch_free(b); ctx->last_error = std::string("import_soa: ") + cudaGetErrorString(ce); return PV_E_CUDA; }
+    // validation the kernels rely on (the reference would index out of bounds instead): on the device, one launch + one
+    // synchronisation, which also completes the copies above
+    if ((rc = batch_validate(ctx, b))) { batch_free(b); return rc; }
     *out = reinterpret_cast<pvacb_batch*>(b);
     return PV_OK;
 }

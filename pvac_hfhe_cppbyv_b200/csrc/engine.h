@@ -22,8 +22,10 @@ namespace pvacb {
 //   [9..72]        lpn_s[64]
 //   [73..746]      powg_B[337] as (lo,hi)
 //   [747]          reserved (0)
-//   [748..]        H : 16384 columns x 128 words
-constexpr size_t kBlobHdrWords = 748;
+//   [748..749]     omega_B (lo,hi): computed by keygen and stored in the reference's pk files, read by no operation
+//   [750..751]     reserved (0)
+//   [752..]        H : 16384 columns x 128 words
+constexpr size_t kBlobHdrWords = 752;
 constexpr size_t kBlobWords = kBlobHdrWords + (size_t)kNBits * kMWords;
 constexpr size_t kBlobBytes = kBlobWords * 8;
 
@@ -47,6 +49,7 @@ struct Ctx {
     std::deque<cudaEvent_t> export_events;   // one per pvacb_batch_export_soa_async still to be waited for, in issue order
     int sm_count = 148;
     bool have_keys = false;
+    bool have_sk = false;            // false after a pk-only import: enc_* / dec_* refuse
     uint64_t* d_blob = nullptr;      // kBlobBytes
     AesTables* d_aes = nullptr;
     uint64_t* d_primes = nullptr;    // libstdc++ bucket-count table
@@ -60,20 +63,45 @@ struct Ctx {
     LpnMasks lpn_m{};                // the LPN secret as per-stream-word masks (prf_core.cuh)
     std::vector<uint64_t> h_hdr;     // host copy of the blob header
     int prf_mode = PRF_FAITHFUL;
+    // the run-time part of Params (core/types.hpp:36-70); everything else is compiled in (common.cuh) and checked by pvacb_keygen_params
+    double noise_entropy_bits = 120.0, tuple2_fraction = 0.55, depth_slope_bits = 16.0;
+    uint32_t edge_budget = kEdgeBudget;
+    int lpn_t = kLpnT;
+    double recrypt_lo = 0.48, recrypt_hi = 0.52;
+    int recrypt_rounds = 8;
+    // RNG tape (common.cuh): ChaCha20 under a key from the OS unless the caller chose otherwise (pvacb_set_tape)
+    int tape_kind = TAPE_CHACHA20;
+    uint32_t tape_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t item_base = 0;                 // global index of item 0 of the next calls (pvacb_set_item_base)
+    uint64_t seed_counter = 0;              // pvacb_fresh_seed
+    uint64_t* d_tape_words = nullptr;       // TAPE_WORDS: [tape_words_items][tape_words_per_item]
+    uint64_t tape_words_items = 0, tape_words_per_item = 0;
+    // test hook: keystream word `prf_patch_word` of every PRF core is OR-ed with `prf_patch_or` (forces AesCtr256::bounded's rejection branch)
+    uint64_t prf_patch_word = ~0ull, prf_patch_or = 0;
     std::string last_error;
     // statistics of the last call (for bench.py)
     uint64_t stat_kernel_launches = 0;
     uint64_t stat_aes_blocks = 0;
     uint64_t stat_sigma_edges = 0;
+    uint64_t stat_rare_prf_cores = 0;   // launches of the serial PRF slow path (bounded() rejections)
     int profile = 0;                 // when set, the dominant kernels are bracketed by CUDA events on ctx->stream
     struct ProfSpan { int tag; cudaEvent_t a, b; };
     std::vector<ProfSpan> prof_spans;
+    struct Relay {                   // exports leave through another GPU's host link (pvacb_set_export_relay)
+        int device = -1;
+        void* stage[2] = {nullptr, nullptr};
+        size_t cap[2] = {0, 0};
+        cudaStream_t stream[2] = {nullptr, nullptr};
+        unsigned next = 0;
+    } relay;
     bool lpn_attr_set = false;
+    bool mul_force_device_sort = false, mul_force_global_table = false;   // ct_mul planning: A/B switches for tests (pvacb_debug_set)
+    bool sigma_test_shape = false;          // sigma kernel shape without spare PRG candidates (exercises the in-kernel continuation)
     std::vector<const void*> configured_kernels;   // kernels whose per-device function attributes this context has set
 };
 
 // profiling tags (pvacb_profile_collect)
-enum : int { PROF_PRF_LPN = 0, PROF_UNUSED1 = 1, PROF_SIGMA = 2, PROF_CONCAT = 3, PROF_DEC_EDGES = 4, PROF_MUL_PLAN = 5, PROF_NTAGS = 8 };
+enum : int { PROF_PRF_LPN = 0, PROF_MUL_PAIRS = 1, PROF_SIGMA = 2, PROF_CONCAT = 3, PROF_DEC_EDGES = 4, PROF_MUL_PLAN = 5, PROF_NTAGS = 8 };
 struct ProfScope {
     Ctx* ctx; cudaEvent_t a = nullptr, b = nullptr; int tag;
     ProfScope(Ctx* c, int t) : ctx(c), tag(t) {
@@ -89,6 +117,7 @@ struct Batch {
     Ctx* ctx = nullptr;
     uint64_t n = 0;          // ciphertexts
     uint64_t nL = 0, nE = 0; // total layers / edges
+    uint64_t nL_alloc = 0;   // layer count the allocation was laid out for (compact_layers shrinks nL in place)
     void* base = nullptr;    // one allocation
     size_t bytes = 0;
     uint32_t* loff = nullptr;  // [n+1]
@@ -154,6 +183,8 @@ inline int check_owner(Ctx* ctx, const Batch* b) {
 int batch_alloc(Ctx* ctx, uint64_t n, uint64_t nL, uint64_t nE, Batch** out);
 void batch_free(Batch* b);
 int batch_clone(Ctx* ctx, const Batch* src, Batch** out);   // field-by-field device copy
+int batch_validate(Ctx* ctx, const Batch* b);                // boundary.cu: ranges / canonical weights of a batch that came from outside
+int keys_from_host_blob(Ctx* ctx, const uint64_t* blob);     // engine.cu: upload a host key blob and derive the key view
 
 // scratch allocator: stream-ordered
 int dev_alloc(Ctx* ctx, void** p, size_t bytes);
@@ -205,8 +236,10 @@ int scan_u32(Ctx* ctx, uint64_t n, const uint32_t* in, uint32_t* out);
 
 // ---- ops
 int op_enc_value(Ctx* ctx, const uint64_t* h_or_d_values, bool on_device, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, Batch** out, int depth_hint = 0, int shares = 2,
-                 uint64_t* h_draws = nullptr /* optional: tape words each item consumed */);
-void plan_noise_host(int depth_hint, int& z2, int& z3);
+                 uint64_t* h_next = nullptr /* optional out: first unused word of each item's tape */, const uint64_t* h_k0 = nullptr /* optional: first word to use */,
+                 const uint64_t* h_ids = nullptr /* optional: global item numbers (default item_base + i) */);
+int tape_spec(Ctx* ctx, Scratch& scratch, uint64_t n, uint64_t batch_seed, const uint64_t* h_states, const uint64_t* h_k0, const uint64_t* h_ids, TapeSpec& ts);
+void plan_noise_host(const Ctx* ctx, int depth_hint, int& z2, int& z3);   // ctx == nullptr: default Params
 int op_ct_add(Ctx* ctx, const Batch* A, const Batch* B, int mode /*0 add, 1 sub*/, Batch** out);
 int op_ct_scale(Ctx* ctx, const Batch* A, Fp s, Batch** out);
 int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, const uint64_t* h_states, Batch** out);
@@ -217,8 +250,9 @@ int batch_select(Ctx* ctx, const Batch* const* srcs, int nsrc, const std::vector
 int batch_concat(Ctx* ctx, const Batch* const* parts, size_t nparts, Batch** out);
 
 // compact_layers (ops/encrypt.hpp:73-104) of every ciphertext of b, in place (layer arrays shrink, edges stay).
-int compact_layers_batch(Ctx* ctx, Batch* b);
+// d_err / h_err (optional): one more device word fetched by the same mailbox read (saves the caller a synchronisation)
+int compact_layers_batch(Ctx* ctx, Batch* b, const unsigned int* d_err = nullptr, unsigned int* h_err = nullptr);
 // guard_budget (ops/encrypt.hpp:106-111): compact_edges on every ciphertext of *pb with more than edge_budget edges; may replace *pb
-int guard_budget_batch(Ctx* ctx, Batch** pb, uint32_t budget = kEdgeBudget);
+int guard_budget_batch(Ctx* ctx, Batch** pb, uint32_t budget);
 
 }  // namespace pvacb

@@ -38,7 +38,7 @@ __global__ void synth_meta_kernel(uint64_t n, int epl, uint64_t seed, uint32_t* 
     loff[i] = (uint32_t)(2 * i);
     eoff[i] = (uint32_t)(2 * epl * i);
     if (i == n) return;
-    Tape t{item_stream_state(seed, i), 0};
+    Tape t = tape_splitmix(item_stream_state(seed, i));     // benchmark data, not secret: always SplitMix64
     for (int l = 0; l < 2; l++) {
         uint64_t L = 2 * i + l;
         rule[L] = 0; nlo[L] = t.next(); nhi[L] = t.next(); ztag[L] = t.next(); pa[L] = 0; pb[L] = 0;
@@ -318,9 +318,14 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
     static const int kCtas[5] = {4, 8, 1, 2, 3};
     // PVACB_PROBE_SMEM=<bytes per CTA>: run the probe with that much dynamic shared memory (shrinks L1), to see whether the
     // gather ceiling depends on the L1 / shared-memory split the sigma kernel runs with
-    const int probe_smem = getenv("PVACB_PROBE_SMEM") ? atoi(getenv("PVACB_PROBE_SMEM")) : 0;
-    if (getenv("PVACB_PROBE_CARVEOUT")) {
-        const int pct = atoi(getenv("PVACB_PROBE_CARVEOUT"));
+#ifdef PVACB_TUNING
+    auto env = [](const char* k) -> const char* { return getenv(k); };
+#else
+    auto env = [](const char*) -> const char* { return nullptr; };       // the probe's tuning switches exist in a -DPVACB_TUNING build only
+#endif
+    const int probe_smem = env("PVACB_PROBE_SMEM") ? atoi(env("PVACB_PROBE_SMEM")) : 0;
+    if (env("PVACB_PROBE_CARVEOUT")) {
+        const int pct = atoi(env("PVACB_PROBE_CARVEOUT"));
         cudaFuncSetAttribute(l2_gather_probe_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(l2_gather_probe_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(l2_gather_probe_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -332,7 +337,7 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
         cudaFuncSetAttribute(l2_gather_probe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, probe_smem);
         cudaFuncSetAttribute(l2_gather_probe_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, probe_smem);
     }
-    const int nshapes = getenv("PVACB_PROBE_VERBOSE") ? 15 : 6;         // the first six shapes hold the maximum; the rest map the curve
+    const int nshapes = env("PVACB_PROBE_VERBOSE") ? 15 : 6;         // the first six shapes hold the maximum; the rest map the curve
     for (int sh = 0; sh < nshapes; sh++) {
         const int shape = sh < 6 ? sh : 2 * ((sh - 6) / 3) + 0;            // columns-in-flight index in shape / 2
         const int ctas_per_sm = sh < 6 ? ((sh & 1) ? 8 : 4) : kCtas[2 + (sh - 6) % 3];
@@ -340,7 +345,7 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
         const unsigned grid = (unsigned)ctx->sm_count * ctas_per_sm;
         for (int r = 0; r < reps + 2; r++) {
             cudaEventRecord(a, ctx->stream);
-            const int ld = getenv("PVACB_PROBE_LD") ? atoi(getenv("PVACB_PROBE_LD")) : 0;
+            const int ld = env("PVACB_PROBE_LD") ? atoi(env("PVACB_PROBE_LD")) : 0;
             if (ld == 1) l2_gather_probe_kernel<8, 1><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (ld == 2) l2_gather_probe_kernel<8, 2><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
             else if (ld == 3) l2_gather_probe_kernel<8, 3><<<grid, 256, probe_smem, ctx->stream>>>(H4, cols_per_warp, sink);
@@ -362,7 +367,7 @@ int pvacb_l2_gather_probe(pvacb_ctx* x, int reps, double* gbps_out) {
             if (r > 1 && g > best) best = g;
             if (r > 1 && g > shape_best) shape_best = g;
         }
-        if (getenv("PVACB_PROBE_VERBOSE")) fprintf(stderr, "l2 gather probe: %d columns in flight per warp%s, %d warps/SM: %.0f GB/s\n", 4 << (shape / 2), sh == 0 ? " (loop unrolled x4)" : "", ctas_per_sm * 8, shape_best);
+        if (env("PVACB_PROBE_VERBOSE")) fprintf(stderr, "l2 gather probe: %d columns in flight per warp%s, %d warps/SM: %.0f GB/s\n", 4 << (shape / 2), sh == 0 ? " (loop unrolled x4)" : "", ctas_per_sm * 8, shape_best);
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     dev_free(ctx, sink);

@@ -22,7 +22,16 @@ void ht_fp_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* o) {
     o[0] = r.lo; o[1] = r.hi;
 }
 void ht_fp_from_words(uint64_t lo, uint64_t hi, uint64_t* o) { Fp r = fp_from_words(lo, hi); o[0] = r.lo; o[1] = r.hi; }
-uint64_t ht_tape_word(uint64_t s0, uint64_t k) { return tape_word(s0, k); }
+uint64_t ht_tape_word(uint64_t s0, uint64_t k) { return splitmix_word(s0, k); }
+// word k of the ChaCha20 tape: key (8 x u32), stream id, lane
+uint64_t ht_chacha_word(const uint32_t* key, uint64_t sid, uint32_t lane, uint64_t k) {
+    TapeSpec ts; ts.kind = TAPE_CHACHA20; for (int i = 0; i < 8; i++) ts.key[i] = key[i];
+    ts.states = &sid;
+    Tape t = tape_open(ts, 0); t.lane = lane;
+    return t.at(k);
+}
+// the raw block function, for the RFC 8439 vector: key, words 12..15 -> 64 bytes
+void ht_chacha_block(const uint32_t* key, const uint32_t* c, uint64_t* out8) { chacha20_block(key, c[0], c[1], c[2], c[3], out8); }
 uint64_t ht_item_stream_state(uint64_t seed, uint64_t item) { return item_stream_state(seed, item); }
 uint64_t ht_fnv(int family, int t) { return t == 3 ? kFnvToep : fnv_prf_dom(family, t); }
 uint64_t ht_ztag(uint64_t canon, uint64_t nlo, uint64_t nhi) { return prg_layer_ztag(canon, nlo, nhi); }
@@ -111,36 +120,52 @@ void ht_prf_core(const uint64_t* prf_k, uint64_t canon, const uint8_t* digest, c
 }
 
 // plan of one enc_value item; flat dump per share: [value lo,hi, nlo, nhi, ztag, n_raw, n_out, then per raw edge: idx, ch, pos, first, salt]
-// and rnd values. Returns tape words consumed.
-uint64_t ht_plan_item(uint64_t s0, uint64_t v, uint64_t canon, int Z2, int Z3, uint64_t* hdr /*2 x 7*/, uint64_t* raw /*2 x kMaxRaw x 5*/,
-                      uint64_t* rnd /*2 x kMaxRnd x 2*/) {
+// and rnd values. Returns the number of tape words consumed. drop: optional 2 x kKeyWords words (slots compact_edges removes)
+constexpr int kHtMaxRaw = 64, kHtMaxRnd = 39;      // dump layout of these test entry points (depth hints up to 23)
+struct HtPlans {
     SharePlan P[2];
-    memset(P, 0, sizeof P);
-    uint64_t used = plan_item(s0, v, canon, Z2, Z3, P[0], P[1]);
+    std::vector<uint8_t> slab;
+    HtPlans(int Z2, int Z3) {
+        const int RAW = plan_raw_edges(Z2, Z3), RND = plan_rnd_values(Z2, Z3);
+        slab.assign(2 * plan_slab_bytes(RAW, RND), 0);
+        memset(P, 0, sizeof P);
+        for (int s = 0; s < 2; s++) plan_bind(P[s], slab.data() + s * plan_slab_bytes(RAW, RND), RAW, RND);
+    }
+};
+uint64_t ht_plan_item_ex(uint64_t s0, uint64_t v, uint64_t canon, int Z2, int Z3, const uint64_t* drop, uint64_t* hdr /*2 x 7*/, uint64_t* raw /*2 x kHtMaxRaw x 5*/,
+                         uint64_t* rnd /*2 x kHtMaxRnd x 2*/) {
+    if (plan_raw_edges(Z2, Z3) > kHtMaxRaw) return 0;
+    HtPlans H(Z2, Z3);
+    SharePlan* P = H.P;
+    Tape t = tape_splitmix(s0);
+    uint64_t used = plan_item(t, v, canon, Z2, Z3, P[0], P[1], drop);
     for (int s = 0; s < 2; s++) {
         uint64_t* h = hdr + 7 * s;
         h[0] = P[s].value.lo; h[1] = P[s].value.hi; h[2] = P[s].nlo; h[3] = P[s].nhi; h[4] = P[s].ztag; h[5] = P[s].n_raw; h[6] = P[s].n_out;
-        for (int r = 0; r < kMaxRaw; r++) {
-            uint64_t* e = raw + ((size_t)s * kMaxRaw + r) * 5;
+        for (uint32_t r = 0; r < P[s].n_raw; r++) {
+            uint64_t* e = raw + ((size_t)s * kHtMaxRaw + r) * 5;
             e[0] = P[s].idx[r]; e[1] = P[s].ch[r]; e[2] = P[s].pos[r]; e[3] = P[s].first[r]; e[4] = P[s].salt[r];
         }
-        for (int r = 0; r < kMaxRnd; r++) { rnd[((size_t)s * kMaxRnd + r) * 2] = P[s].rnd[r].lo; rnd[((size_t)s * kMaxRnd + r) * 2 + 1] = P[s].rnd[r].hi; }
+        for (int r = 0; r < plan_rnd_values(Z2, Z3); r++) { rnd[((size_t)s * kHtMaxRnd + r) * 2] = P[s].rnd[r].lo; rnd[((size_t)s * kHtMaxRnd + r) * 2 + 1] = P[s].rnd[r].hi; }
     }
     return used;
 }
-int ht_max_raw() { return kMaxRaw; }
-int ht_max_rnd() { return kMaxRnd; }
+uint64_t ht_plan_item(uint64_t s0, uint64_t v, uint64_t canon, int Z2, int Z3, uint64_t* hdr, uint64_t* raw, uint64_t* rnd) {
+    return ht_plan_item_ex(s0, v, canon, Z2, Z3, nullptr, hdr, raw, rnd);
+}
+int ht_max_raw() { return kHtMaxRaw; }
+int ht_max_rnd() { return kHtMaxRnd; }
 
-// weights of both shares of one item given the PRF values (prf: 2 x G x (lo,hi)); out: 2 x kMaxRaw x (lo,hi) per slot
+// weights of both shares of one item given the PRF values (prf: 2 x G x (lo,hi)); out: 2 x kHtMaxRaw x (lo,hi) per slot
 int ht_item_weights(uint64_t s0, uint64_t v, uint64_t canon, int Z2, int Z3, const uint64_t* prf, const uint64_t* powg, uint64_t* out) {
-    SharePlan P[2];
-    memset(P, 0, sizeof P);
-    plan_item(s0, v, canon, Z2, Z3, P[0], P[1]);
+    HtPlans H(Z2, Z3);
+    SharePlan* P = H.P;
+    Tape t = tape_splitmix(s0);
+    plan_item(t, v, canon, Z2, Z3, P[0], P[1]);
     int G = Z2 + Z3, ok = 1;
     for (int s = 0; s < 2; s++) {
-        Fp w[kMaxRaw];
-        ok &= share_weights(P[s], reinterpret_cast<const Fp*>(prf) + (size_t)s * G, reinterpret_cast<const Fp*>(powg), Z2, Z3, w) ? 1 : 0;
-        for (int p = 0; p < P[s].n_out; p++) { out[((size_t)s * kMaxRaw + p) * 2] = w[p].lo; out[((size_t)s * kMaxRaw + p) * 2 + 1] = w[p].hi; }
+        ok &= share_weights(P[s], reinterpret_cast<const Fp*>(prf) + (size_t)s * G, reinterpret_cast<const Fp*>(powg), Z2, Z3) == 0 ? 1 : 0;
+        for (uint32_t p = 0; p < P[s].n_out; p++) { out[((size_t)s * kHtMaxRaw + p) * 2] = P[s].wsum[p].lo; out[((size_t)s * kHtMaxRaw + p) * 2 + 1] = P[s].wsum[p].hi; }
     }
     return ok;
 }

@@ -80,9 +80,9 @@ Fp fp_pow_u128(Fp a, unsigned __int128 e) {
 
 }  // namespace
 
-int keygen_host(uint64_t tape_state, std::vector<uint64_t>& blob) {
+// the tape is either SplitMix64 from a 64-bit state (reference-parity vectors) or ChaCha20 keyed by a 256-bit seed (pvacb_keygen_params)
+int keygen_host(Tape& t, std::vector<uint64_t>& blob) {
     blob.assign(kBlobWords, 0);
-    Tape t{tape_state, 0};
     const uint64_t canon = t.next();
     blob[0] = canon;
     uint64_t* H = &blob[kBlobHdrWords];
@@ -124,10 +124,14 @@ int keygen_host(uint64_t tape_state, std::vector<uint64_t>& blob) {
     }
     for (;;) {   // omega_B, keygen.hpp:99-122: exponent truncated to 64 bits; B = 337 is prime so the first w != 1 is accepted
         Fp w = fp_pow_u128(rand_fp(), (unsigned __int128)(uint64_t)E);
-        if (!fp_eq(w, fp_one())) break;
+        if (!fp_eq(w, fp_one())) { blob[748] = w.lo; blob[749] = w.hi; break; }
     }
     for (int i = 0; i < kLpnWords; i++) blob[9 + i] = t.next();
     return PV_OK;
+}
+int keygen_host(uint64_t tape_state, std::vector<uint64_t>& blob) {
+    Tape t = tape_splitmix(tape_state);
+    return keygen_host(t, blob);
 }
 
 }  // namespace pvacb

@@ -20,6 +20,7 @@
 #include "sha256.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -44,34 +45,76 @@ __device__ __forceinline__ uint64_t next_bkt(const uint64_t* __restrict__ primes
     return primes[lo];
 }
 
-__global__ void mul_count_kernel(uint64_t n, const uint32_t* __restrict__ la, const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ea,
-                                 const uint32_t* __restrict__ eb, const uint64_t* __restrict__ primes, int np, uint32_t* __restrict__ c_lpre,
-                                 uint32_t* __restrict__ c_lp, uint32_t* __restrict__ c_keys, uint32_t* __restrict__ c_tbl, uint64_t* __restrict__ nb,
-                                 unsigned long long* __restrict__ max_pairs /*[0] max pairs, [1] sum keys, [2] sum table slots, [3] max keys, [4] max buckets*/,
-                                 unsigned int* __restrict__ err) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+struct MulShape { uint32_t lpre, lp, keys, tbl; uint64_t nb, pairs; bool bad; };
+__device__ __forceinline__ MulShape mul_shape(uint64_t i, const uint32_t* __restrict__ la, const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ea,
+                                              const uint32_t* __restrict__ eb, const uint64_t* __restrict__ primes, int np) {
+    MulShape m;
     uint64_t LA = la[i + 1] - la[i], LB = lb[i + 1] - lb[i], EA = ea[i + 1] - ea[i], EB = eb[i + 1] - eb[i];
     uint64_t lp = LA * LB, keys = lp * kB, pairs = EA * EB;
-    if (lp > 0xFFFFFFull || keys >= (1ull << 31) || pairs >= (1ull << 31)) { atomicOr(err, 1u); lp = keys = pairs = 0; }
-    c_lpre[i] = (uint32_t)(LA + LB + lp);
-    c_lp[i] = (uint32_t)lp;
-    c_keys[i] = (uint32_t)keys;
+    m.bad = lp > 0xFFFFFFull || keys >= (1ull << 31) || pairs >= (1ull << 31);
+    if (m.bad) lp = keys = pairs = 0;
+    m.lpre = (uint32_t)(LA + LB + lp); m.lp = (uint32_t)lp; m.keys = (uint32_t)keys; m.pairs = pairs;
     uint64_t present_max = keys < pairs ? keys : pairs;
     uint32_t t = 2;
     while (t < 2 * present_max) t <<= 1;
-    c_tbl[i] = present_max ? t : 0;
-    nb[i] = pairs ? next_bkt(primes, np, pairs) : 1;
-    atomicMax(max_pairs, (unsigned long long)pairs);
-    atomicAdd(max_pairs + 1, (unsigned long long)keys);
-    atomicAdd(max_pairs + 2, (unsigned long long)c_tbl[i]);
-    atomicMax(max_pairs + 3, (unsigned long long)keys);
-    atomicMax(max_pairs + 4, (unsigned long long)nb[i]);
+    m.tbl = present_max ? t : 0;
+    m.nb = pairs ? next_bkt(primes, np, pairs) : 1;
+    return m;
+}
+
+// Shapes of every pair, the four offset tables (exclusive scans) and the batch totals in ONE launch of one CTA: the totals go
+// straight to the host mailbox (mapped pinned memory), so the host needs a single stream synchronisation before it can size the
+// result. mail: [0] layers (pre-compaction), [1] layer pairs, [2] keys, [3] table slots, [4..5] max edge pairs, [6..7] sum keys,
+// [8..9] sum table slots, [10..11] max keys, [12..13] max buckets, [14] error bits.
+__global__ void __launch_bounds__(1024)
+mul_count_scan_kernel(uint64_t n, const uint32_t* __restrict__ la, const uint32_t* __restrict__ lb, const uint32_t* __restrict__ ea,
+                      const uint32_t* __restrict__ eb, const uint64_t* __restrict__ primes, int np, uint32_t* __restrict__ loP, uint32_t* __restrict__ lpoff,
+                      uint32_t* __restrict__ koff, uint32_t* __restrict__ toff, uint64_t* __restrict__ nb, volatile uint32_t* __restrict__ mail) {
+    __shared__ uint32_t p_lpre[1024], p_lp[1024], p_keys[1024], p_tbl[1024];
+    __shared__ unsigned long long s_stat[5];
+    __shared__ unsigned int s_err;
+    const int t = threadIdx.x;
+    if (t < 5) s_stat[t] = 0;
+    if (t == 0) s_err = 0;
+    __syncthreads();
+    const uint64_t per = (n + 1023) / 1024, b = (uint64_t)t * per, e = b + per < n ? b + per : n;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    unsigned long long mxp = 0, sk = 0, st = 0, mxk = 0, mxb = 0;
+    bool bad = false;
+    for (uint64_t i = b; i < e; i++) {
+        const MulShape m = mul_shape(i, la, lb, ea, eb, primes, np);
+        a0 += m.lpre; a1 += m.lp; a2 += m.keys; a3 += m.tbl;
+        bad |= m.bad;
+        mxp = max(mxp, (unsigned long long)m.pairs); sk += m.keys; st += m.tbl; mxk = max(mxk, (unsigned long long)m.keys); mxb = max(mxb, (unsigned long long)m.nb);
+    }
+    p_lpre[t] = a0; p_lp[t] = a1; p_keys[t] = a2; p_tbl[t] = a3;
+    if (b < e) {
+        atomicMax(&s_stat[0], mxp); atomicAdd(&s_stat[1], sk); atomicAdd(&s_stat[2], st); atomicMax(&s_stat[3], mxk); atomicMax(&s_stat[4], mxb);
+        if (bad) atomicOr(&s_err, 1u);
+    }
+    __syncthreads();
+    if (t < 4) {                       // four serial scans of 1024 partials, one per thread
+        uint32_t* part = t == 0 ? p_lpre : t == 1 ? p_lp : t == 2 ? p_keys : p_tbl;
+        uint32_t run = 0;
+        for (int k = 0; k < 1024; k++) { uint32_t v = part[k]; part[k] = run; run += v; }
+        (t == 0 ? loP : t == 1 ? lpoff : t == 2 ? koff : toff)[n] = run;
+        mail[t] = run;
+    }
+    __syncthreads();
+    if (t < 5) { mail[4 + 2 * t] = (uint32_t)s_stat[t]; mail[5 + 2 * t] = (uint32_t)(s_stat[t] >> 32); }
+    if (t == 5) mail[14] = s_err;
+    uint32_t r0 = p_lpre[t], r1 = p_lp[t], r2 = p_keys[t], r3 = p_tbl[t];
+    for (uint64_t i = b; i < e; i++) {
+        const MulShape m = mul_shape(i, la, lb, ea, eb, primes, np);
+        loP[i] = r0; lpoff[i] = r1; koff[i] = r2; toff[i] = r3; nb[i] = m.nb;
+        r0 += m.lpre; r1 += m.lp; r2 += m.keys; r3 += m.tbl;
+    }
+    __threadfence_system();
 }
 
 // one CTA per pair
 __global__ void __launch_bounds__(128)
-mul_layers_kernel(uint64_t n, uint64_t batch_seed, const uint64_t* __restrict__ states, uint64_t canon_tag, const uint32_t* __restrict__ loA, const uint32_t* __restrict__ loB,
+mul_layers_kernel(uint64_t n, const __grid_constant__ TapeSpec ts, uint64_t canon_tag, const uint32_t* __restrict__ loA, const uint32_t* __restrict__ loB,
                   const uint8_t* __restrict__ ruleA, const uint64_t* __restrict__ ztA, const uint64_t* __restrict__ nlA, const uint64_t* __restrict__ nhA,
                   const uint32_t* __restrict__ paA, const uint32_t* __restrict__ pbA, const uint8_t* __restrict__ ruleB, const uint64_t* __restrict__ ztB,
                   const uint64_t* __restrict__ nlB, const uint64_t* __restrict__ nhB, const uint32_t* __restrict__ paB, const uint32_t* __restrict__ pbB,
@@ -91,10 +134,11 @@ mul_layers_kernel(uint64_t n, uint64_t batch_seed, const uint64_t* __restrict__ 
         pa[o0 + LA + k] = paB[b0 + k] + off; pb[o0 + LA + k] = pbB[b0 + k] + off;
     }
     if (o0 + LA + LB + LA * LB != loP[i + 1]) return;   // shape overflow was flagged by mul_count_kernel
-    const uint64_t s0 = states ? states[i] : item_stream_state(batch_seed, i);
+    Tape tp = tape_open(ts, i);
+    const uint64_t w0 = tp.k;
     const uint32_t base = o0 + LA + LB, lp0 = lpoff[i];
     for (uint32_t lp = threadIdx.x; lp < LA * LB; lp += blockDim.x) {   // ops/arithmetic.hpp:59-70, row-major (la, lb)
-        uint64_t nlo = tape_word(s0, 2ull * lp), nhi = tape_word(s0, 2ull * lp + 1);
+        uint64_t nlo = tp.at(w0 + 2ull * lp), nhi = tp.at(w0 + 2ull * lp + 1);
         rule[base + lp] = 1;
         nl[base + lp] = nlo; nh[base + lp] = nhi;
         zt[base + lp] = prg_layer_ztag(canon_tag, nlo, nhi);
@@ -152,6 +196,7 @@ mul_pairs_kernel(EdgeView A, EdgeView Bv, const uint32_t* __restrict__ lp_item, 
     __shared__ Fp s_aw[kB * 2];          // a layer holds at most one edge per (idx, sign)
     __shared__ uint32_t s_ai[kB * 2];    // idx << 1 | sign
     __shared__ uint32_t s_aia[kB * 2];   // edge index inside the ciphertext
+    __shared__ uint32_t s_ndup;
     const uint32_t g = blockIdx.x;
     const uint32_t i = lp_item[g];
     const uint32_t lp = g - lpoff[i];
@@ -167,14 +212,29 @@ mul_pairs_kernel(EdgeView A, EdgeView Bv, const uint32_t* __restrict__ lp_item, 
         return;
     }
     for (int k = s; k < kB * 2; k += kPairThreads) s_ib[k] = kNone;
+    if (s == 0) s_ndup = 0;
     __syncthreads();
     const uint32_t ea0 = A.eoff[i], eb0 = Bv.eoff[i];
     for (uint32_t k = s; k < nB; k += kPairThreads) {
         uint32_t ib = Bv.order[eb0 + Bv.lstart[b_l] + k];
         uint32_t slot = (uint32_t)Bv.idx[eb0 + ib] * 2 + Bv.ch[eb0 + ib];
-        uint32_t old = atomicCAS(&s_ib[slot], kNone, ib);
-        if (old != kNone) atomicOr(err, 4u);          // two edges with equal (layer, idx, sign)
-        else s_w[slot] = Bv.w[eb0 + ib];
+        uint32_t old = atomicMin(&s_ib[slot], ib);    // the earliest edge of the slot decides its insertion times
+        if (old != kNone) atomicAdd(&s_ndup, 1u);     // two edges with equal (layer, idx, sign): legal in an imported ciphertext
+    }
+    __syncthreads();
+    for (uint32_t k = s; k < nB; k += kPairThreads) {
+        uint32_t ib = Bv.order[eb0 + Bv.lstart[b_l] + k];
+        uint32_t slot = (uint32_t)Bv.idx[eb0 + ib] * 2 + Bv.ch[eb0 + ib];
+        if (s_ib[slot] == ib) s_w[slot] = Bv.w[eb0 + ib];
+    }
+    if (s_ndup) {                                     // rare: the reference's map simply keeps adding (ops/arithmetic.hpp:79-88); sums are exact
+        __syncthreads();
+        if (s == 0)
+            for (uint32_t k = 0; k < nB; k++) {
+                uint32_t ib = Bv.order[eb0 + Bv.lstart[b_l] + k];
+                uint32_t slot = (uint32_t)Bv.idx[eb0 + ib] * 2 + Bv.ch[eb0 + ib];
+                if (s_ib[slot] != ib) s_w[slot] = fp_add(s_w[slot], Bv.w[eb0 + ib]);
+            }
     }
     const uint32_t npairs = nA * nB;
     if (nA <= kB * 2 && npairs <= kSparsePairs) {
@@ -403,7 +463,7 @@ __global__ void mul_emit_count_kernel(uint32_t nkeys, const uint32_t* __restrict
 }
 
 __global__ void mul_eoff_kernel(uint64_t n, const uint32_t* __restrict__ koff, const uint32_t* __restrict__ epos, uint32_t nkeys, uint32_t total,
-                                uint32_t* __restrict__ eoff, unsigned int* __restrict__ err) {
+                                uint32_t* __restrict__ eoff, uint32_t budget, unsigned int* __restrict__ err) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     uint32_t k = koff[i];
@@ -411,16 +471,16 @@ __global__ void mul_eoff_kernel(uint64_t n, const uint32_t* __restrict__ koff, c
     if (i < n) {
         uint32_t k1 = koff[i + 1];
         uint32_t e1 = (k1 >= nkeys) ? total : epos[k1];
-        if (e1 - eoff[i] > kEdgeBudget) atomicOr(err, 8u);
+        if (e1 - eoff[i] > budget) atomicOr(err, 8u);
     }
 }
 
-__global__ void mul_emit_kernel(uint32_t nkeys, uint64_t batch_seed, const uint64_t* __restrict__ states, const uint32_t* __restrict__ sval, const uint32_t* __restrict__ epos,
+__global__ void mul_emit_kernel(uint32_t nkeys, const __grid_constant__ TapeSpec ts, const uint32_t* __restrict__ sval, const uint32_t* __restrict__ epos,
                                 const uint32_t* __restrict__ k_item, const uint32_t* __restrict__ koff, const uint32_t* __restrict__ eoff,
                                 const uint32_t* __restrict__ loA, const uint32_t* __restrict__ loB, const uint32_t* __restrict__ loP,
                                 const uint8_t* __restrict__ k_flags, const Fp* __restrict__ k_wp, const Fp* __restrict__ k_wm,
                                 const uint32_t* __restrict__ k_tins, uint32_t* __restrict__ o_lid, uint16_t* __restrict__ o_idx, uint8_t* __restrict__ o_ch,
-                                Fp* __restrict__ o_w, uint64_t* __restrict__ salt, uint32_t* __restrict__ seed_idx) {
+                                Fp* __restrict__ o_w, uint64_t* __restrict__ salt, uint32_t* __restrict__ seed_idx, unsigned int* __restrict__ err) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nkeys) return;
     uint32_t k = sval[q];
@@ -430,68 +490,53 @@ __global__ void mul_emit_kernel(uint32_t nkeys, uint64_t batch_seed, const uint6
     uint32_t lp = rel / kB, s = rel % kB;
     uint32_t LA = loA[i + 1] - loA[i], LB = loB[i + 1] - loB[i];
     uint32_t lid = LA + LB + lp;
-    uint64_t s0 = states ? states[i] : item_stream_state(batch_seed, i);
+    Tape tp = tape_open(ts, i);
+    const uint64_t w0 = tp.k;
     uint32_t e = epos[q];
     uint8_t fl = k_flags[k];
     for (int sg = 0; sg < 2; sg++) {
         Fp w = sg ? k_wm[k] : k_wp[k];
         if (!(fl & (1 << sg)) || fp_is_zero(w)) continue;
         o_lid[e] = lid; o_idx[e] = (uint16_t)s; o_ch[e] = (uint8_t)sg; o_w[e] = w;
-        salt[e] = tape_word(s0, 2ull * LA * LB + (e - eoff[i]));      // salts follow the 2*LA*LB nonce words, in emission order
+        salt[e] = tp.at(w0 + 2ull * LA * LB + (e - eoff[i]));      // salts follow the 2*LA*LB nonce words, in emission order
         seed_idx[e] = loP[i] + lid;
         e++;
     }
+    if (tp.overrun) atomicOr(err, 16u);
 }
 
-#define MUL_ALLOC(ptr, bytes)                                   \
-    do {                                                        \
-        if ((rc = dev_alloc(ctx, (void**)&(ptr), (bytes)))) {   \
-            for (void* _p : scratch) dev_free(ctx, _p);         \
-            return rc;                                          \
-        }                                                       \
-        scratch.push_back((void*)(ptr));                        \
+#define MUL_ALLOC(ptr, bytes)                                  \
+    do {                                                       \
+        if ((rc = scratch.alloc(ptr, (bytes)))) return rc;     \
     } while (0)
 
 int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, const uint64_t* h_states, Batch** out) {
     const uint64_t n = A->n;
     int rc;
     if (n == 0) return batch_alloc(ctx, 0, 0, 0, out);
-    std::vector<void*> scratch;
-    auto cleanup = [&]() { for (void* p : scratch) dev_free(ctx, p); scratch.clear(); };
+    Scratch scratch(ctx);                 // every temporary is freed (stream-ordered) on every return path
 
-    uint32_t *c_lpre, *c_lp, *c_keys, *c_tbl, *loP, *lpoff, *koff, *toff;
+    uint32_t *loP, *lpoff, *koff, *toff;
     uint64_t* nb;
-    unsigned long long* max_pairs;
     unsigned int* err;
-    MUL_ALLOC(c_lpre, n * 4); MUL_ALLOC(c_lp, n * 4); MUL_ALLOC(c_keys, n * 4); MUL_ALLOC(c_tbl, n * 4);
     MUL_ALLOC(loP, (n + 1) * 4); MUL_ALLOC(lpoff, (n + 1) * 4); MUL_ALLOC(koff, (n + 1) * 4); MUL_ALLOC(toff, (n + 1) * 4);
-    MUL_ALLOC(nb, n * 8); MUL_ALLOC(max_pairs, 40); MUL_ALLOC(err, 4);
-    uint64_t* d_states = nullptr;
-    if (h_states) {
-        MUL_ALLOC(d_states, n * 8);
-        PV_CUDA(cudaMemcpyAsync(d_states, h_states, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    PV_CUDA(cudaMemsetAsync(max_pairs, 0, 40, ctx->stream));
+    MUL_ALLOC(nb, n * 8); MUL_ALLOC(err, 4);
+    TapeSpec ts;
+    if ((rc = tape_spec(ctx, scratch, n, batch_seed, h_states, nullptr, nullptr, ts))) return rc;
     PV_CUDA(cudaMemsetAsync(err, 0, 4, ctx->stream));
-    mul_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, A->loff, B->loff, A->eoff, B->eoff, ctx->d_primes, ctx->n_primes, c_lpre, c_lp,
-                                                                           c_keys, c_tbl, nb, max_pairs, err);
+    mul_count_scan_kernel<<<1, 1024, 0, ctx->stream>>>(n, A->loff, B->loff, A->eoff, B->eoff, ctx->d_primes, ctx->n_primes, loP, lpoff, koff, toff, nb, ctx->d_mail);
+    PV_CUDA(cudaGetLastError());
     ctx->stat_kernel_launches += 1;
-    if ((rc = scan_u32(ctx, n, c_lpre, loP)) || (rc = scan_u32(ctx, n, c_lp, lpoff)) || (rc = scan_u32(ctx, n, c_keys, koff)) ||
-        (rc = scan_u32(ctx, n, c_tbl, toff))) { cleanup(); return rc; }
-    uint32_t tot[4];
-    unsigned long long h_stats[5] = {0, 0, 0, 0, 0};
-    unsigned int h_err = 0;
-    {
-        SmallRead sr;
-        sr.add(&tot[0], loP + n, 4); sr.add(&tot[1], lpoff + n, 4); sr.add(&tot[2], koff + n, 4); sr.add(&tot[3], toff + n, 4);
-        sr.add(h_stats, max_pairs, 40); sr.add(&h_err, err, 4);
-        if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
-    }
-    if (h_err) { cleanup(); ctx->last_error = "ct_mul: operand too large for the batched path (layer pairs / keys / edge pairs overflow)"; return PV_E_SHAPE; }
-    const uint32_t nLpre = tot[0], nLP = tot[1], nKeys = tot[2], nTbl = tot[3];
+    PV_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint32_t mail[15];
+    memcpy(mail, ctx->h_mail, sizeof mail);
+    unsigned long long h_stats[5];
+    for (int k = 0; k < 5; k++) h_stats[k] = (unsigned long long)mail[4 + 2 * k] | ((unsigned long long)mail[5 + 2 * k] << 32);
+    unsigned int h_err = mail[14];
+    if (h_err) { ctx->last_error = "ct_mul: operand too large for the batched path (layer pairs / keys / edge pairs overflow)"; return PV_E_SHAPE; }
+    const uint32_t nLpre = mail[0], nLP = mail[1], nKeys = mail[2], nTbl = mail[3];
     const unsigned long long h_maxpairs = h_stats[0];
     if (h_stats[1] >= (1ull << 31) || h_stats[2] >= (1ull << 32)) {   // 32-bit offsets index the key space
-        cleanup();
         ctx->last_error = "ct_mul: batch too large (key space needs more than 2^31 slots); split it into smaller tiles";
         return PV_E_SHAPE;
     }
@@ -500,7 +545,7 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
     uint8_t* p_rule; uint64_t *p_zt, *p_nl, *p_nh; uint32_t *p_pa, *p_pb, *lp_item;
     MUL_ALLOC(p_rule, nLpre); MUL_ALLOC(p_zt, (size_t)nLpre * 8); MUL_ALLOC(p_nl, (size_t)nLpre * 8); MUL_ALLOC(p_nh, (size_t)nLpre * 8);
     MUL_ALLOC(p_pa, (size_t)nLpre * 4); MUL_ALLOC(p_pb, (size_t)nLpre * 4); MUL_ALLOC(lp_item, (size_t)(nLP ? nLP : 1) * 4);
-    mul_layers_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>(n, batch_seed, d_states, ctx->kv.canon_tag, A->loff, B->loff, A->rule, A->ztag, A->nlo, A->nhi, A->pa, A->pb,
+    mul_layers_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>(n, ts, ctx->kv.canon_tag, A->loff, B->loff, A->rule, A->ztag, A->nlo, A->nhi, A->pa, A->pb,
                                                             B->rule, B->ztag, B->nlo, B->nhi, B->pa, B->pb, loP, lpoff, p_rule, p_zt, p_nl, p_nh, p_pa, p_pb, lp_item);
     // ---- edges by layer
     uint32_t *lsA, *lcA, *curA, *ordA, *lsB, *lcB, *curB, *ordB;
@@ -521,22 +566,23 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
         MUL_ALLOC(k_item, (size_t)nKeys * 4); MUL_ALLOC(t_key, (size_t)(nTbl ? nTbl : 1) * 8); MUL_ALLOC(t_val, (size_t)(nTbl ? nTbl : 1) * 4);
         EdgeView VA{A->loff, A->eoff, A->idx, A->ch, A->w, lsA, lcA, ordA};
         EdgeView VB{B->loff, B->eoff, B->idx, B->ch, B->w, lsB, lcB, ordB};
-        mul_pairs_kernel<<<nLP, kPairThreads, 0, ctx->stream>>>(VA, VB, lp_item, lpoff, koff, k_wp, k_wm, k_flags, k_tins, err);
+        {
+            ProfScope ps(ctx, PROF_MUL_PAIRS);
+            mul_pairs_kernel<<<nLP, kPairThreads, 0, ctx->stream>>>(VA, VB, lp_item, lpoff, koff, k_wp, k_wm, k_flags, k_tins, err);
+        }
         const unsigned kb = (nKeys + 255) / 256;
         // ---- libstdc++ iteration order by radix sort
         int pbits = 1;
         while ((1ull << pbits) - 1 < h_maxpairs + 1) pbits++;
         int ibits = 1;
         while ((1ull << ibits) < n) ibits++;
-        if (2 * pbits + ibits > 64) { cleanup(); ctx->last_error = "ct_mul: sort key does not fit 64 bits (batch too large for these operand sizes)"; return PV_E_SHAPE; }
+        if (2 * pbits + ibits > 64) { ctx->last_error = "ct_mul: sort key does not fit 64 bits (batch too large for these operand sizes)"; return PV_E_SHAPE; }
         uint64_t *skey = nullptr, *skey2 = nullptr; uint32_t *sval = nullptr, *sval2, *ecnt, *epos;
         MUL_ALLOC(sval2, (size_t)nKeys * 4); MUL_ALLOC(ecnt, (size_t)nKeys * 4); MUL_ALLOC(epos, (size_t)nKeys * 4);
         size_t tmp_bytes = 0, tmp2 = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ecnt, epos, (int)nKeys, ctx->stream);
-        static const bool force_device_sort = getenv("PVACB_MUL_DEVICE_SORT") != nullptr;      // A/B switches for tuning runs and tests
-        static const bool force_global_table = getenv("PVACB_MUL_GLOBAL_TABLE") != nullptr;
-        const bool block_sort = !force_device_sort && h_stats[3] <= (unsigned long long)kBlockSortKeys && 2 * pbits + 1 <= 32;
-        const bool smem_table = block_sort && !force_global_table && h_stats[4] <= (unsigned long long)kSmemBuckets;
+        const bool block_sort = !ctx->mul_force_device_sort && h_stats[3] <= (unsigned long long)kBlockSortKeys && 2 * pbits + 1 <= 32;
+        const bool smem_table = block_sort && !ctx->mul_force_global_table && h_stats[4] <= (unsigned long long)kSmemBuckets;
         if (!smem_table) {
             // first-occupation time of every hash bucket in an open-addressing table in global memory
             PV_CUDA(cudaMemsetAsync(t_key, 0xFF, (size_t)(nTbl ? nTbl : 1) * 8, ctx->stream));
@@ -563,49 +609,45 @@ int op_ct_mul(Ctx* ctx, const Batch* A, const Batch* B, uint64_t batch_seed, con
         {
             SmallRead sr;
             sr.add(&last[0], epos + (nKeys - 1), 4); sr.add(&last[1], ecnt + (nKeys - 1), 4); sr.add(&h_err, err, 4);
-            if ((rc = read_small_sync(ctx, sr))) { cleanup(); return rc; }
+            if ((rc = read_small_sync(ctx, sr))) return rc;
         }
         // pairs, [bucket_insert], sort (block kernel, or sortkey + cub histogram, exclusive sum, one onesweep pass per 8 key bits), emit_count, cub scan (init + scan)
         ctx->stat_kernel_launches += 1 /* pairs */ + (smem_table ? 0 : 1) /* bucket_insert */ + 1 /* emit_count */ + 2 /* cub scan */ +
                                      (block_sort ? 1 : 1 + 2 + (uint64_t)((2 * pbits + ibits + 7) / 8)) /* block sort | sortkey + cub radix sort */;
-        if (h_err) {
-            cleanup();
-            if (h_err & 2) { ctx->last_error = "ct_mul: edge layer id out of range"; return PV_E_FORMAT; }
-            ctx->last_error = "ct_mul: operand holds two edges with equal (layer, idx, sign); the batched path needs compacted operands";
-            return PV_E_DUP_EDGE;
-        }
+        if (h_err & 2) { ctx->last_error = "ct_mul: edge layer id out of range"; return PV_E_FORMAT; }
         nEout = last[0] + last[1];
-        if ((rc = batch_alloc(ctx, n, nLpre, nEout, &o))) { cleanup(); return rc; }
-        MUL_ALLOC(salt, (size_t)(nEout ? nEout : 1) * 8);
-        MUL_ALLOC(seed_idx, (size_t)(nEout ? nEout : 1) * 4);
-        mul_eoff_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, koff, epos, nKeys, nEout, o->eoff, err);
-        mul_emit_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, batch_seed, d_states, sval2, epos, k_item, koff, o->eoff, A->loff, B->loff, loP, k_flags, k_wp, k_wm, k_tins,
-                                                     o->lid, o->idx, o->ch, o->w, salt, seed_idx);
+        if ((rc = batch_alloc(ctx, n, nLpre, nEout, &o))) return rc;
+        if ((rc = scratch.alloc(salt, (size_t)(nEout ? nEout : 1) * 8)) || (rc = scratch.alloc(seed_idx, (size_t)(nEout ? nEout : 1) * 4))) { batch_free(o); return rc; }
+        mul_eoff_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, koff, epos, nKeys, nEout, o->eoff, ctx->edge_budget, err);
+        mul_emit_kernel<<<kb, 256, 0, ctx->stream>>>(nKeys, ts, sval2, epos, k_item, koff, o->eoff, A->loff, B->loff, loP, k_flags, k_wp, k_wm, k_tins,
+                                                     o->lid, o->idx, o->ch, o->w, salt, seed_idx, err);
         ctx->stat_kernel_launches += 2;
     } else {
-        if ((rc = batch_alloc(ctx, n, nLpre, 0, &o))) { cleanup(); return rc; }
+        if ((rc = batch_alloc(ctx, n, nLpre, 0, &o))) return rc;
         PV_CUDA(cudaMemsetAsync(o->eoff, 0, (n + 1) * 4, ctx->stream));
     }
+    auto fail = [&](int code) { batch_free(o); return code; };
     // layers of the result (pre-compaction)
-    PV_CUDA(cudaMemcpyAsync(o->loff, loP, (n + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(o->rule, p_rule, nLpre, cudaMemcpyDeviceToDevice, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(o->ztag, p_zt, (size_t)nLpre * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(o->nlo, p_nl, (size_t)nLpre * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(o->nhi, p_nh, (size_t)nLpre * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(o->pa, p_pa, (size_t)nLpre * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    PV_CUDA(cudaMemcpyAsync(o->pb, p_pb, (size_t)nLpre * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    cudaError_t ce = cudaSuccess;
+    auto d2d = [&](void* dst, const void* src, size_t bytes) { if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream); };
+    d2d(o->loff, loP, (n + 1) * 4); d2d(o->rule, p_rule, nLpre); d2d(o->ztag, p_zt, (size_t)nLpre * 8); d2d(o->nlo, p_nl, (size_t)nLpre * 8);
+    d2d(o->nhi, p_nh, (size_t)nLpre * 8); d2d(o->pa, p_pa, (size_t)nLpre * 4); d2d(o->pb, p_pb, (size_t)nLpre * 4);
+    if (ce != cudaSuccess) { ctx->last_error = std::string("ct_mul: ") + cudaGetErrorString(ce); return fail(PV_E_CUDA); }
     // ---- sigma of every output edge, seeded by its PROD layer (pre-compaction tables)
     if (nEout) {
         SigmaJobs J;
         J.n = nEout; J.ztag = p_zt; J.nlo = p_nl; J.nhi = p_nh; J.seed_idx = seed_idx; J.idx = o->idx; J.ch = o->ch; J.salt = salt; J.out = o->sigma;
-        if ((rc = sigma_run(ctx, J))) { cleanup(); batch_free(o); return rc; }
+        if ((rc = sigma_run(ctx, J))) return fail(rc);
     }
-    { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) { cleanup(); batch_free(o); return rc; } }
-    cleanup();
-    if (h_err & 8) {   // guard_budget(pk, C, "mul") -> compact_edges, ops/arithmetic.hpp:103
-        if ((rc = guard_budget_batch(ctx, &o))) { batch_free(o); return rc; }
-    }
-    if ((rc = compact_layers_batch(ctx, o))) { batch_free(o); return rc; }
+    // guard_budget(pk, C, "mul") then compact_layers(C), ops/arithmetic.hpp:103-104. Only a batch with more than edge_budget edges
+    // in total can hold a ciphertext over the budget; otherwise the error bits of the kernels above ride along with the mailbox
+    // read compact_layers needs anyway (one synchronisation instead of two).
+    if (nEout > ctx->edge_budget) {
+        { SmallRead sr; sr.add(&h_err, err, 4); if ((rc = read_small_sync(ctx, sr))) return fail(rc); }
+        if ((h_err & 8) && (rc = guard_budget_batch(ctx, &o, ctx->edge_budget))) return fail(rc);
+        if ((rc = compact_layers_batch(ctx, o))) return fail(rc);
+    } else if ((rc = compact_layers_batch(ctx, o, err, &h_err))) return fail(rc);
+    if (h_err & 16) { ctx->last_error = "ct_mul: the supplied tape words (pvacb_set_tape_words) ran out"; return fail(PV_E_ARG); }
     *out = o;
     return PV_OK;
 }

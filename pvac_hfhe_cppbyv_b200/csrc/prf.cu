@@ -43,10 +43,14 @@ constexpr int kLpnThreads = 512;
 
 // rpc_log2: log2(row pairs evaluated per core): 13 (all 16384 rows, as the reference) or 6 (rows 0..127, the only ones
 // toep_127 can see). Persistent grid: one CTA per SM, static round-robin over units of kLpnThreads row pairs.
+// A noise word >= 2^64 - 8 makes AesCtr256::bounded draw again (crypto/lpn.hpp:141-148), which shifts every later word of that
+// core's stream by one: such a core is only FLAGGED here (rare_core) and recomputed serially by prf_lpn_serial_kernel.
+// PATCH: test hook, keystream word patch_word of every core is OR-ed with patch_or (the hot instantiation has none of it).
+template <bool PATCH>
 __global__ void __launch_bounds__(kLpnThreads, 1)
 prf_lpn_kernel(const uint32_t* __restrict__ gT0, const __grid_constant__ LpnMasks msk, uint64_t ncores, int rpc_log2,
                const uint32_t* __restrict__ rk_all, const uint64_t* __restrict__ ctr0_all, const uint8_t* __restrict__ flags,
-               uint64_t* __restrict__ ybits, unsigned int* __restrict__ rare_flag) {
+               uint64_t* __restrict__ ybits, unsigned int* __restrict__ rare_flag, uint8_t* __restrict__ rare_core, uint64_t patch_word, uint64_t patch_or) {
     extern __shared__ __align__(16) uint8_t sT[];
     aes_fill_rep_tables(sT, gT0);
     __syncthreads();
@@ -66,15 +70,50 @@ prf_lpn_kernel(const uint32_t* __restrict__ gT0, const __grid_constant__ LpnMask
         if (active) {
             AesCtrThread aes;
             aes.load_keys(rk_all + core * 60);
-            uint64_t ctr = __ldg(ctr0_all + core) + 65ull * rp;
+            const uint64_t c0 = __ldg(ctr0_all + core);
+            uint64_t ctr = c0 + 65ull * rp;
             aes.prime(sT, lane4, ctr);
             bool rare = false;
-            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) { aes.block(sT, lane4, c, w0, w1); }, ctr, msk, ye, yo, rare);
-            if (rare) atomicOr(rare_flag, 1u);
+            lpn_row_pair([&](uint64_t c, uint64_t& w0, uint64_t& w1) {
+                aes.block(sT, lane4, c, w0, w1);
+                if (PATCH && c - c0 == (patch_word >> 1)) { if (patch_word & 1) w1 |= patch_or; else w0 |= patch_or; }
+            }, ctr, msk, ye, yo, rare);
+            if (rare) { atomicOr(rare_flag, 1u); rare_core[core] = 1; }
         }
         uint32_t be = __ballot_sync(0xffffffffu, ye);
         uint32_t bo = __ballot_sync(0xffffffffu, yo);
         if (lane == 0 && active) ybits[slot >> 5] = spread_bits32(be) | (spread_bits32(bo) << 1);
+    }
+}
+
+// The flagged slow path: one thread per flagged core walks the keystream as the reference's word FIFO does (crypto/lpn.hpp:108-148,
+// 219-232) -- 64 words for the dot product, then bounded(8): words until one is < 2^64 - 8 -- and rewrites all of the core's y bits.
+__global__ void prf_lpn_serial_kernel(KeyView kv, const __grid_constant__ LpnMasks msk, uint64_t ncores, int rows, const uint8_t* __restrict__ rare_core,
+                                      const uint32_t* __restrict__ rk_all, const uint64_t* __restrict__ ctr0_all, uint64_t* __restrict__ ybits, int words_per_core,
+                                      uint64_t patch_word, uint64_t patch_or) {
+    const uint64_t core = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (core >= ncores || !rare_core[core]) return;
+    const uint32_t* rk = rk_all + core * 60;
+    uint64_t ctr = ctr0_all[core], nout = 0, buf1 = 0;
+    bool has = false;
+    auto next = [&]() -> uint64_t {
+        uint64_t x;
+        if (has) { has = false; x = buf1; }
+        else { uint64_t w0, w1; aes256_ctr_block(kv.T0, kv.sbox, rk, ctr++, w0, w1); buf1 = w1; has = true; x = w0; }
+        if (nout == patch_word) x |= patch_or;
+        nout++;
+        return x;
+    };
+    uint64_t* y = ybits + core * (uint64_t)words_per_core;
+    uint64_t word = 0;
+    for (int r = 0; r < rows; r++) {
+        uint64_t acc = 0;
+        for (int wi = 0; wi < kLpnWords; wi++) acc ^= next() & msk.e[wi];      // e[w] = s[w] for w < 64
+        uint64_t x;
+        do { x = next(); } while (x >= 0xFFFFFFFFFFFFFFF8ull);                 // lim = UINT64_MAX - UINT64_MAX % 8
+        const uint64_t bit = (uint64_t)((__popcll(acc) & 1) ^ ((x & 7ull) == 0ull ? 1 : 0));
+        word |= bit << (r & 63);
+        if ((r & 63) == 63 || r == rows - 1) { y[r >> 6] = word; word = 0; }
     }
 }
 
@@ -104,6 +143,7 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     uint32_t* rk = nullptr;
     uint64_t *ctr0 = nullptr, *top = nullptr, *ybits = nullptr;
     unsigned int* rare = nullptr;
+    uint8_t* rare_core = nullptr;
     int rc;
     if ((rc = scratch.alloc(rk, ncores * 60 * 4))) return rc;
     if ((rc = scratch.alloc(ctr0, ncores * 8))) return rc;
@@ -111,18 +151,24 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     if (d_ybits_out) ybits = d_ybits_out;
     else if ((rc = scratch.alloc(ybits, ncores * wpc * 8))) return rc;
     if ((rc = scratch.alloc(rare, 8))) return rc;                    // [0] rare-path flag, [1] active cores
+    if ((rc = scratch.alloc(rare_core, ncores))) return rc;
     PV_CUDA(cudaMemsetAsync(rare, 0, 8, ctx->stream));
+    PV_CUDA(cudaMemsetAsync(rare_core, 0, ncores, ctx->stream));
+    const bool patch = ctx->prf_patch_word != ~0ull;
 
     prf_setup_kernel<<<(unsigned)((ncores + 127) / 128), 128, 0, ctx->stream>>>(ctx->kv, ncores, d_ztag, d_nlo, d_nhi, d_flags, rk, ctr0, top, rare + 1);
     if (!ctx->lpn_attr_set) {
-        PV_CUDA(cudaFuncSetAttribute(prf_lpn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesRepBytes));
+        PV_CUDA(cudaFuncSetAttribute(prf_lpn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesRepBytes));
+        PV_CUDA(cudaFuncSetAttribute(prf_lpn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAesRepBytes));
         ctx->lpn_attr_set = true;
     }
     uint64_t units = ((ncores << rpc_log2) + kLpnThreads - 1) / kLpnThreads;
     unsigned grid = (unsigned)(units < (uint64_t)ctx->sm_count ? units : (uint64_t)ctx->sm_count);
     {
         ProfScope ps(ctx, PROF_PRF_LPN);
-        prf_lpn_kernel<<<grid, kLpnThreads, kAesRepBytes, ctx->stream>>>(ctx->kv.T0, ctx->lpn_m, ncores, rpc_log2, rk, ctr0, d_flags, ybits, rare);
+        if (patch) prf_lpn_kernel<true><<<grid, kLpnThreads, kAesRepBytes, ctx->stream>>>(ctx->kv.T0, ctx->lpn_m, ncores, rpc_log2, rk, ctr0, d_flags, ybits, rare, rare_core,
+                                                                                          ctx->prf_patch_word, ctx->prf_patch_or);
+        else prf_lpn_kernel<false><<<grid, kLpnThreads, kAesRepBytes, ctx->stream>>>(ctx->kv.T0, ctx->lpn_m, ncores, rpc_log2, rk, ctr0, d_flags, ybits, rare, rare_core, ~0ull, 0ull);
     }
     prf_finalize_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, ctx->stream>>>(njobs, d_flags, ybits, wpc, top, d_out);
     PV_CUDA(cudaGetLastError());
@@ -131,8 +177,14 @@ int prf_run(Ctx* ctx, uint64_t njobs, const uint64_t* d_ztag, const uint64_t* d_
     { SmallRead sr; sr.add(&h_rare, rare, 4); sr.add(&h_active, rare + 1, 4); if ((rc = read_small_sync(ctx, sr))) return rc; }
     ctx->stat_aes_blocks += (uint64_t)h_active * ((65ull << rpc_log2) + 1);
     if (h_rare) {
-        ctx->last_error = "AesCtr256::bounded rejection branch hit (p = 2^-61 per row); not supported on device";
-        return PV_E_RARE_PATH;
+        // AesCtr256::bounded rejected a noise word somewhere (p = 2^-61 per row): the flagged cores are walked again serially with
+        // the reference's word FIFO, then the (cheap) finalize step runs once more over everything
+        prf_lpn_serial_kernel<<<(unsigned)((ncores + 63) / 64), 64, 0, ctx->stream>>>(ctx->kv, ctx->lpn_m, ncores, 2 << rpc_log2, rare_core, rk, ctr0, ybits, wpc,
+                                                                                         ctx->prf_patch_word, ctx->prf_patch_or);
+        prf_finalize_kernel<<<(unsigned)((njobs + 127) / 128), 128, 0, ctx->stream>>>(njobs, d_flags, ybits, wpc, top, d_out);
+        PV_CUDA(cudaGetLastError());
+        ctx->stat_kernel_launches += 2;
+        ctx->stat_rare_prf_cores += 1;
     }
     return PV_OK;
 }

@@ -228,6 +228,17 @@ int op_ct_recrypt(Ctx* ctx, const Batch* in, const Batch* pool, uint64_t batch_s
     Batch* cur = nullptr;
     if ((rc = batch_clone(ctx, in, &cur))) return rc;
     std::vector<uint64_t> draws(n, 0);
+    TapeSpec ts;                            // the pool indices are drawn on the host, item i from word draws[i] of its stream
+    ts.kind = ctx->tape_kind;
+    for (int k = 0; k < 8; k++) ts.key[k] = ctx->tape_key[k];
+    ts.batch_seed = batch_seed; ts.item_base = ctx->item_base; ts.states = h_states;
+    std::vector<uint64_t> h_words;
+    if (ts.kind == TAPE_WORDS) {
+        if (!ctx->d_tape_words || ctx->item_base + n > ctx->tape_words_items) { ctx->last_error = "tape kind WORDS: no words supplied for these items"; return PV_E_ARG; }
+        h_words.resize(ctx->tape_words_items * ctx->tape_words_per_item);
+        PV_CUDA(cudaMemcpy(h_words.data(), ctx->d_tape_words, h_words.size() * 8, cudaMemcpyDeviceToHost));
+        ts.words = h_words.data(); ts.words_per_item = ctx->tape_words_per_item;
+    }
     auto needs = [&](uint64_t i) { double d = density_of(ones[i], ne[i]); return d < 0.495 || d > 0.505; };
     for (int it = 0; it < 8; it++) {
         std::vector<uint32_t> act;
@@ -238,8 +249,9 @@ int op_ct_recrypt(Ctx* ctx, const Batch* in, const Batch* pool, uint64_t batch_s
         std::vector<uint32_t> w0(act.size(), 0), w1(act.size(), 1), zi(act.size());
         for (size_t q = 0; q < act.size(); q++) {
             const uint64_t i = act[q];
-            const uint64_t s0 = h_states ? h_states[i] : item_stream_state(batch_seed, i);
-            zi[q] = (uint32_t)(tape_word(s0, draws[i]++) % pool->n);
+            Tape tp = tape_open(ts, i);
+            zi[q] = (uint32_t)(tp.at(draws[i]++) % pool->n);
+            if (tp.overrun) { batch_free(cur); ctx->last_error = "ct_recrypt: the supplied tape words ran out"; return PV_E_ARG; }
         }
         const Batch* srcs[2] = {cur, pool};
         Batch *ra = nullptr, *za = nullptr, *sum = nullptr, *perm = nullptr;
@@ -251,7 +263,7 @@ int op_ct_recrypt(Ctx* ctx, const Batch* in, const Batch* pool, uint64_t batch_s
         rc = op_ubk_apply(ctx, sum, &perm);
         batch_free(sum);
         if (rc) { batch_free(cur); return rc; }
-        if ((rc = guard_budget_batch(ctx, &perm))) { batch_free(cur); batch_free(perm); return rc; }
+        if ((rc = guard_budget_batch(ctx, &perm, ctx->edge_budget))) { batch_free(cur); batch_free(perm); return rc; }
         // put them back in place
         std::vector<uint32_t> which(n, 0), index(n);
         for (uint64_t i = 0; i < n; i++) index[i] = (uint32_t)i;

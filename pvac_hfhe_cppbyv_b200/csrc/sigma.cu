@@ -348,7 +348,9 @@ static int sigma_launch(Ctx* ctx, const SigmaJobs& J) {
         // ask for exactly the shared memory MINB CTAs need, not the maximum: with the 228 KB carve-out (28 KB of L1 left) the L2
         // gather ceiling drops from 19.9 to 16.3 TB/s (pvacb_l2_gather_probe under PVACB_PROBE_CARVEOUT, profiles/r01_notes.md)
         int carve = (int)(((size_t)MINB * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+#ifdef PVACB_TUNING
         if (getenv("PVACB_SIGMA_CARVEOUT")) carve = atoi(getenv("PVACB_SIGMA_CARVEOUT"));
+#endif
         PV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
         ctx->configured_kernels.push_back(kid);
     }
@@ -368,17 +370,23 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
     // shape (G edges per warp-group, warps per CTA, CTAs per SM). G*68 hashes should fill whole 32-lane rounds (G = 8: 17
     // rounds exactly, G = 5: 10.6); shared memory per warp = 2576 + 616 G bytes bounds the resident warps, and the total must
     // stay under ~196 KB per SM or the L2 gather ceiling drops by 18 % (see sigma_launch). Since the ALU trimming of round 1 the
-    // kernel fits 64 registers without spills and 32 resident warps beat 28 (7.02 vs 7.15 ms per 2^20 edges). PVACB_SIGMA_CFG picks another
-    // compiled shape for tuning runs. Small batches use groups of 2 edges so that more warps (and SMs) take part.
-    static int cfg = -1;
-    if (cfg < 0) {
+    // kernel fits 64 registers without spills and 32 resident warps beat 28 (7.02 vs 7.15 ms per 2^20 edges). Small batches use groups of 2 edges so that more warps (and SMs) take part.
+    // The other compiled shapes (the tuning history of profiles/r01_notes.md, two of which skip half the work and return WRONG
+    // syndromes) exist only in a -DPVACB_TUNING build (python -m pvac_hfhe_cppbyv_b200.build --tuning -> libpvacb_tuning.so).
+    int cfg = 0;
+#ifdef PVACB_TUNING
+    static int env_cfg = -1;
+    if (env_cfg < 0) {
         const char* e = getenv("PVACB_SIGMA_CFG");
-        cfg = e ? atoi(e) : 0;
+        env_cfg = e ? atoi(e) : 0;
     }
-    if (cfg == 40) rc = sigma_launch<5, 4, 8, true, 0, 4, 32>(ctx, J);   // test shape: no spare candidates, the PRG continuation runs for ~3 of 4 edges
+    cfg = env_cfg;
+#endif
+    if (ctx->sigma_test_shape) rc = sigma_launch<5, 4, 8, true, 0, 4, 32>(ctx, J);   // test shape (pvacb_debug_set): no spare candidates, the PRG continuation runs for ~3 of 4 edges
     else if (J.n < (uint64_t)ctx->sm_count * 8 * 4 * 5) rc = sigma_launch<2, 4, 8, true, 0, 4>(ctx, J);
     else switch (cfg) {
         default: rc = sigma_launch<5, 4, 8, true, 0, 4>(ctx, J); break;   // 32 warps/SM at 64 registers, 183 KB of shared memory: L1 keeps 45 KB
+#ifdef PVACB_TUNING
         case 1: rc = sigma_launch<8, 4, 6, true, 0, 4>(ctx, J); break;    // 24 warps/SM, exact 17-round groups
         case 2: rc = sigma_launch<6, 4, 7, true, 0, 4>(ctx, J); break;    // 28 warps/SM at 72 registers (the default before the ALU trimming)
         case 3: rc = sigma_launch<8, 4, 7, true, 0, 4>(ctx, J); break;    // 28 warps/SM but 217 KB shared: the slow L1 split
@@ -389,6 +397,7 @@ int sigma_run(Ctx* ctx, const SigmaJobs& J) {
         case 9: rc = sigma_launch<8, 4, 6, true, 0, 8>(ctx, J); break;    // 24 warps/SM, 16 loads in flight per lane
         case 21: rc = sigma_launch<5, 4, 8, true, 1, 4>(ctx, J); break;   // experiment: no gather loads (wrong results)
         case 22: rc = sigma_launch<5, 4, 8, true, 2, 4>(ctx, J); break;   // experiment: no hashing (wrong results)
+#endif
     }
     if (rc) return rc;
     PV_CUDA(cudaGetLastError());

@@ -99,39 +99,38 @@ int pvacb_enc_text(pvacb_ctx* x, const uint8_t* bytes, const uint64_t* msg_off, 
         if (msg_off[m + 1] < msg_off[m]) return PV_E_ARG;
         max_blocks = std::max(max_blocks, (size_t)((msg_off[m + 1] - msg_off[m] + 14) / 15));
     }
-    if (max_blocks > 22) { ctx->last_error = "enc_text: messages longer than 330 bytes need depth hints above 23 (not built in)"; return PV_E_ARG; }
     std::vector<Batch*> waves;
     auto fail = [&](int rc) { for (Batch* b : waves) batch_free(b); return rc; };
     // wave 0: enc_value(length)
-    std::vector<uint64_t> state(n), lens(n), draws(n);
-    for (size_t m = 0; m < n; m++) {
-        state[m] = tape_states ? tape_states[m] : item_stream_state(batch_seed, m);
-        lens[m] = msg_off[m + 1] - msg_off[m];
-    }
+    // every message walks ONE tape stream (its item's): a wave starts each message at the word the previous wave stopped at
+    std::vector<uint64_t> lens(n), next(n, 0);
+    for (size_t m = 0; m < n; m++) lens[m] = msg_off[m + 1] - msg_off[m];
     Batch* b = nullptr;
-    int rc = op_enc_value(ctx, lens.data(), false, n, 0, state.data(), &b, 0, 2, draws.data());
+    int rc = op_enc_value(ctx, lens.data(), false, n, batch_seed, tape_states, &b, 0, 2, next.data());
     if (rc) return fail(rc);
     waves.push_back(b);
-    for (size_t m = 0; m < n; m++) state[m] += draws[m] * 0x9E3779B97F4A7C15ull;
     // waves 1..: block j of every message that has one, enc_fp_depth(pack15, 2 + j)
-    std::vector<uint64_t> vals, st, dr;
+    std::vector<uint64_t> vals, st, k0, ids, dr;
     std::vector<size_t> who;
+    const uint64_t base = ctx->item_base;
     for (size_t j = 0; j < max_blocks; j++) {
-        vals.clear(); st.clear(); who.clear();
+        vals.clear(); st.clear(); who.clear(); k0.clear(); ids.clear();
         for (size_t m = 0; m < n; m++) {
             if (lens[m] <= 15 * j) continue;
             uint64_t lo, hi;
             pack15(bytes + msg_off[m] + 15 * j, (size_t)std::min<uint64_t>(15, lens[m] - 15 * j), lo, hi);
             vals.push_back(lo); vals.push_back(hi);
-            st.push_back(state[m]);
+            if (tape_states) st.push_back(tape_states[m]);
+            k0.push_back(next[m]);
+            ids.push_back(base + m);
             who.push_back(m);
         }
         dr.assign(who.size(), 0);
         b = nullptr;
-        rc = op_enc_value(ctx, vals.data(), false, who.size(), 0, st.data(), &b, 2 + (int)j, 1, dr.data());
+        rc = op_enc_value(ctx, vals.data(), false, who.size(), batch_seed, tape_states ? st.data() : nullptr, &b, 2 + (int)j, 1, dr.data(), k0.data(), ids.data());
         if (rc) return fail(rc);
         waves.push_back(b);
-        for (size_t q = 0; q < who.size(); q++) state[who[q]] += dr[q] * 0x9E3779B97F4A7C15ull;
+        for (size_t q = 0; q < who.size(); q++) next[who[q]] = dr[q];
     }
     std::vector<const Batch*> parts(waves.begin(), waves.end());
     Batch* o = nullptr;

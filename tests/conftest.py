@@ -102,7 +102,15 @@ def api():
 @pytest.fixture(scope="session")
 def engine():
     from pvac_hfhe_cppbyv_b200 import api
-    eng = api.Engine(device=0, prf_mode=api.PRF_LIVE)
+    # the SplitMix64 tape: what the committed golden vectors and the oracle's default streams are defined on
+    eng = api.Engine(device=0, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX)
     eng.keygen(1)
+    dbg = os.environ.get("PVACB_TEST_DEBUG", "")          # bit-exact test shapes of the library (pvacb_debug_set), chosen by the tests that re-run others
+    if dbg == "sigma_test_shape":
+        eng.debug_set(2, 1)
+    elif dbg == "mul_device_sort":
+        eng.debug_set(0, 1, 0)
+    elif dbg == "mul_global_table":
+        eng.debug_set(0, 0, 1)
     yield eng
     eng.close()

@@ -64,7 +64,7 @@ def test_keygen_matches_reference(engine, kat):
 @pytest.fixture(scope="module")
 def synth_engine(api, synth_keys_raw):
     r = synth_keys_raw
-    eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL)
+    eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL, tape=api.TAPE_SPLITMIX)
     eng.import_keys(r["canon_tag"], r["H_digest"], None, None, r["prf_k"], r["lpn_s"])
     yield eng
     eng.close()
@@ -684,7 +684,7 @@ def test_two_contexts_in_one_process(engine, api):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    e1 = api.Engine(device=1, prf_mode=api.PRF_LIVE)
+    e1 = api.Engine(device=1, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX)
     try:
         b0 = torch.empty(api.KEY_BLOB_BYTES, dtype=torch.uint8, device="cuda:0")
         engine.copy_key_blob_to(b0.data_ptr())
@@ -709,13 +709,13 @@ def test_two_contexts_in_one_process(engine, api):
 def test_prg_continuation_path():
     """The sigma kernel computes 34 counter hashes per label up front (136 candidates for 128 picks); a label with more than 8
     duplicates continues the PRG stream inside the kernel -- about once per 10^8 labels, so ordinary runs never get there.
-    PVACB_SIGMA_CFG=40 selects a shape with NO spare candidates (32 hashes), which sends ~3 of 4 edges through that
-    continuation; the golden / oracle comparisons must still hold bit for bit. (The shape is chosen once per process, hence the
-    subprocess.)"""
+    pvacb_debug_set(ctx, 2, 1) selects a shape with NO spare candidates (32 hashes), which sends ~3 of 4 edges through that
+    continuation; the golden / oracle comparisons must still hold bit for bit. (conftest's engine fixture applies the switch named
+    by PVACB_TEST_DEBUG to the session engine, hence the subprocess.)"""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PVACB_SIGMA_CFG="40")
+    env = dict(os.environ, PVACB_TEST_DEBUG="sigma_test_shape")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k",
                         "sigma_from_H or enc_value_golden or mul_golden or mul_chain_golden or chain10 or enc_value_vs_oracle"],
                        capture_output=True, text=True, env=env, cwd=root, timeout=800)
@@ -785,16 +785,16 @@ def test_no_device_memory_growth(engine):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("switch", ["PVACB_MUL_DEVICE_SORT", "PVACB_MUL_GLOBAL_TABLE"])
+@pytest.mark.parametrize("switch", ["mul_device_sort", "mul_global_table"])
 def test_mul_planning_fallback_paths(switch):
     """ct_mul orders the keys of a ciphertext pair (libstdc++'s unordered_map iteration order) inside one CTA when the pair is small
     -- keys and bucket table in shared memory -- and with a device-wide radix sort / a global bucket table otherwise. Fresh
-    operands never reach the fallbacks, so the golden / oracle ct_mul cases are run again with each fallback forced (the
-    switches are read once per process, hence the subprocess)."""
+    operands never reach the fallbacks, so the golden / oracle ct_mul cases are run again with each fallback forced
+    (pvacb_debug_set(ctx, 0, ...), applied by conftest's engine fixture from PVACB_TEST_DEBUG, hence the subprocess)."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, **{switch: "1"})
+    env = dict(os.environ, PVACB_TEST_DEBUG=switch)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k",
                         "mul_golden or mul_chain_golden or mul_vs_oracle_batch or ct_fuzz_random_circuits"],
                        capture_output=True, text=True, env=env, cwd=root, timeout=800)

@@ -186,7 +186,7 @@ def test_aes_and_prf_core(ht, port, kat, synth_keys_raw):
 
 def test_keygen_host(ht):
     g = load_npz("keys_seed1.npz")
-    words = 748 + 16384 * 128
+    words = 752 + 16384 * 128
     blob = np.zeros(words, np.uint64)
     assert ht.ht_keygen(1, _p(blob), words) == 0
     assert int(blob[0]) == int(g["canon_tag"])

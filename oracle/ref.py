@@ -100,6 +100,7 @@ def lib():
         "ref_ct_export": (None, [vp, P(u8), P(u64), P(u64), P(u64), P(u32), P(u32), P(u32), P(u16), P(u8), P(u64), P(u64)]),
         "ref_ct_import": (vp, [u32, u32, u32, P(u8), P(u64), P(u64), P(u64), P(u32), P(u32), P(u32), P(u16), P(u8), P(u64), P(u64)]),
         "ref_bench": (C.c_double, [vp, i32, i32, i32, u64, P(u64)]),
+        "ref_bench_chain": (None, [vp, i32, i32, u64, P(C.c_double), P(C.c_double), P(u64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -334,6 +335,12 @@ class Keys:
         o = np.zeros(2, np.uint64)
         lib().ref_dec_value(self.h, c, _p(o, C.c_uint64))
         return o
+
+    def bench_chain(self, threads, steps, seed=1):
+        """test_depth's chain c <- c*c on every thread: -> (mul seconds per step, dec seconds per step, edges per step), slowest thread"""
+        m, d, e = np.zeros(steps, np.float64), np.zeros(steps, np.float64), np.zeros(steps, np.uint64)
+        lib().ref_bench_chain(self.h, threads, steps, seed, _p(m, C.c_double), _p(d, C.c_double), _p(e, C.c_uint64))
+        return m, d, e
 
     def bench(self, op, threads, iters, seed=1):
         done = C.c_uint64()

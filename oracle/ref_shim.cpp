@@ -429,7 +429,8 @@ void* ref_ct_import(uint32_t nL, uint32_t nE, uint32_t m_bits, const uint8_t* ru
 }
 
 // ---------------------------------------------------------------- CPU baseline (bench.py --impl reference / cpu_baseline)
-// op: 0 enc_value, 1 ct_add, 2 ct_sub, 3 ct_mul (fresh x fresh), 4 dec_value (fresh), 5 dec_value (fresh x fresh product)
+// op: 0 enc_value, 1 ct_add, 2 ct_sub, 3 ct_mul (fresh x fresh), 4 dec_value (fresh), 5 dec_value (fresh x fresh product),
+//     11 commit_ct (fresh), 12 commit_ct (product), 13 compact_edges (product), 14 ct_recrypt (fresh, pool of 4), 15 enc_text (100 bytes)
 // Runs `iters` operations on each of `threads` std::threads (independent items, thread-local tape) and
 // returns elapsed seconds of the slowest thread; *ops_done = threads*iters.
 double ref_bench(void* h, int op, int threads, int iters, uint64_t seed, uint64_t* ops_done) {
@@ -445,7 +446,10 @@ double ref_bench(void* h, int op, int threads, int iters, uint64_t seed, uint64_
             Cipher a = enc_value(k->pk, k->sk, 1000 + t);
             Cipher b = enc_value(k->pk, k->sk, 77 + t);
             Cipher p;
-            if (op == 5) p = ct_mul(k->pk, a, b);
+            if (op == 5 || op == 12 || op == 13) p = ct_mul(k->pk, a, b);
+            EvalKey ek;
+            if (op == 14) ek = make_evalkey(k->pk, k->sk, 4, 0);
+            const std::string msg(100, 'x');
             ready++;
             while (!go.load()) std::this_thread::yield();
             auto t0 = std::chrono::steady_clock::now();
@@ -458,6 +462,11 @@ double ref_bench(void* h, int op, int threads, int iters, uint64_t seed, uint64_
                     case 3: { Cipher c = ct_mul(k->pk, a, b); sink += c.E.size(); break; }
                     case 4: { Fp r = dec_value(k->pk, k->sk, a); sink += r.lo; break; }
                     case 5: { Fp r = dec_value(k->pk, k->sk, p); sink += r.lo; break; }
+                    case 11: { auto d = commit_ct(k->pk, a); sink += d[0]; break; }
+                    case 12: { auto d = commit_ct(k->pk, p); sink += d[0]; break; }
+                    case 13: { Cipher c = p; compact_edges(k->pk, c); sink += c.E.size(); break; }
+                    case 14: { Cipher c = ct_recrypt(k->pk, ek, a); sink += c.E.size(); break; }
+                    case 15: { auto v = enc_text(k->pk, k->sk, msg); sink += v.size(); break; }
                 }
             }
             auto t1 = std::chrono::steady_clock::now();
@@ -471,6 +480,41 @@ double ref_bench(void* h, int op, int threads, int iters, uint64_t seed, uint64_
     for (double s : secs) mx = s > mx ? s : mx;
     *ops_done = (uint64_t)threads * (uint64_t)iters;
     return mx;
+}
+
+
+// tests/test_depth.cpp:44-72 on every thread at once: c0 = enc(2), then c <- c*c for `steps` steps, timing each ct_mul and each
+// dec_value separately. mul_s[s] / dec_s[s] = elapsed seconds of the slowest thread for step s + 1; edges[s] = edges of that product.
+void ref_bench_chain(void* h, int threads, int steps, uint64_t seed, double* mul_s, double* dec_s, uint64_t* edges) {
+    Keys* k = (Keys*)h;
+    ref_init();
+    std::vector<std::vector<double>> tm(threads, std::vector<double>(steps, 0.0)), td(threads, std::vector<double>(steps, 0.0));
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+        th.emplace_back([&, t]() {
+            g_tape_state = item_stream_state(seed, (uint64_t)t);
+            g_tape_draws = 0;
+            Cipher c = enc_value(k->pk, k->sk, 2);
+            Fp expect = fp_from_u64(2);
+            for (int s = 0; s < steps; s++) {
+                auto t0 = std::chrono::steady_clock::now();
+                c = ct_mul(k->pk, c, c);
+                auto t1 = std::chrono::steady_clock::now();
+                Fp d = dec_value(k->pk, k->sk, c);
+                auto t2 = std::chrono::steady_clock::now();
+                expect = fp_mul(expect, expect);
+                if (d.lo != expect.lo || d.hi != expect.hi) std::abort();
+                tm[t][s] = std::chrono::duration<double>(t1 - t0).count();
+                td[t][s] = std::chrono::duration<double>(t2 - t1).count();
+                if (t == 0) edges[s] = c.E.size();
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    for (int s = 0; s < steps; s++) {
+        mul_s[s] = dec_s[s] = 0;
+        for (int t = 0; t < threads; t++) { mul_s[s] = std::max(mul_s[s], tm[t][s]); dec_s[s] = std::max(dec_s[s], td[t][s]); }
+    }
 }
 
 }  // extern "C"

@@ -7,6 +7,8 @@
 //      sigma -- in the structure-of-arrays layout this stage is a pure HBM stream.
 #include "engine.h"
 
+#include <algorithm>
+
 namespace pvacb {
 
 // thread per ciphertext; R[] holds prf_R for BASE layers and 0 elsewhere on entry
@@ -51,7 +53,13 @@ __device__ __forceinline__ Fp warp_sum_fp(Fp v) {
     return v;
 }
 
-// WARPS_PER_ITEM == 0: one warp per ciphertext (small ciphertexts); otherwise one CTA of 256 threads per ciphertext
+// Edge stage: acc = sum_e +- w_e g^idx_e Rinv[layer_e]. Integer-pipe bound, not HBM bound (ncu r02: 23 B per edge against two
+// 128-bit modular products): so the work per edge is ONE reduced product (w g^idx, then its sign) and one UNREDUCED 256-bit
+// multiply-accumulate with Rinv into a 320-bit accumulator per thread (fp_mac_wide), reduced once at the end.
+// kBlockPerItem == false: one warp per ciphertext (small ciphertexts). kBlockPerItem == true: grid (ciphertext, slice); a CTA walks
+// chunks slice, slice + gridDim.y, ... of 256 x kDecEdgesPerThread edges of its ciphertext and leaves one partial sum per (ciphertext, slice),
+// so that a few very large ciphertexts (depth-3 products: 172 544 edges) still fill the machine; dec_partials_kernel adds them.
+constexpr int kDecChunk = 256 * 8;
 template <bool kBlockPerItem>
 __global__ void __launch_bounds__(256)
 dec_edges_kernel(uint64_t n, const uint32_t* __restrict__ loff, const uint32_t* __restrict__ eoff, const uint32_t* __restrict__ lid,
@@ -63,16 +71,22 @@ dec_edges_kernel(uint64_t n, const uint32_t* __restrict__ loff, const uint32_t* 
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t item = kBlockPerItem ? (uint64_t)blockIdx.x : (uint64_t)blockIdx.x * 8 + wid;
-    Fp acc = fp_zero();
+    uint64_t wide[5] = {0, 0, 0, 0, 0};
     if (item < n) {
-        uint32_t l0 = loff[item], e0 = eoff[item], E = eoff[item + 1] - e0;
-        uint32_t start = kBlockPerItem ? threadIdx.x : lane, step = kBlockPerItem ? 256 : 32;
-        for (uint32_t e = start; e < E; e += step) {
-            Fp term = fp_mul(fp_mul(w[e0 + e], s_g[idx[e0 + e]]), Rinv[l0 + lid[e0 + e]]);
-            acc = ch[e0 + e] == 0 ? fp_add(acc, term) : fp_sub(acc, term);
+        const uint32_t l0 = loff[item], e0 = eoff[item], E = eoff[item + 1] - e0;
+        auto edge = [&](uint32_t e) {
+            Fp t = fp_mul(w[e0 + e], s_g[idx[e0 + e]]);
+            if (ch[e0 + e]) t = fp_neg(t);
+            fp_mac_wide(wide, t, Rinv[l0 + lid[e0 + e]]);
+        };
+        if (kBlockPerItem) {
+            for (uint32_t c = blockIdx.y * kDecChunk; c < E; c += gridDim.y * kDecChunk)
+                for (uint32_t e = c + threadIdx.x; e < min(E, c + (uint32_t)kDecChunk); e += 256) edge(e);
+        } else {
+            for (uint32_t e = lane; e < E; e += 32) edge(e);
         }
     }
-    acc = warp_sum_fp(acc);
+    Fp acc = warp_sum_fp(fp_wide_reduce(wide));
     if (!kBlockPerItem) {
         if (lane == 0 && item < n) out[item] = acc;
     } else {
@@ -81,9 +95,16 @@ dec_edges_kernel(uint64_t n, const uint32_t* __restrict__ loff, const uint32_t* 
         if (threadIdx.x == 0) {
             Fp t = s_part[0];
             for (int k = 1; k < 8; k++) t = fp_add(t, s_part[k]);
-            out[item] = t;
+            out[item * gridDim.y + blockIdx.y] = t;
         }
     }
+}
+__global__ void dec_partials_kernel(uint64_t n, uint32_t slices, const Fp* __restrict__ part, Fp* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp t = part[i * slices];
+    for (uint32_t k = 1; k < slices; k++) t = fp_add(t, part[i * slices + k]);
+    out[i] = t;
 }
 
 // ---- BASE layers with equal seeds share one PRF evaluation. The reference memoises by layer id, so c*c (every seed twice),
@@ -162,13 +183,27 @@ int op_dec_value(Ctx* ctx, const Batch* Cb, uint64_t* h_out) {
         dec_inv_kernel<<<(unsigned)((Cb->nL + 127) / 128), 128, 0, ctx->stream>>>(Cb->nL, R, Rinv);
         ctx->stat_kernel_launches += 2;
     }
-    bool block_per_item = Cb->nE / Cb->n > 256;
+    const bool block_per_item = Cb->nE / Cb->n > 256;
+    uint32_t slices = 1;
+    Fp* part = res;
+    if (block_per_item) {
+        // enough CTAs for the whole machine even when the batch holds a handful of huge ciphertexts; a ciphertext with more chunks than
+        // slices is walked in a loop
+        const uint64_t avg_chunks = (Cb->nE / Cb->n + kDecChunk - 1) / kDecChunk;
+        const uint64_t want = ((uint64_t)ctx->sm_count * 8 + Cb->n - 1) / Cb->n;
+        slices = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(avg_chunks, want), 1024));
+        if (slices > 1 && (rc = scratch.alloc(part, Cb->n * (uint64_t)slices * 16))) return rc;
+    }
     {
     ProfScope ps(ctx, PROF_DEC_EDGES);
     if (block_per_item)
-        dec_edges_kernel<true><<<(unsigned)Cb->n, 256, 0, ctx->stream>>>(Cb->n, Cb->loff, Cb->eoff, Cb->lid, Cb->idx, Cb->ch, Cb->w, ctx->kv.powg, Rinv, res);
+        dec_edges_kernel<true><<<dim3((unsigned)Cb->n, slices), 256, 0, ctx->stream>>>(Cb->n, Cb->loff, Cb->eoff, Cb->lid, Cb->idx, Cb->ch, Cb->w, ctx->kv.powg, Rinv, part);
     else
         dec_edges_kernel<false><<<(unsigned)((Cb->n + 7) / 8), 256, 0, ctx->stream>>>(Cb->n, Cb->loff, Cb->eoff, Cb->lid, Cb->idx, Cb->ch, Cb->w, ctx->kv.powg, Rinv, res);
+    }
+    if (slices > 1) {
+        dec_partials_kernel<<<(unsigned)((Cb->n + 127) / 128), 128, 0, ctx->stream>>>(Cb->n, slices, part, res);
+        ctx->stat_kernel_launches += 1;
     }
     ctx->stat_kernel_launches += 1;
     PV_CUDA(cudaGetLastError());

@@ -43,6 +43,13 @@ PV_HD Fp fp_neg(const Fp& a) {
 // core/field.hpp:69-71
 PV_HD Fp fp_sub(const Fp& a, const Fp& b) { return fp_add(a, fp_neg(b)); }
 
+// value of a 320-bit accumulator mod p: 2^128 = 2, 2^256 = 4
+PV_HD Fp fp_wide_reduce(const uint64_t acc[5]) {
+    const Fp x = fp_from_words(acc[0], acc[1]), y = fp_from_words(acc[2], acc[3]), z = fp_from_words(acc[4], 0);
+    const Fp y2 = fp_add(y, y), z2 = fp_add(z, z);
+    return fp_add(fp_add(x, y2), fp_add(z2, z2));
+}
+
 PV_HD void mul64wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
 #if defined(__CUDA_ARCH__)
     lo = a * b;
@@ -54,40 +61,39 @@ PV_HD void mul64wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
 #endif
 }
 
-// core/field.hpp:113-213 : 2x2 schoolbook product (256 bits), two Mersenne folds, canonicalise.
-// Inputs must be canonical (< 2^127), which every value produced by this engine is.
+// core/field.hpp:113-213 : 2x2 schoolbook product (256 bits), Mersenne folds, canonicalise. Inputs must be canonical (< 2^127),
+// which every value produced by this engine is. Written on unsigned __int128 (nvcc lowers it to IMAD.WIDE.U32 carry chains: 87
+// instructions against 110 for the round-1 form with explicit carry compares). With a = a0 + 2^64 a1, b likewise and 2^127 = 1:
+//   a b = p00 + 2^64 mid + 2^128 p11,  mid = a0 b1 + a1 b0 < 2^128 (the high limbs are < 2^63)
+//       = (p00 mod 2^127) + (p00 >> 127) + 2^64 (mid_lo mod 2^63) + (mid_lo >> 63) + 2 mid_hi + 2 p11   (mod p)
+typedef unsigned __int128 pv_u128;
 PV_HD Fp fp_mul(const Fp& a, const Fp& b) {
-    uint64_t p00l, p00h, p01l, p01h, p10l, p10h, p11l, p11h;
-    mul64wide(a.lo, b.lo, p00l, p00h);
-    mul64wide(a.lo, b.hi, p01l, p01h);
-    mul64wide(a.hi, b.lo, p10l, p10h);
-    mul64wide(a.hi, b.hi, p11l, p11h);
-    uint64_t z0 = p00l;
-    // z1 = p00h + p01l + p10l (carry c1 in 0..2)
-    uint64_t z1 = p00h + p01l;
-    uint64_t c1 = (z1 < p00h) ? 1ull : 0ull;
-    uint64_t t = z1 + p10l;
-    c1 += (t < z1) ? 1ull : 0ull;
-    z1 = t;
-    // z2 = p01h + p10h + p11l + c1
-    uint64_t z2 = p01h + p10h;
-    uint64_t c2 = (z2 < p01h) ? 1ull : 0ull;
-    t = z2 + p11l;
-    c2 += (t < z2) ? 1ull : 0ull;
-    z2 = t;
-    t = z2 + c1;
-    c2 += (t < z2) ? 1ull : 0ull;
-    z2 = t;
-    uint64_t z3 = p11h + c2;
-    // value = L + 2^127 * H with L = low 127 bits, H = bits 127..253 (< 2^127 for canonical inputs)
-    uint64_t l0 = z0, l1 = z1 & kMask63;
-    uint64_t h0 = (z1 >> 63) | (z2 << 1);
-    uint64_t h1 = (z2 >> 63) | (z3 << 1);
-    uint64_t s0 = l0 + h0;
-    uint64_t s1 = l1 + h1 + ((s0 < l0) ? 1ull : 0ull);   // < 2^64: l1,h1 < 2^63
-    return fp_from_words(s0, s1);                          // L + H < 2^128 ; fold bit 127 and canonicalise
+    const pv_u128 M127 = (((pv_u128)kMask63) << 64) | ~0ull;
+    const pv_u128 p00 = (pv_u128)a.lo * b.lo, p11 = (pv_u128)a.hi * b.hi;
+    const pv_u128 mid = (pv_u128)a.lo * b.hi + (pv_u128)a.hi * b.lo;
+    const uint64_t ml = (uint64_t)mid, mh = (uint64_t)(mid >> 64);
+    pv_u128 s1 = (p00 & M127) + ((pv_u128)(ml & kMask63) << 64);                    // < 2^128
+    pv_u128 s2 = ((p11 + mh) << 1) + (uint64_t)(p00 >> 127) + (ml >> 63);           // < 2^127 + 2^65 + 2
+    s1 = (s1 & M127) + (uint64_t)(s1 >> 127);                                       // <= 2^127 - 1
+    s2 = (s2 & M127) + (uint64_t)(s2 >> 127);                                       // <= 2^127
+    const pv_u128 r = s1 + s2;                                                      // < 2^128: fold bit 127 and canonicalise
+    return fp_from_words((uint64_t)r, (uint64_t)(r >> 64));
 }
 
+// acc (320 bits, little-endian 64-bit limbs) += a * b as a plain 256-bit integer product: no reduction at all. dec_value's edge sum
+// multiplies every edge by the (reduced) inverse of its layer key this way and reduces once per thread.
+PV_HD void fp_mac_wide(uint64_t acc[5], const Fp& a, const Fp& b) {
+    const pv_u128 p00 = (pv_u128)a.lo * b.lo, p01 = (pv_u128)a.lo * b.hi, p10 = (pv_u128)a.hi * b.lo, p11 = (pv_u128)a.hi * b.hi;
+    pv_u128 t = (pv_u128)acc[0] + (uint64_t)p00;
+    acc[0] = (uint64_t)t;
+    t = (t >> 64) + acc[1] + (uint64_t)(p00 >> 64) + (uint64_t)p01 + (uint64_t)p10;
+    acc[1] = (uint64_t)t;
+    t = (t >> 64) + acc[2] + (uint64_t)(p01 >> 64) + (uint64_t)(p10 >> 64) + (uint64_t)p11;
+    acc[2] = (uint64_t)t;
+    t = (t >> 64) + acc[3] + (uint64_t)(p11 >> 64);
+    acc[3] = (uint64_t)t;
+    acc[4] += (uint64_t)(t >> 64);
+}
 PV_HD Fp fp_sqr_n(Fp a, int n) {
     for (int i = 0; i < n; i++) a = fp_mul(a, a);
     return a;

@@ -1,0 +1,475 @@
+"""GPU parity tests of the round-2 additions, through the C ABI (libpvacb.so) against the oracle (and the unmodified reference where it
+travels as oracle/_ref): the ChaCha20 tape, caller-supplied tape words and the compact_edges drop path, the serial slow path of the PRF
+for AesCtr256::bounded rejections, faithful-mode enc / dec against the lpn_t = 16384 oracle, Params, key files, whole-batch blobs,
+the multi-GPU group."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ct_equal
+
+from oracle import ref as _ref
+
+pytestmark = pytest.mark.gpu
+
+P127 = (1 << 127) - 1
+KEY = bytes(range(32))
+
+
+def fpv(x):
+    return int(x[0]) | (int(x[1]) << 64)
+
+
+@pytest.fixture()
+def chacha_engine(api):
+    eng = api.Engine(device=0, prf_mode=api.PRF_LIVE, tape=api.TAPE_CHACHA20, tape_key=KEY)
+    eng.keygen(1)
+    yield eng
+    eng.close()
+
+
+def test_default_tape_is_keyed_and_fresh(api):
+    """a context draws from ChaCha20 under a key from the OS: two contexts, same seed -> different ciphertexts; one context, no seed
+    given -> every call on fresh streams"""
+    e1, e2 = api.Engine(0, prf_mode=api.PRF_LIVE), api.Engine(0, prf_mode=api.PRF_LIVE)
+    try:
+        assert e1.L.pvacb_get_tape(e1.h) == api.TAPE_CHACHA20
+        e1.keygen(1); e2.keygen(1)
+        v = np.array([5, 6], np.uint64)
+        a, b = e1.export_soa(e1.enc_value(v, 123)), e2.export_soa(e2.enc_value(v, 123))
+        assert not np.array_equal(a["nlo"], b["nlo"]) and not np.array_equal(a["sigma"], b["sigma"])
+        c, d = e1.export_soa(e1.enc_value(v)), e1.export_soa(e1.enc_value(v))
+        assert not np.array_equal(c["nlo"], d["nlo"])
+        assert [fpv(x) for x in e1.dec_value(e1.enc_value(v))] == [5, 6]
+        assert e1.fresh_seed() != e1.fresh_seed()
+    finally:
+        e1.close(); e2.close()
+
+
+def test_chacha_tape_vs_oracle(chacha_engine, api, port, port_keys):
+    """enc_value / ct_mul / enc_text / dec under the ChaCha20 tape: batch-seed streams (lane = global item + 1, item base included) and
+    explicit stream ids (lane 0), every byte against the oracle under the same key"""
+    eng, K = chacha_engine, port_keys
+    vals = np.array([42, 2**64 - 1, 0, 7, 99], np.uint64)
+    try:
+        for base in (0, 1000):
+            eng.set_item_base(base)
+            A, Bv = eng.enc_value(vals, 555), eng.enc_value(vals[::-1].copy(), 556)
+            Pm = eng.ct_mul(A, Bv, 557)
+            eng.set_item_base(0)
+            ga, gp = api.split_items(eng.export_soa(A)), api.split_items(eng.export_soa(Pm))
+            dec = eng.dec_value(Pm)
+            for i in range(len(vals)):
+                port.set_tape(1, KEY, base + i + 1)
+                oa, ob = K.enc_value(555, int(vals[i])), K.enc_value(556, int(vals[::-1][i]))
+                ok, f = ct_equal(ga[i], port.ct_export(oa))
+                assert ok, (base, i, f)
+                ok, f = ct_equal(gp[i], port.ct_export(K.ct_mul(557, oa, ob)))
+                assert ok, (base, i, "mul", f)
+                assert fpv(dec[i]) == int(vals[i]) * int(vals[::-1][i]) % P127
+        # explicit stream ids
+        ids = np.array([0xDEADBEEF, 2**64 - 1, 3], np.uint64)
+        X = eng.enc_value(vals[:3], tape_states=ids)
+        gx = api.split_items(eng.export_soa(X))
+        port.set_tape(1, KEY, 0)
+        for i in range(3):
+            ok, f = ct_equal(gx[i], port.ct_export(K.enc_value(int(ids[i]), int(vals[i]))))
+            assert ok, (i, f)
+        # the text codec continues one stream per message across its waves
+        msgs = [b"hello world, more than one block", b"", b"x" * 31]
+        T = eng.enc_text(msgs, 600)
+        got = api.split_items(eng.export_soa(T))
+        pos = len(msgs)
+        want = []
+        for i, m in enumerate(msgs):
+            port.set_tape(1, KEY, i + 1)
+            want.append([port.ct_export(c) for c in K.enc_text(600, m)])
+        for i in range(len(msgs)):
+            assert ct_equal(got[i], want[i][0])[0]
+        for j in range(3):
+            for i, m in enumerate(msgs):
+                if (len(m) + 14) // 15 > j:
+                    ok, f = ct_equal(got[pos], want[i][1 + j])
+                    assert ok, (i, j, f)
+                    pos += 1
+        assert eng.dec_text(T, len(msgs)) == msgs
+    finally:
+        port.set_tape(0)
+
+
+def test_tape_words_and_compact_edges_drop_path(api, port, port_keys):
+    """caller-supplied tape words; with words crafted so that a merged edge of the first-drawn share has weight 0 AND syndrome 0 the
+    engine takes its flagged slow path (re-plan with the slot removed) and returns the reference's bytes (oracle pinned on the
+    unmodified reference for exactly these words in tests/test_round2_cpu.py). Ordinary items in the same batch are untouched."""
+    from test_round2_cpu import drop_words
+    eng = api.Engine(0, prf_mode=api.PRF_LIVE, tape=api.TAPE_WORDS)
+    try:
+        eng.keygen(1)
+        rng = np.random.default_rng(3)
+        plain = [rng.integers(0, 2**64, 440, dtype=np.uint64) for _ in range(3)]
+        words = np.stack([plain[0], drop_words(5, 100, 1)[:440], plain[1], drop_words(7, 336, 1)[:440], plain[2]])
+        vals = np.array([11, 22, 33, 44, 55], np.uint64)
+        eng.set_tape_words(words)
+        st0 = eng.stats()["kernel_launches"]
+        X = eng.enc_value(vals, 0)
+        got = api.split_items(eng.export_soa(X))
+        for i in range(5):
+            port.set_tape(2, words=words[i])
+            ok, f = ct_equal(got[i], port.ct_export(port_keys.enc_value(0, int(vals[i]))))
+            assert ok, (i, f)
+        assert len(got[1]["lid"]) < len(got[0]["lid"]) + 2 and [fpv(x) for x in eng.dec_value(X)] == [11, 22, 33, 44, 55]
+        assert eng.stats()["kernel_launches"] - st0 > 25          # the second pass ran
+        # too few words: refused, never zero-filled
+        eng.set_tape_words(words[:, :100])
+        with pytest.raises(api.PvacbError):
+            eng.enc_value(vals, 0)
+        # ct_mul under supplied words
+        eng.set_tape_words(words)
+        A, Bv = eng.enc_value(vals[:1], 0), eng.enc_value(vals[:1] + 1, 0)
+        mw = rng.integers(0, 2**64, (1, 1500), dtype=np.uint64)
+        eng.set_tape_words(mw)
+        Pm = eng.ct_mul(A, Bv, 0)
+        port.set_tape(2, words=words[0])
+        oa, ob = port_keys.enc_value(0, 11), port_keys.enc_value(0, 12)
+        port.set_tape(2, words=mw[0])
+        ok, f = ct_equal(api.split_items(eng.export_soa(Pm))[0], port.ct_export(port_keys.ct_mul(0, oa, ob)))
+        assert ok, f
+    finally:
+        port.set_tape(0)
+        eng.close()
+
+
+def test_prf_bounded_rejection_slow_path(engine, api, port, port_keys):
+    """AesCtr256::bounded draws again when a noise word is >= 2^64 - 8 (crypto/lpn.hpp:141-148, p = 2^-61 per row), which shifts the rest
+    of that core's keystream by one word. A keystream patch (pvacb_debug_set / the oracle's orc_set_prf_patch) forces it: rejected noise
+    word of a live row (output changes), of a dead row (only the y bits change), two rejections in a row; live and faithful mode."""
+    K = port_keys
+    rng = np.random.default_rng(17)
+    zt, lo, hi = (rng.integers(0, 2**64, 5, dtype=np.uint64) for _ in range(3))
+    plain = engine.prf(zt, lo, hi)
+    doms = ["pvac.prf.r.1", "pvac.prf.r.2", "pvac.prf.r.3"]
+    try:
+        for word, mask in ((64, 0xFFFFFFFFFFFFFFF8), (65 * 5 + 64, 2**64 - 1), (65 * 126 + 64, 0xFFFFFFFFFFFFFFF8), (65 * 200 + 64, 0xFFFFFFFFFFFFFFF8)):
+            engine.debug_set(1, word, mask)
+            port.set_prf_patch(word, mask)
+            for mode, rows in ((api.PRF_LIVE, 128), (api.PRF_FAITHFUL, 16384)):
+                if rows == 128 and word >= 65 * 128:
+                    continue
+                engine.set_prf_mode(mode)
+                K.set_lpn_t(rows if rows == 16384 else 128)
+                got, yb = engine.prf(zt[:2], lo[:2], hi[:2], want_ybits=True)
+                for i in range(2):
+                    assert np.array_equal(got[i], K.prf_R(int(zt[i]), int(lo[i]), int(hi[i]))), (word, mode, i)
+                    for t in range(3):
+                        want_y = K.lpn_make_ybits(int(zt[i]), int(lo[i]), int(hi[i]), doms[t], rows)
+                        assert np.array_equal(yb[3 * i + t], want_y), (word, mode, i, t)
+                if word < 65 * 64:
+                    assert not np.array_equal(got, plain[:2])            # the shift moves dozens of live rows: visible in the output
+        # and through enc_value / dec_value: every PRF core of the item takes the slow path
+        engine.set_prf_mode(api.PRF_LIVE)
+        K.set_lpn_t(127)
+        engine.debug_set(1, 64, 0xFFFFFFFFFFFFFFF8)
+        port.set_prf_patch(64, 0xFFFFFFFFFFFFFFF8)
+        X = engine.enc_value(np.array([31337], np.uint64), tape_states=[4711])
+        ok, f = ct_equal(api.split_items(engine.export_soa(X))[0], port.ct_export(K.enc_value(4711, 31337)))
+        assert ok, f
+        assert fpv(engine.dec_value(X)[0]) == 31337
+    finally:
+        engine.debug_set(1, 2**64 - 1, 0)
+        port.set_prf_patch()
+        engine.set_prf_mode(api.PRF_LIVE)
+        K.set_lpn_t(127)
+
+
+def test_faithful_mode_vs_full_oracle(api, port):
+    """the mode the headline enc_value_faithful number is quoted in: all 16384 LPN rows on the GPU against the oracle evaluating all 16384
+    rows too (no live-row shortcut on either side), 32 enc_value + 32 dec_value items, products included"""
+    eng = api.Engine(0, prf_mode=api.PRF_FAITHFUL, tape=api.TAPE_SPLITMIX)
+    try:
+        eng.keygen(1)
+        K = port.Keys.keygen(1)                     # lpn rows = 16384 (the default)
+        rng = np.random.default_rng(23)
+        vals = rng.integers(0, 2**64, 32, dtype=np.uint64)
+        X = eng.enc_value(vals, 31000)
+        got = api.split_items(eng.export_soa(X))
+        hs = []
+        for i in range(32):
+            h = K.enc_value(port.item_stream_state(31000, i), int(vals[i]))
+            hs.append(h)
+            ok, f = ct_equal(got[i], port.ct_export(h))
+            assert ok, (i, f)
+        dec = eng.dec_value(X)
+        for i in range(32):
+            assert np.array_equal(dec[i], K.dec_value(hs[i])), i
+        Pm = eng.ct_mul(eng.slice(X, 0, 4), eng.slice(X, 4, 4), 31001)
+        dp = eng.dec_value(Pm)
+        for i in range(4):
+            assert np.array_equal(dp[i], K.dec_value(K.ct_mul(port.item_stream_state(31001, i), hs[i], hs[4 + i])))
+    finally:
+        eng.close()
+
+
+def test_params_and_keygen_from_seed(api, port, port_keys):
+    """pvacb_keygen_params: non-default shapes are refused with the field named; run-time fields are honoured; keys from a 256-bit seed
+    are reproducible and equal the oracle's keygen under the same ChaCha20 stream (key = seed, stream id 0, lane 0)"""
+    eng = api.Engine(0, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX)
+    try:
+        for field, val in (("B", 257), ("m_bits", 4096), ("n_bits", 8192), ("h_col_wt", 64), ("lpn_n", 2048), ("lpn_tau_den", 4), ("lpn_t", 64), ("edge_budget", 10)):
+            p = api.Params.default()
+            setattr(p, field, val)
+            with pytest.raises(api.PvacbError) as ei:
+                eng.keygen_params(p, KEY)
+            assert ei.value.code == 1 and "Params" in str(ei.value)
+        p = api.Params.default()
+        p.lpn_t = 127; p.noise_entropy_bits = 200.0; p.depth_slope_bits = 8.0; p.tuple2_fraction = 0.4; p.edge_budget = 5000
+        eng.keygen_params(p, KEY)
+        q = eng.get_params()
+        assert (q.lpn_t, q.noise_entropy_bits, q.depth_slope_bits, q.tuple2_fraction, q.edge_budget) == (127, 200.0, 8.0, 0.4, 5000)
+        k1 = eng.export_keys(with_H=True)
+        port.set_tape(1, KEY, 0)
+        try:
+            ko = port.Keys.keygen(0).export(with_H=True)
+        finally:
+            port.set_tape(0)
+        for f in ("canon_tag", "H_digest", "H", "powg", "prf_k", "lpn_s"):
+            assert np.array_equal(np.asarray(k1[f]), np.asarray(ko[f])), f
+        # plan_noise follows the context's entropy budget: (200 * 0.4) / (2 log2 337) = 4, (200 * 0.6) / (3 log2 337) = 4
+        X = eng.enc_value(np.array([9], np.uint64), tape_states=[5])
+        nl, ne = X.totals()
+        assert nl == 2 and 2 * (8 + 2 * 4 + 3 * 4) - 6 <= ne <= 2 * (8 + 2 * 4 + 3 * 4)
+        assert fpv(eng.dec_value(X)[0]) == 9
+        # a product whose edges exceed the (small) edge budget is compacted like guard_budget does
+        A = eng.enc_value(np.array([3] * 8, np.uint64), 41)
+        S = A
+        for _ in range(3):
+            S = eng.ct_add(S, S)                                           # 8 x the edges, duplicates of every (layer, idx, sign)... in distinct layers
+        P2 = eng.ct_mul(S, S, 42)
+        assert [fpv(x) for x in eng.dec_value(P2)] == [(3 * 8) ** 2] * 8
+        e2 = api.Engine(0, prf_mode=api.PRF_LIVE)
+        e2.keygen_params(None, KEY)
+        assert e2.export_keys(with_H=False)["canon_tag"] == k1["canon_tag"] and e2.get_params().lpn_t == 16384
+        e2.keygen_params()                                                  # OS seed
+        assert e2.export_keys(with_H=False)["canon_tag"] != k1["canon_tag"]
+        e2.close()
+    finally:
+        eng.close()
+
+
+def test_key_files_byte_compatible(engine, api, tmp_path):
+    """pvacb_keys_export_file / import_file against the reference's formats (tests/bounty2_test.cpp:145-236): the engine's files for the
+    seed-1 keys hash to what the UNMODIFIED reference wrote for the same keys (tests/golden/keyfiles_seed1.json); the reference
+    repository's own sk.bin loads; a reference-written pk.bin loads (when oracle/_ref travelled); damaged files are refused"""
+    with open(os.path.join(GOLDEN, "keyfiles_seed1.json")) as f:
+        g = json.load(f)
+    pk, sk = str(tmp_path / "pk.bin"), str(tmp_path / "sk.bin")
+    engine.export_key_files(pk, sk)
+    pkb = open(pk, "rb").read()
+    assert len(pkb) == g["pk_bytes"] and hashlib.sha256(pkb).hexdigest() == g["pk_sha256"]
+    assert open(sk, "rb").read().hex() == g["sk_hex"]
+    e2 = api.Engine(0, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX)
+    try:
+        e2.import_key_files(pk, sk)
+        k1, k2 = engine.export_keys(), e2.export_keys()
+        for f in k1:
+            assert np.array_equal(np.asarray(k1[f]), np.asarray(k2[f])), f
+        v = np.array([42, 17], np.uint64)
+        a1, a2 = engine.export_soa(engine.enc_value(v, 77)), e2.export_soa(e2.enc_value(v, 77))
+        assert all(np.array_equal(a1[k], a2[k]) for k in a1)
+        # public key only: homomorphic ops work, enc / dec refuse
+        e2.import_key_files(pk, None)
+        A = e2.import_soa(a1)
+        Pm = e2.ct_mul(A, A, 5)
+        assert np.array_equal(e2.commit_ct(Pm), engine.commit_ct(engine.ct_mul(engine.import_soa(a1), engine.import_soa(a1), 5)))
+        for bad in (lambda: e2.enc_value(v, 1), lambda: e2.dec_value(Pm)):
+            with pytest.raises(api.PvacbError) as ei:
+                bad()
+            assert ei.value.code == 4
+        # the reference repository's own secret-key fixture: loads (with this pk) and re-exports byte for byte
+        fx = os.path.join(GOLDEN, "bounty2", "sk.bin")
+        e2.import_key_files(pk, fx)
+        out = str(tmp_path / "sk2.bin")
+        e2.export_key_files(None, out)
+        assert open(out, "rb").read() == open(fx, "rb").read()
+        # damaged files
+        for cut in (3, 40, 100, len(pkb) - 1):
+            p2 = str(tmp_path / "cut.bin")
+            open(p2, "wb").write(pkb[:cut])
+            with pytest.raises(api.PvacbError):
+                e2.import_key_files(p2, sk)
+        bad = bytearray(pkb)
+        bad[8] ^= 1                                                          # m_bits
+        open(str(tmp_path / "bad.bin"), "wb").write(bytes(bad))
+        with pytest.raises(api.PvacbError):
+            e2.import_key_files(str(tmp_path / "bad.bin"), sk)
+        open(str(tmp_path / "long.bin"), "wb").write(pkb + b"\0")
+        with pytest.raises(api.PvacbError):
+            e2.import_key_files(str(tmp_path / "long.bin"), sk)
+        if _ref.available():
+            _ref.set_tape(0)
+            Kr = _ref.Keys.keygen(31)
+            rp, rs = str(tmp_path / "rpk.bin"), str(tmp_path / "rsk.bin")
+            Kr.save(rp, rs)
+            e2.import_key_files(rp, rs)
+            kr, ke = Kr.export(), e2.export_keys()
+            for f in kr:
+                assert np.array_equal(np.asarray(kr[f]), np.asarray(ke[f])), f
+            e2.export_key_files(str(tmp_path / "epk.bin"), str(tmp_path / "esk.bin"))
+            assert open(str(tmp_path / "epk.bin"), "rb").read() == open(rp, "rb").read()
+            assert open(str(tmp_path / "esk.bin"), "rb").read() == open(rs, "rb").read()
+    finally:
+        e2.close()
+
+
+def test_blob_export_import_round_trip(engine, api):
+    """one copy per batch: the image of a batch (fresh, product, layer-compacted sum, empty) equals the field-by-field export; import of
+    the image gives the same batch; damaged images are refused by the device-side validation"""
+    import torch
+    v = np.arange(1, 9, dtype=np.uint64)
+    A, Bv = engine.enc_value(v, 901), engine.enc_value(v + 100, 902)
+    Pm = engine.ct_mul(A, Bv, 903)
+    S = engine.ct_add(Pm, A)
+    for X in (A, Pm, S, engine.slice(A, 0, 0)):
+        n, nl, ne, by = engine.blob_info(X)
+        host = torch.empty(by, dtype=torch.uint8).pin_memory()
+        hv = host.numpy()
+        engine.export_blob_async(X, hv)
+        engine.export_wait()
+        d, want = api.blob_views(hv, n, nl, ne), engine.export_soa(X)
+        for k in want:
+            assert np.array_equal(d[k], want[k]), k
+        Y = engine.import_blob(hv, n, nl, ne)
+        got = engine.export_soa(Y)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), k
+        if len(X):
+            assert np.array_equal(engine.dec_value(Y), engine.dec_value(X))
+    # pack_blob: the image of an SoA dict
+    buf, n, nl, ne = api.pack_blob(engine.export_soa(Pm))
+    Z = engine.import_blob(buf, n, nl, ne)
+    assert np.array_equal(engine.commit_ct(Z), engine.commit_ct(Pm))
+    d = api.blob_views(buf, n, nl, ne)
+    for field, val in (("lid", 99), ("idx", 400), ("ch", 2), ("rule", 3)):
+        keep = d[field][0].copy()
+        d[field][0] = val
+        with pytest.raises(api.PvacbError) as ei:
+            engine.import_blob(buf, n, nl, ne)
+        assert ei.value.code == 9
+        d[field][0] = keep
+    prod = int(np.flatnonzero(d["rule"] == 1)[0])
+    keep = int(d["pa"][prod])
+    d["pa"][prod] = 1000                                   # PROD parent out of range: caught at import, not at dec_value
+    with pytest.raises(api.PvacbError):
+        engine.import_blob(buf, n, nl, ne)
+    d["pa"][prod] = keep
+    d["w"][0] = [2**64 - 1, 2**63 - 1]                      # p itself is not canonical
+    with pytest.raises(api.PvacbError):
+        engine.import_blob(buf, n, nl, ne)
+    # import_soa: arrays that may not be NULL
+    so = engine.export_soa(A)
+    for k in ("rule", "ztag", "lid", "idx", "ch", "w"):
+        bad = dict(so)
+        bad[k] = None
+        with pytest.raises((api.PvacbError, KeyError)):
+            engine.import_soa(bad)
+    no_sigma = dict(so)
+    no_sigma["sigma"] = None                                # allowed: zero syndromes
+    assert np.array_equal(engine.dec_value(engine.import_soa(no_sigma)), engine.dec_value(A))
+
+
+def _group(api, devices):
+    g = C.c_void_p()
+    arr = (C.c_int * len(devices))(*devices)
+    rc = api.load_library().pvacb_group_create(arr, len(devices), C.byref(g))
+    assert rc == 0
+    return g
+
+
+def _group_pipeline(api, port, port_keys, devices):
+    L = api.load_library()
+    g = _group(api, devices)
+    try:
+        assert L.pvacb_group_size(g) == len(devices)
+        key = np.frombuffer(KEY, np.uint8).copy()
+        assert L.pvacb_group_set_tape(g, api.TAPE_SPLITMIX, None) == 0
+        assert L.pvacb_keygen(L.pvacb_group_ctx(g, 0), 1) == 0
+        assert L.pvacb_group_replicate_keys(g) == 0
+        for k in range(len(devices)):
+            assert L.pvacb_set_prf_mode(L.pvacb_group_ctx(g, k), api.PRF_LIVE) == 0
+        n = 37                                               # not a multiple of the group size: ragged ranges
+        rng = np.random.default_rng(8)
+        va, vb = rng.integers(0, 2**64, n, dtype=np.uint64), rng.integers(0, 2**64, n, dtype=np.uint64)
+        A, Bv, Pm, S = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+        assert L.pvacb_group_enc_value(g, p(va), n, 8801, C.byref(A)) == 0
+        assert L.pvacb_group_enc_value(g, p(vb), n, 8802, C.byref(Bv)) == 0
+        assert L.pvacb_group_ct_mul(g, A, Bv, 8803, C.byref(Pm)) == 0
+        assert L.pvacb_group_ct_add(g, Pm, A, C.byref(S)) == 0
+        dec = np.zeros((n, 2), np.uint64)
+        assert L.pvacb_group_dec_value(g, S, p(dec)) == 0, L.pvacb_group_last_error(g)
+        for i in range(n):
+            assert fpv(dec[i]) == (int(va[i]) * int(vb[i]) + int(va[i])) % P127
+        dig = np.zeros((n, 32), np.uint8)
+        assert L.pvacb_group_commit_ct(g, Pm, dig.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
+        # byte identity with the single-stream definition: item i of the product equals the oracle's under the GLOBAL item streams
+        for i in (0, 1, n // 2, n - 1):
+            oa = port_keys.enc_value(port.item_stream_state(8801, i), int(va[i]))
+            ob = port_keys.enc_value(port.item_stream_state(8802, i), int(vb[i]))
+            want = port_keys.commit_ct(port_keys.ct_mul(port.item_stream_state(8803, i), oa, ob))
+            assert dig[i].tobytes() == bytes(want), i
+        d0, d1 = C.c_double(), C.c_double()
+        assert L.pvacb_group_tune_export(g, C.byref(d0), C.byref(d1)) == 0
+        assert d0.value > 1.0
+        for b in (A, Bv, Pm, S):
+            L.pvacb_group_batch_free(b)
+        return dig, (d0.value, d1.value)
+    finally:
+        L.pvacb_group_destroy(g)
+
+
+def test_group_api_single_device(api, port, port_keys):
+    _group_pipeline(api, port, port_keys, [0])
+
+
+def test_group_api_two_devices_byte_identical(api, port, port_keys):
+    """N-GPU run == 1-GPU run, through the C ABI group: the digests of every product are equal whatever the sharding"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    d1, _ = _group_pipeline(api, port, port_keys, [0])
+    d2, rates = _group_pipeline(api, port, port_keys, [0, 1])
+    assert np.array_equal(d1, d2)
+    if torch.cuda.device_count() >= 8:
+        d8, rates8 = _group_pipeline(api, port, port_keys, list(range(8)))
+        assert np.array_equal(d1, d8)
+        print("group export GB/s direct / relayed:", rates8)
+
+
+def test_export_relay_two_devices(api):
+    """the image of a batch exported through ANOTHER GPU's host link (peer copy into a staging buffer there, D2H from there) is the
+    same bytes"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    eng = api.Engine(0, prf_mode=api.PRF_LIVE, tape=api.TAPE_SPLITMIX)
+    try:
+        eng.keygen(1)
+        X = eng.ct_mul(eng.enc_value(np.arange(64, dtype=np.uint64), 1), eng.enc_value(np.arange(64, dtype=np.uint64) + 5, 2), 3)
+        n, nl, ne, by = eng.blob_info(X)
+        h0, h1 = torch.empty(by, dtype=torch.uint8).pin_memory(), torch.empty(by, dtype=torch.uint8).pin_memory()
+        eng.export_blob_async(X, h0.numpy())
+        eng.export_wait()
+        eng.set_export_relay(1)
+        for _ in range(3):                                   # both staging slots
+            h1.zero_()
+            eng.export_blob_async(X, h1.numpy())
+            eng.export_wait()
+            assert torch.equal(h0, h1)
+        eng.set_export_relay(-1)
+        with pytest.raises(api.PvacbError):
+            eng.set_export_relay(0)                          # itself
+    finally:
+        eng.close()

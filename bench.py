@@ -7,7 +7,11 @@ reported in the same JSON line under "ops", each with its own roofline.
 
   step      = one pass of ct_mul over one tile of `--pairs` synthetic ciphertext pairs (default 4096 per GPU)
   value     = pairs/s, whole job, inputs resident in HBM, timed with CUDA events on the engine's stream, max over ranks
-  e2e       = the same metric through the C ABI with HOST buffers: pinned host SoA -> H2D import, ct_mul, D2H export
+  e2e       = the same metric through the C ABI with HOST buffers: pinned host images -> H2D import, ct_mul, D2H export (one copy
+              per batch each way); its roofline is the host link of the box measured live with every rank copying at once, direct and
+              -- where the GPUs reach host memory unequally -- with the slower half relayed through the faster half over NVLink
+  global_digest = SHA-256 over the commit_ct digests of one fixed global batch of products, sharded over the ranks by index: the same
+              string at every N (an N-GPU run returns the bytes of the 1-GPU run)
   roofline  = dominant kernel (sigma_fused_kernel): algorithmic L2 gather bytes / its CUDA-event time vs the measured
               L2 gather ceiling of this GPU (pvacb_l2_gather_probe); ct_add's HBM roofline is under ops.ct_add
   cpu_baseline / --impl reference = the unmodified reference (oracle/_ref, built from /root/reference) on the host cores
@@ -29,6 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 P127 = (1 << 127) - 1
+BENCH_TAPE_KEY = bytes((37 * i + 11) & 255 for i in range(32))
 EDGE_WIRE_BYTES = 1052          # serialised edge (tests/bounty2_test.cpp:98-106): the byte convention of SURVEY 8d
 GATHER_BYTES_PER_EDGE = 128 * 1024
 WORKLOAD = "ct_mul fresh x fresh (2 layers, 39-40 edges each -> 8 layers, ~1200 edges), default Params"   # both arms
@@ -36,6 +41,8 @@ SHA_PER_EDGE = 70               # 2 midstates + 2 x 34 counter hashes (csrc/sigm
 AES_LDS_PER_BLOCK = 197         # T-table lookups per AES-256 block after hoisting rounds 1-2 (csrc/aes256.cuh)
 ALU_LANE_OPS_PER_S = 18.55e12    # measured LOP3/SHF/PRMT rate of this GPU (profiles/micro/int_pipes.cu): 63.8 lanes/clk/SM
 SHA_ALU_INSTR = 1024            # ALU-pipe instructions (SHF + LOP3) of one compression in the rolled form (cuobjdump); the adds run as IMAD on the FMA pipe
+INT_LANE_OPS_PER_S = 124.5 * 148 * 1.965e9   # IMAD + LOP3/SHF issued together: 124.5 lanes/clk/SM (profiles/r01_int_pipes.txt)
+DEC_INSTR_PER_EDGE = 190        # SASS instructions in the per-edge loop body of dec_edges_kernel (cuobjdump, round 2)
 ALU_WARP_INSTR_PER_EDGE = 3395  # fallback for profiles/r01_ncu_summary.json: ALU-pipe warp instructions per edge of sigma_fused_kernel (ncu)
 
 
@@ -188,7 +195,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    eng = api.Engine(device=local, prf_mode=api.PRF_LIVE)
+    # RNG tape: ChaCha20 (the library's default) under a FIXED key, so that every rank of every N draws the same streams for the same
+    # global items and runs are comparable; a deployment leaves the key to the OS CSPRNG (pvacb_ctx_create does that)
+    eng = api.Engine(device=local, prf_mode=api.PRF_LIVE, tape=api.TAPE_CHACHA20, tape_key=BENCH_TAPE_KEY)
     # ---- keys: generated once on rank 0, replicated over NVLink with one NCCL broadcast (16.8 MB), no steady-state collective
     blob = torch.empty(api.KEY_BLOB_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
     if rank == 0:
@@ -230,6 +239,38 @@ def main():
         e1.synchronize()
         barrier()
         return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    def all_gather_bytes(b):
+        if world == 1:
+            return [b]
+        t = torch.tensor(list(b), dtype=torch.uint8, device=f"cuda:{local}")
+        outs = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return [bytes(o.cpu().numpy().tolist()) for o in outs]
+
+    # ---- proof that N GPUs return the bytes of one GPU: one fixed GLOBAL batch of 8192 fresh pairs, contiguous index ranges, the
+    # streams of the global items (pvacb_set_item_base). Every rank XORs sha256(global index || commit_ct digest of the product) over
+    # its items; XOR does not care how the batch was split, so the string must be the same in the N = 1, 2, 4, 8 lines.
+    import hashlib
+    from pvac_hfhe_cppbyv_b200 import shard as shardmod
+    GD = 8192
+    gfirst, gcount = shardmod.partition(GD, world)[rank]
+    gi = np.arange(gfirst, gfirst + gcount, dtype=np.uint64)
+    eng.set_item_base(gfirst)
+    GA = eng.enc_value(shardmod.mix64(gi * np.uint64(2) + np.uint64(0xA11CE)), 7001)
+    GB = eng.enc_value(shardmod.mix64(gi * np.uint64(2) + np.uint64(0xB0B)), 7002)
+    GP = eng.ct_mul(GA, GB, 7003)
+    eng.set_item_base(0)
+    dig = eng.commit_ct(GP)
+    acc = np.zeros(32, np.uint8)
+    for k in range(gcount):
+        acc ^= np.frombuffer(hashlib.sha256(int(gfirst + k).to_bytes(8, "little") + dig[k].tobytes()).digest(), np.uint8)
+    tot = np.zeros(32, np.uint8)
+    for pz in all_gather_bytes(acc.tobytes()):
+        tot ^= np.frombuffer(pz, np.uint8)
+    global_digest = tot.tobytes().hex()
+    for x in (GA, GB, GP):
+        x.free()
 
     hbm_peak, peak_src = peaks()
     M = args.pairs
@@ -307,57 +348,86 @@ def main():
         if per_edge is not None and gather_launches:
             roofline["traffic"] = per_edge * edges_per_step * args.steps / gather_launches
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with host buffers: ONE copy per batch each way (the batch image)
     Me = min(args.e2e_pairs, M)
     Ae, Be = eng.slice(A, 0, Me), eng.slice(B, 0, Me)
-    ha, hb = eng.export_soa(Ae), eng.export_soa(Be)
+
+    def pinned(nbytes):
+        t = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory()
+        return t, t.numpy()
+
+    def host_image(X):
+        """the batch image in pinned host memory -> (keepalive, uint8 view, n, layout layers, layout edges)"""
+        n_, nl_, ne_, by_ = eng.blob_info(X)
+        t, v = pinned(by_)
+        eng.export_blob_async(X, v)
+        eng.export_wait()
+        return t, v, n_, nl_, ne_
+    img_a, img_b = host_image(Ae), host_image(Be)
     Ae.free(); Be.free()
-
-    def pin(d):
-        o = {}
-        for k, v in d.items():
-            if v is None:
-                o[k] = None
-                continue
-            t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
-            o[k] = t.numpy()
-            o["_t_" + k] = t
-        return o
-    ha, hb = pin(ha), pin(hb)
-    h2d = sum(v.nbytes for k, v in list(ha.items()) + list(hb.items()) if isinstance(v, np.ndarray))
-    cap_edges, cap_layers = int(Me * 1400), int(Me * 8)
-    spec = dict(loff=(Me + 1, np.uint32), eoff=(Me + 1, np.uint32), rule=(cap_layers, np.uint8), ztag=(cap_layers, np.uint64), nlo=(cap_layers, np.uint64),
-                nhi=(cap_layers, np.uint64), pa=(cap_layers, np.uint32), pb=(cap_layers, np.uint32), lid=(cap_edges, np.uint32), idx=(cap_edges, np.uint16),
-                ch=(cap_edges, np.uint8), w=((cap_edges, 2), np.uint64), sigma=((cap_edges, 128), np.uint64))
-    keep = []
-
-    def pinned_set():
-        o = {}
-        for k, (shape, dt) in spec.items():
-            t = torch.empty(int(np.prod(shape)) * np.dtype(dt).itemsize, dtype=torch.uint8).pin_memory()
-            keep.append(t)
-            o[k] = t.numpy().view(dt).reshape(shape)
-        return o
-    out_bufs = [pinned_set(), pinned_set()]          # double buffer: the D2H of step k overlaps import + compute of step k+1
-    d2h_list = []
-    in_a = {kk: vv for kk, vv in ha.items() if not kk.startswith("_t_")}
-    in_b = {kk: vv for kk, vv in hb.items() if not kk.startswith("_t_")}
-    pending = []
+    h2d = img_a[1].nbytes + img_b[1].nbytes
+    out_cap = api.blob_layout(Me, 12 * Me, 1400 * Me)[13]
+    out_bufs = [pinned(out_cap), pinned(out_cap)]      # double buffer: the D2H of step k overlaps import + compute of step k+1
+    pending, d2h_list, last_info = [], [], [None]
 
     def retire():
         eng.export_wait_one()                        # the oldest product is now complete in host memory
-        P0, d0 = pending.pop(0)
-        d2h_list.append(sum(v.nbytes for v in d0.values() if isinstance(v, np.ndarray)))
+        P0, info = pending.pop(0)
+        d2h_list.append(info[3])
+        last_info[0] = info
         P0.free()
 
     def step_e2e(k):
-        X = eng.import_soa(in_a)                     # H2D from pinned host arrays
-        Y = eng.import_soa(in_b)
+        X = eng.import_blob(img_a[1], img_a[2], img_a[3], img_a[4])          # H2D from pinned host memory, validated on the device
+        Y = eng.import_blob(img_b[1], img_b[2], img_b[3], img_b[4])
         P = eng.ct_mul(X, Y, tape_states=item_states(3000 + k, g0, Me))
-        pending.append((P, eng.export_soa_async(P, out_bufs[k & 1])))    # queued behind the previous export: the copy engine never idles
+        info = eng.blob_info(P)
+        eng.export_blob_async(P, out_bufs[k & 1][1])                          # queued behind the previous export: the copy engine never idles
+        pending.append((P, info))
         if len(pending) > 1:
-            retire()                                 # frees the other buffer set for step k + 1
+            retire()                                 # frees the other buffer for step k + 1
         X.free(); Y.free()
+
+    # ---- the host link of this box with every rank copying at once = the ceiling of e2e; direct, and relayed where the links are unequal
+    Pprobe = eng.ct_mul(eng.import_blob(img_a[1], img_a[2], img_a[3], img_a[4]), eng.import_blob(img_b[1], img_b[2], img_b[3], img_b[4]),
+                        tape_states=item_states(2999, g0, Me))
+    probe_bytes = eng.blob_info(Pprobe)[3]
+
+    def link_probe(reps=4):
+        """aggregate GB/s of all ranks exporting the image of a product batch `reps` times between two barriers, and this rank's own rate"""
+        eng.export_blob_async(Pprobe, out_bufs[0][1]); eng.export_wait()          # warm-up (relay staging buffers, peer mappings)
+        barrier()
+        t0 = time.perf_counter()
+        for r in range(reps):
+            eng.export_blob_async(Pprobe, out_bufs[r & 1][1])
+        eng.export_wait()
+        mine = time.perf_counter() - t0
+        slowest = max_over_ranks(mine)
+        return world * probe_bytes * reps / slowest / 1e9, probe_bytes * reps / mine / 1e9
+    link = {"direct_gbs": None, "relay_gbs": None, "routing": "direct", "per_rank_gbs_direct": None}
+    agg0, mine0 = link_probe()
+    link["direct_gbs"] = agg0
+    rates = [mine0]
+    if world > 1:
+        t = torch.tensor([mine0], dtype=torch.float64, device=f"cuda:{local}")
+        outs = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        rates = [float(o.item()) for o in outs]
+    link["per_rank_gbs_direct"] = rates
+    if world >= 2 and min(rates) < 0.8 * max(rates) and torch.cuda.device_count() >= world:
+        order = sorted(range(world), key=lambda r: rates[r])                      # same list on every rank
+        half = world // 2
+        relay_of = {order[i]: order[world - half + i] for i in range(half)}       # slow rank -> device of a fast rank (local rank = device)
+        if rank in relay_of:
+            eng.set_export_relay(relay_of[rank])
+        agg1, _ = link_probe()
+        link["relay_gbs"] = agg1
+        if agg1 > 1.05 * agg0:
+            link["routing"] = "slower half of the GPUs relayed through the faster half over NVLink: " + ", ".join(f"{a}->{b}" for a, b in sorted(relay_of.items()))
+        else:
+            eng.set_export_relay(-1)
+    Pprobe.free()
+    link_peak = max(x for x in (link["direct_gbs"], link["relay_gbs"]) if x)
 
     for k in range(args.warmup):
         step_e2e(k)
@@ -373,21 +443,64 @@ def main():
     torch.cuda.synchronize()
     e2e_secs = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    # the exported bytes are the real thing: the last product, read back from the pinned buffers, decrypts correctly
-    chk = out_bufs[(args.warmup + args.steps - 1) & 1]
-    nchk = 4
-    eL, eE = int(chk["loff"][nchk]), int(chk["eoff"][nchk])
-    sub = {kk: (chk[kk][:nchk + 1] if kk in ("loff", "eoff") else chk[kk][:eL] if kk in ("rule", "ztag", "nlo", "nhi", "pa", "pb") else chk[kk][:eE]) for kk in spec}
-    R = eng.import_soa(sub)
-    dchk = eng.dec_value(R)
+    # the exported bytes are the real thing: the last product, read back from the pinned buffer, decrypts correctly
+    n_, nl_, ne_, by_ = last_info[0]
+    R = eng.import_blob(out_bufs[(args.warmup + args.steps - 1) & 1][1][:by_], n_, nl_, ne_)
+    dchk = eng.dec_value(eng.slice(R, 0, 4))
     R.free()
-    for i in range(nchk):
+    for i in range(4):
         assert (int(dchk[i][0]) | (int(dchk[i][1]) << 64)) == int(va[i]) * int(vb[i]) % P127, "e2e export does not decrypt"
-    e2e = {"value": world * Me * args.steps / e2e_secs, "unit": "ct_mul/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(np.mean(d2h_list)),
+    d2h_step = float(np.mean(d2h_list))
+    d2h_gbs = world * d2h_step * args.steps / e2e_secs / 1e9
+    e2e = {"value": world * Me * args.steps / e2e_secs, "unit": "ct_mul/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_step),
            "pairs_per_step_per_gpu": Me, "ms_per_step": 1e3 * e2e_secs / args.steps,
-           "note": "per step: pinned host SoA arrays -> pvacb_batch_import_soa x2 -> pvacb_ct_mul_ex -> pvacb_batch_export_soa_async into pinned host "
-                   "buffers (1.3 MB per product over PCIe); double-buffered so the device->host read of step k overlaps step k+1; all inside the timed region"}
-    del out_bufs, keep
+           "roofline": {"bound": "host link (pinned device->host copies of every rank at once)", "achieved": d2h_gbs, "peak": link_peak, "unit": "GB/s",
+                        "frac": d2h_gbs / link_peak, "peak_source": "measured live before the timed region: all ranks export a product batch 4 times between two barriers "
+                        "(profiles/r02_hostlink_probe.txt has the same numbers from a stand-alone probe)", "link": link},
+           "note": "per step: two pinned host batch images -> pvacb_batch_import_blob x2 (one H2D copy each, validated on the device) -> pvacb_ct_mul_ex -> "
+                   "pvacb_batch_export_blob_async (one D2H copy, 1.3 MB per product); double-buffered so the device->host read of step k overlaps step k+1; all inside the timed region"}
+
+    # ---- enc_value end to end: host plaintexts in, host ciphertexts out (live-row PRF)
+    Ne = 8192
+    tv, vv = pinned(Ne * 8)
+    vals_e = vv.view(np.uint64)
+    vals_e[:] = rng.integers(0, 2**64, Ne, dtype=np.uint64)
+    enc_cap = api.blob_layout(Ne, 2 * Ne, 44 * Ne)[13]
+    enc_bufs = [pinned(enc_cap), pinned(enc_cap)]
+    enc_d2h = []
+
+    def step_enc(k):
+        X = eng.enc_value(vals_e, tape_states=item_states(4000 + k, g0, Ne))      # the plaintexts cross PCIe inside the call
+        info = eng.blob_info(X)
+        eng.export_blob_async(X, enc_bufs[k & 1][1])
+        pending.append((X, info))
+        if len(pending) > 1:
+            retire()
+    for k in range(3):
+        step_enc(k)
+    while pending:
+        retire()
+    d2h_list.clear()
+    barrier()
+    t0 = time.perf_counter()
+    enc_steps = 5
+    for k in range(enc_steps):
+        step_enc(3 + k)
+    while pending:
+        retire()
+    torch.cuda.synchronize()
+    enc_secs = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    n_, nl_, ne_, by_ = last_info[0]
+    R = eng.import_blob(enc_bufs[(3 + enc_steps - 1) & 1][1][:by_], n_, nl_, ne_)
+    dchk = eng.dec_value(eng.slice(R, 0, 4))
+    R.free()
+    assert [int(x[0]) for x in dchk] == [int(x) for x in vals_e[:4]], "e2e enc_value export does not decrypt"
+    e2e_enc = {"value": world * Ne * enc_steps / enc_secs, "unit": "enc_value/s", "prf_mode": "live", "items_per_step_per_gpu": Ne, "ms_per_step": 1e3 * enc_secs / enc_steps,
+               "h2d_bytes_per_step": Ne * 8 * 2, "d2h_bytes_per_step": int(np.mean(d2h_list)),
+               "d2h_gbs": world * float(np.mean(d2h_list)) * enc_steps / enc_secs / 1e9, "link_peak_gbs": link_peak,
+               "note": "per step: pinned host plaintexts + tape states -> pvacb_enc_value_ex -> pvacb_batch_export_blob_async (42 KB per ciphertext); double-buffered"}
+    del out_bufs, enc_bufs
 
     # ---- the other ops of the path (short, device-timed), each with the roofline that bounds it
     ops = {}
@@ -458,6 +571,131 @@ def main():
             D.free()
         eng.set_prf_mode(api.PRF_LIVE)
 
+        int_peak = INT_LANE_OPS_PER_S / 1e12
+
+        def prof_run(fn, n_items, steps=2, warmup=1):
+            """device-timed rate of fn plus the per-tag kernel times of the timed launches only"""
+            for k in range(warmup):
+                fn(k)
+            eng.profile_enable(True)
+            eng.profile_collect()
+            s = timed(fn, steps, 0)
+            pr = eng.profile_collect()
+            eng.profile_enable(False)
+            return world * n_items * steps / s, s / steps, {t: (ms / steps, cnt // max(steps, 1)) for t, (ms, cnt) in pr.items()}
+
+        # ---- BASELINE config 4: the depth chain of tests/test_depth.cpp:44-72, c0 = enc(2), c <- c*c, every product decrypted
+        chain = {}
+        tiles = {1: 2048, 2: 256, 3: 16}
+        c_prev = eng.enc_value(np.full(tiles[1], 2, np.uint64), tape_states=item_states(6000, g0, tiles[1]))
+        expect = 2
+        for step in (1, 2, 3):
+            T = tiles[step]
+            src = eng.slice(c_prev, 0, T)
+            outs = []
+
+            def mul_fn(k, src=src, T=T, step=step):
+                P = eng.ct_mul(src, src, tape_states=item_states(6100 + 10 * step + k, g0, T))
+                outs.append(P)
+                if len(outs) > 1:
+                    outs.pop(0).free()
+            rate_m, spp_m, pr_m = prof_run(mul_fn, T)
+            c_next = outs[-1]
+            nl_c, ne_c = c_next.totals()
+            expect = expect * expect % P127
+            rate_d, spp_d, pr_d = prof_run(lambda k, c=c_next: eng.dec_value(c), T, steps=3, warmup=1)
+            dchk = eng.dec_value(eng.slice(c_next, 0, 2))
+            assert all((int(x[0]) | (int(x[1]) << 64)) == expect for x in dchk), "depth chain product does not decrypt"
+            edges_ct = ne_c / T
+            de_ms = pr_d["dec_edges"][0]
+            chain[f"step{step}"] = {
+                "tile_per_gpu": T, "edges_per_ciphertext": edges_ct, "layers_per_ciphertext": nl_c / T,
+                "ct_mul/s": rate_m, "ct_mul_ms_per_tile": spp_m * 1e3, "dec_value/s": rate_d, "dec_value_ms_per_tile": spp_d * 1e3,
+                "ct_mul_kernels_ms": {"sigma_fused": pr_m["sigma"][0], "mul_pairs": pr_m["mul_pairs"][0]},
+                "dec_kernels_ms": {"prf_lpn": pr_d["prf_lpn"][0], "dec_edges": de_ms},
+                "sigma_roofline": {"kernel": "sigma_fused_kernel", "bound": "l2", "achieved": ne_c * GATHER_BYTES_PER_EDGE / (pr_m["sigma"][0] * 1e-3) / 1e9 if pr_m["sigma"][0] else None,
+                                   "peak": l2_peak, "unit": "GB/s", "frac": (ne_c * GATHER_BYTES_PER_EDGE / (pr_m["sigma"][0] * 1e-3) / 1e9 / l2_peak) if pr_m["sigma"][0] else None},
+                "dec_edges_roofline": {"kernel": "dec_edges_kernel", "bound": "integer pipes (one reduced 128x128 product + one 256-bit multiply-accumulate per edge)",
+                                       "achieved": ne_c * DEC_INSTR_PER_EDGE * 32 / 32 / (de_ms * 1e-3) / 1e12 if de_ms else None, "unit": "T lane-ops/s", "peak": int_peak,
+                                       "frac": (ne_c * DEC_INSTR_PER_EDGE / (de_ms * 1e-3) / 1e12 / int_peak) if de_ms else None,
+                                       "instructions_per_edge": DEC_INSTR_PER_EDGE, "hbm_gbs": ne_c * 23 / (de_ms * 1e-3) / 1e9 if de_ms else None, "hbm_peak": hbm_peak,
+                                       "peak_source": "measured IMAD + LOP3 issue rate when mixed, 124.5 lanes/clk/SM (profiles/r01_int_pipes.txt)"},
+            }
+            if step > 1:
+                src.free()
+            if step == 1:
+                c_prev.free()
+            c_prev = c_next
+        # the mul_pairs kernel on dense layers (products of products): weight products per second
+        ops["depth_chain"] = chain
+        c3 = c_prev
+
+        # ---- dec_value of fresh x fresh products (BASELINE.md: 20.9 ms on the reference): 4 distinct seeds, ~1200 edges, 8 layers
+        Pab = eng.ct_mul(A, B, tape_states=item_states(6501, g0, M))
+        decp = {}
+        for mode, tag, n_dec in ((api.PRF_LIVE, "live", 2048), (api.PRF_FAITHFUL, "faithful", 256)):
+            eng.set_prf_mode(mode)
+            D = eng.slice(Pab, 0, min(n_dec, M))
+            rate, spp, pr = prof_run(lambda k, D=D: eng.dec_value(D), len(D), steps=3, warmup=1)
+            decp[tag] = {"value": rate, "unit": "dec_value/s", "items_per_step_per_gpu": len(D), "ms_per_step": spp * 1e3, "edges_per_ciphertext": D.totals()[1] / len(D),
+                         "kernels_ms": {"prf_lpn": pr["prf_lpn"][0], "dec_edges": pr["dec_edges"][0]}, "share_prf": pr["prf_lpn"][0] * 1e-3 / spp, "share_dec_edges": pr["dec_edges"][0] * 1e-3 / spp}
+            D.free()
+        eng.set_prf_mode(api.PRF_LIVE)
+        ops["dec_product"] = decp
+
+        # ---- the "next" kernels of SURVEY 8(f), one line each with the bound named
+        nxt = {}
+        # commit_ct: SHA-256 over 1 057 B per edge; the chain of one ciphertext is serial, parallel across ciphertexts
+        for tag, X in (("fresh_65536", eng.enc_value(rng.integers(0, 2**64, 1 << 16, dtype=np.uint64), tape_states=item_states(6500, g0, 1 << 16))),
+                       ("products_4096", Pab)):
+            nlx, nex = X.totals()
+            compressions = (nex * 1057 + nlx * 25 + len(X) * 64) / 64.0
+            rate, spp, pr = prof_run(lambda k, X=X: eng.commit_ct(X), len(X), steps=2, warmup=1)
+            kms = pr["commit"][0]
+            nxt["commit_ct_" + tag] = {"value": rate, "unit": "commit_ct/s", "ms_per_step": spp * 1e3, "bytes_hashed_per_step": nex * 1057,
+                                       "roofline": {"kernel": "commit_kernel", "bound": "ALU pipe (SHA-256 rounds, one serial chain per ciphertext)", "achieved": compressions / (kms * 1e-3) / 1e9,
+                                                    "unit": "G compressions/s", "peak": 15.2, "frac": compressions / (kms * 1e-3) / 1e9 / 15.2,
+                                                    "peak_source": "measured stand-alone SHA-256 compression rate (profiles/r01_sha_variants.txt)",
+                                                    "hbm_gbs": nex * 1057 / (kms * 1e-3) / 1e9}}
+            X.free()
+        # compact_edges: sort by (layer, idx, sign) + merge; the 1.38 M-edge case = a depth-3 product added to itself three times
+        big = eng.slice(c3, 0, 2)
+        for _ in range(3):
+            nb_ = eng.ct_add(big, big)
+            big.free()
+            big = nb_
+        nlb, neb = big.totals()
+        rate, spp, pr = prof_run(lambda k: eng.compact_edges(big).free(), len(big), steps=2, warmup=1)
+        nxt["compact_edges_1p38M"] = {"value": rate, "unit": "compact_edges/s", "edges_per_ciphertext": neb / len(big), "ms_per_step": spp * 1e3,
+                                      "edges_per_s": neb / spp, "bound": "HBM: every 1 KiB syndrome row is read and rewritten once, plus an 8-byte-key radix sort",
+                                      "hbm_gbs": neb * 2 * 1052 / spp / 1e9, "hbm_peak": hbm_peak, "frac": neb * 2 * 1052 / spp / 1e9 / hbm_peak}
+        big.free()
+        # ct_recrypt round (fresh ciphertexts are balanced: density check + compact_edges + compact_layers), pool of 16 zeros
+        pool = eng.enc_zero_depth(16, 0, tape_states=item_states(6600, g0, 16))
+        rate, spp, pr = prof_run(lambda k: eng.ct_recrypt(A, pool, tape_states=item_states(6601 + k, g0, M)).free(), M, steps=2, warmup=1)
+        nxt["ct_recrypt_fresh"] = {"value": rate, "unit": "ct_recrypt/s", "items_per_step_per_gpu": M, "ms_per_step": spp * 1e3,
+                                   "bound": "HBM (popcount of every syndrome row, then a sort + rewrite of the batch)", "hbm_gbs": A.totals()[1] * 3 * 1052 / spp / 1e9, "hbm_peak": hbm_peak}
+        pool.free()
+        # enc_text: 1024 messages of 100 bytes = 1024 x (1 length ciphertext + 7 blocks with depth hints 2..8)
+        msgs = [bytes((i + j) & 255 for j in range(100)) for i in range(1024)]
+        rate, spp, pr = prof_run(lambda k: eng.enc_text(msgs, tape_states=item_states(6700 + k, g0, 1024)).free(), 1024, steps=2, warmup=1)
+        nxt["enc_text_100B"] = {"value": rate, "unit": "messages/s", "messages_per_step_per_gpu": 1024, "ms_per_step": spp * 1e3,
+                                "bound": "PRF (LDS) + sigma (L2 gather): 8 waves of enc_value-shaped work per message", "prf_lpn_ms": pr["prf_lpn"][0], "sigma_ms": pr["sigma"][0]}
+        ops["next"] = nxt
+        c3.free()
+
+        # ---- BASELINE config 5: this GPU's shard of the mixed enc / ct_mul / dec job (tiles of 4096 pairs, only the 16-byte decrypts leave)
+        from pvac_hfhe_cppbyv_b200 import pipeline
+        n_mixed = 1 << 16
+        barrier()
+        t0 = time.perf_counter()
+        checked, bad = pipeline.run_mixed_pipeline(eng, rank * n_mixed, n_mixed, 4096, seed=9000)
+        torch.cuda.synchronize()
+        mixed_secs = max_over_ranks(time.perf_counter() - t0)
+        assert bad == 0, "mixed pipeline: a product decrypted wrong"
+        ops["mixed"] = {"value": world * n_mixed / mixed_secs, "unit": "items/s (2 enc_value + 1 ct_mul + 1 dec_value per 2 items)", "items_per_gpu": n_mixed, "tile_pairs": 4096,
+                        "products_verified": checked * world, "seconds": mixed_secs, "prf_mode": "live", "timing": "wall clock with host-side verification inside, max over ranks"}
+
     # ---- CPU baseline: the unmodified reference on the host cores (rank 0, bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -472,6 +710,13 @@ def main():
             for op, nm, it in ((0, "enc_value/s", 8), (1, "ct_add/s", 20000), (4, "dec_value/s", 32)):
                 s2, n2 = K.bench(op, threads, it)
                 extra[nm] = n2 / s2
+            for op, nm, it in ((5, "dec_value_product/s", 16), (11, "commit_ct_fresh/s", 200), (12, "commit_ct_product/s", 8), (13, "compact_edges_product/s", 32),
+                               (14, "ct_recrypt_fresh/s", 200), (15, "enc_text_100B/s", 1)):
+                s2, n2 = K.bench(op, threads, it)
+                extra[nm] = n2 / s2
+            cm, cd, ce = K.bench_chain(threads, 3)         # tests/test_depth.cpp on every host thread at once
+            extra["depth_chain"] = {f"step{k + 1}": {"ct_mul/s": threads / float(cm[k]), "dec_value/s": threads / float(cd[k]), "ct_mul_ms_one_thread": 1e3 * float(cm[k]),
+                                                     "dec_ms_one_thread": 1e3 * float(cd[k]), "edges": int(ce[k])} for k in range(3)}
             cpu["other_ops"] = extra
         else:
             from oracle import port
@@ -494,7 +739,7 @@ def main():
                        "pairs_per_step_per_gpu": M, "out_edges_per_step_per_gpu": edges_per_step, "input_bytes_resident": in_bytes,
                        "l2": "inputs (%.0f MB) and outputs (%.1f GB per step) exceed the 126 MB L2; the 16 MiB matrix H is meant to be L2 resident" % (in_bytes / 1e6, edges_per_step * 1052 / 1e9),
                        "sharding": f"batch index, {world} rank(s), keys replicated by one NCCL broadcast, no steady-state collective", "prf_mode_for_inputs": "live"},
-            "e2e": e2e, "gpu_launches": st["kernel_launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "ops": ops,
+            "e2e": e2e, "e2e_enc_value": e2e_enc, "global_digest": global_digest, "gpu_launches": st["kernel_launches"], "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "ops": ops,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -3,7 +3,9 @@
 //   w as 16 bytes with bit 127 cleared, sigma as 1 024 bytes).
 // The only public consumer of sigma: 1 057 bytes hashed per edge (16.5 compressions), so it is bound by the SHA-256 ALU rate
 // (15 G compressions/s = 0.97 TB/s of input), not by HBM. A hash chain is sequential, so the parallelism is across
-// ciphertexts: one thread per ciphertext. The message is a byte stream with 1-byte fields in it, so u64 items are appended
+// ciphertexts: one thread per ciphertext. A chain is also a long run of DEPENDENT instructions, so a scheduler needs several warps
+// to stay busy: when the batch has fewer ciphertexts than 16 warps per SM x 32 lanes, each warp takes fewer of them (lanes_per_warp
+// < 32) and more warps are launched -- the ALU lanes were idle anyway, the issue slots are what a small batch lacks. The message is a byte stream with 1-byte fields in it, so u64 items are appended
 // through a byte-granular shift register; the 64-byte block being filled lives in shared memory (dynamic index), the
 // sigma rows are read 32 bytes (one sector) at a time.
 #include "engine.h"
@@ -11,7 +13,7 @@
 
 namespace pvacb {
 
-constexpr int kCommitThreads = 32;
+constexpr int kCommitThreads = 128;
 
 struct CommitStream {
     uint32_t h[8];
@@ -56,10 +58,12 @@ commit_kernel(uint64_t n, uint64_t canon_tag, const uint64_t* __restrict__ hdig 
               const uint32_t* __restrict__ eoff, const uint8_t* __restrict__ rule, const uint64_t* __restrict__ ztag, const uint64_t* __restrict__ nlo,
               const uint64_t* __restrict__ nhi, const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pb, const uint32_t* __restrict__ lid,
               const uint16_t* __restrict__ idx, const uint8_t* __restrict__ ch, const Fp* __restrict__ w, const uint64_t* __restrict__ sigma,
-              uint32_t* __restrict__ out /* n x 8 words = the digest bytes */) {
+              uint32_t* __restrict__ out /* n x 8 words = the digest bytes */, int lanes_per_warp) {
     __shared__ uint64_t block[8][kCommitThreads];
-    const uint64_t i = (uint64_t)blockIdx.x * kCommitThreads + threadIdx.x;
-    if (i >= n) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * kCommitThreads + threadIdx.x) >> 5;
+    const uint64_t i = warp * (uint64_t)lanes_per_warp + lane;
+    if (lane >= (uint32_t)lanes_per_warp || i >= n) return;
     CommitStream S;
     ShaState iv;
     sha_init(iv);
@@ -114,8 +118,14 @@ int op_commit_ct(Ctx* ctx, const Batch* b, uint8_t* h_out /* n x 32 */) {
     if ((rc = dev_alloc(ctx, (void**)&d_out, b->n * 32))) return rc;
     if ((rc = dev_alloc(ctx, (void**)&d_dig, 32))) { dev_free(ctx, d_out); return rc; }
     PV_CUDA(cudaMemcpyAsync(d_dig, ctx->d_blob + 1, 32, cudaMemcpyDeviceToDevice, ctx->stream));   // H_digest = blob words 1..4
-    commit_kernel<<<(unsigned)((b->n + kCommitThreads - 1) / kCommitThreads), kCommitThreads, 0, ctx->stream>>>(
-        b->n, ctx->kv.canon_tag, d_dig, b->loff, b->eoff, b->rule, b->ztag, b->nlo, b->nhi, b->pa, b->pb, b->lid, b->idx, b->ch, b->w, b->sigma, d_out);
+    int lpw = 32;
+    while (lpw > 1 && b->n < (uint64_t)ctx->sm_count * 16 * (uint64_t)lpw) lpw >>= 1;
+    const uint64_t warps = (b->n + lpw - 1) / lpw;
+    {
+        ProfScope ps(ctx, PROF_COMMIT);
+        commit_kernel<<<(unsigned)((warps * 32 + kCommitThreads - 1) / kCommitThreads), kCommitThreads, 0, ctx->stream>>>(
+            b->n, ctx->kv.canon_tag, d_dig, b->loff, b->eoff, b->rule, b->ztag, b->nlo, b->nhi, b->pa, b->pb, b->lid, b->idx, b->ch, b->w, b->sigma, d_out, lpw);
+    }
     PV_CUDA(cudaGetLastError());
     ctx->stat_kernel_launches += 1;
     PV_CUDA(cudaMemcpyAsync(h_out, d_out, b->n * 32, cudaMemcpyDeviceToHost, ctx->stream));

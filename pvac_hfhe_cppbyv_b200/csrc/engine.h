@@ -101,7 +101,7 @@ struct Ctx {
 };
 
 // profiling tags (pvacb_profile_collect)
-enum : int { PROF_PRF_LPN = 0, PROF_MUL_PAIRS = 1, PROF_SIGMA = 2, PROF_CONCAT = 3, PROF_DEC_EDGES = 4, PROF_MUL_PLAN = 5, PROF_NTAGS = 8 };
+enum : int { PROF_PRF_LPN = 0, PROF_MUL_PAIRS = 1, PROF_SIGMA = 2, PROF_CONCAT = 3, PROF_DEC_EDGES = 4, PROF_COMMIT = 5, PROF_COMPACT = 6, PROF_NTAGS = 8 };
 struct ProfScope {
     Ctx* ctx; cudaEvent_t a = nullptr, b = nullptr; int tag;
     ProfScope(Ctx* c, int t) : ctx(c), tag(t) {

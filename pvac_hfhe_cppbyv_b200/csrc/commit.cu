@@ -4,8 +4,8 @@
 // The only public consumer of sigma: 1 057 bytes hashed per edge (16.5 compressions), so it is bound by the SHA-256 ALU rate
 // (15 G compressions/s = 0.97 TB/s of input), not by HBM. A hash chain is sequential, so the parallelism is across
 // ciphertexts: one thread per ciphertext. A chain is also a long run of DEPENDENT instructions, so a scheduler needs several warps
-// to stay busy: when the batch has fewer ciphertexts than 16 warps per SM x 32 lanes, each warp takes fewer of them (lanes_per_warp
-// < 32) and more warps are launched -- the ALU lanes were idle anyway, the issue slots are what a small batch lacks. The message is a byte stream with 1-byte fields in it, so u64 items are appended
+// to stay busy, while every warp instruction costs an issue slot however few lanes it carries: the launcher picks the smallest
+// lanes_per_warp that keeps the warp count within what the schedulers can issue (commit.cu: op_commit_ct). The message is a byte stream with 1-byte fields in it, so u64 items are appended
 // through a byte-granular shift register; the 64-byte block being filled lives in shared memory (dynamic index), the
 // sigma rows are read 32 bytes (one sector) at a time.
 #include "engine.h"
@@ -118,8 +118,11 @@ int op_commit_ct(Ctx* ctx, const Batch* b, uint8_t* h_out /* n x 32 */) {
     if ((rc = dev_alloc(ctx, (void**)&d_out, b->n * 32))) return rc;
     if ((rc = dev_alloc(ctx, (void**)&d_dig, 32))) { dev_free(ctx, d_out); return rc; }
     PV_CUDA(cudaMemcpyAsync(d_dig, ctx->d_blob + 1, 32, cudaMemcpyDeviceToDevice, ctx->stream));   // H_digest = blob words 1..4
-    int lpw = 32;
-    while (lpw > 1 && b->n < (uint64_t)ctx->sm_count * 16 * (uint64_t)lpw) lpw >>= 1;
+    // a chain issues about 0.4 instructions per clock (dependent rounds): up to ~2.5 warps keep one scheduler busy. Fewer ciphertexts
+    // than that many full warps -> fewer lanes per warp, so that no chain waits for an issue slot; more -> full warps (throughput).
+    const uint64_t busy_warps = (uint64_t)ctx->sm_count * 4 * 5 / 2;
+    int lpw = 1;
+    while (lpw < 32 && (b->n + lpw - 1) / lpw > busy_warps) lpw <<= 1;
     const uint64_t warps = (b->n + lpw - 1) / lpw;
     {
         ProfScope ps(ctx, PROF_COMMIT);

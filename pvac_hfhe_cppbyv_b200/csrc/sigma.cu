@@ -323,6 +323,7 @@ __global__ void sigma_xor_rows_kernel(uint64_t npairs, const uint2* __restrict__
     uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (p >= npairs) return;
     uint2 pr = pairs[p];
+    if (pr.x == 0xFFFFFFFFu) return;          // the raw edge's slot was dropped by compact_edges (enc.cu): its row is not merged anywhere
     unsigned long long* d = reinterpret_cast<unsigned long long*>(out + (uint64_t)pr.x * kMWords);
     const uint64_t* s = (uint64_t)pr.y < split ? out + (uint64_t)pr.y * kMWords : out2 + ((uint64_t)pr.y - split) * kMWords;
     for (int k = lane; k < kMWords; k += 32) atomicXor(d + k, (unsigned long long)s[k]);

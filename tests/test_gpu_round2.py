@@ -473,3 +473,25 @@ def test_export_relay_two_devices(api):
             eng.set_export_relay(0)                          # itself
     finally:
         eng.close()
+
+
+@pytest.mark.timeout(1500)
+def test_reference_example_program_unmodified_on_gpu():
+    """BASELINE config 1 as a drop-in: the reference's OWN examples/basic_usage.cpp, unmodified, compiled against the reference headers
+    plus the GPU binding (tests/cpp/ref_binding: functions with the reference's signatures over libpvacb.so; oracle/Makefile builds
+    oracle/_ref/basic_usage_on_gpu where the reference tree is present). Every keygen / enc_value / ct_add / ct_sub / ct_mul / dec_value /
+    commit_ct / enc_text / dec_text of the program runs on the B200. The one CHECK that cannot pass is "2^16 = 65536": x^16 = x^8 * x^8
+    has 172 544^2 edge pairs, more than the batched ct_mul indexes (the reference itself aborts there on hosts with <= 64 GB)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "basic_usage_on_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/basic_usage_on_gpu not built (reference tree absent at build time)")
+    env = dict(os.environ, PVAC_GPU_SOFT_SHAPE="1", PVAC_GPU_PRF_LIVE="1")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1400, env=env)
+    out = r.stdout
+    fails = [ln for ln in out.splitlines() if "FAIL" in ln]
+    assert len(fails) <= 1 and all("65536" in ln for ln in fails), out[-3000:] + r.stderr[-2000:]
+    oks = [ln for ln in out.splitlines() if ln.strip().startswith("ok:") or ln.rstrip().endswith(" ok")]
+    assert len(oks) >= 40, out[-3000:] + r.stderr[-2000:]
+    assert "ascii roundtrip" in out and "2^10 = 1024" in out and "6! = 720" in out

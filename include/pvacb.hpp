@@ -70,8 +70,19 @@ public:
     Engine(const Engine&) = delete;
     Engine& operator=(const Engine&) = delete;
 
-    void keygen(uint64_t tape_state) { ck(pvacb_keygen(ctx_, tape_state)); }
+    // keygen(prm, pk, sk), crypto/keygen.hpp:35: default Params unless given, seed = 32 bytes or nullptr for the OS CSPRNG
+    void keygen(const pvacb_params* prm = nullptr, const uint8_t* seed32 = nullptr) { ck(pvacb_keygen_params(ctx_, prm, seed32)); }
+    void keygen(uint64_t tape_state) { ck(pvacb_keygen(ctx_, tape_state)); }       // parity vectors only (SplitMix64 from 64 bits)
     void set_prf_mode(int mode) { ck(pvacb_set_prf_mode(ctx_, mode)); }
+    // RNG tape of the context (pvacb.h): ChaCha20 under an OS key by default
+    void set_tape(int kind, const uint8_t* key32 = nullptr) { ck(pvacb_set_tape(ctx_, kind, key32)); }
+    uint64_t fresh_seed() { return pvacb_fresh_seed(ctx_); }
+    // savePk / loadPk / saveSk / loadSk of the reference's programs (tests/bounty2_test.cpp:145-236)
+    void save_keys(const char* pk_path, const char* sk_path) { ck(pvacb_keys_export_file(ctx_, pk_path, sk_path)); }
+    void load_keys(const char* pk_path, const char* sk_path) { ck(pvacb_keys_import_file(ctx_, pk_path, sk_path)); }
+    // the reference's signatures carry no seed: these overloads draw a fresh one from the context
+    Ciphers enc_value(const std::vector<uint64_t>& v) { return enc_value(v, fresh_seed()); }
+    Ciphers ct_mul(const Ciphers& a, const Ciphers& b) { return ct_mul(a, b, fresh_seed()); }
 
     Ciphers enc_value(const std::vector<uint64_t>& v, uint64_t batch_seed) {
         pvacb_batch* o = nullptr;
@@ -171,6 +182,61 @@ public:
 private:
     void ck(int rc) { if (rc) throw Error(rc, pvacb_last_error(ctx_)); }
     pvacb_ctx* ctx_ = nullptr;
+};
+
+// Several GPUs of one box behind one object (pvacb_group_*): batches are split into contiguous index ranges, every item keeps the RNG
+// stream of its global index (the bytes do not depend on the number of GPUs), keys are replicated once over NVLink.
+class ShardedCiphers {
+public:
+    ShardedCiphers() = default;
+    explicit ShardedCiphers(pvacb_gbatch* h) : h_(h) {}
+    ShardedCiphers(ShardedCiphers&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    ShardedCiphers& operator=(ShardedCiphers&& o) noexcept { if (this != &o) { reset(); h_ = o.h_; o.h_ = nullptr; } return *this; }
+    ShardedCiphers(const ShardedCiphers&) = delete;
+    ShardedCiphers& operator=(const ShardedCiphers&) = delete;
+    ~ShardedCiphers() { reset(); }
+    void reset() { if (h_) pvacb_group_batch_free(h_); h_ = nullptr; }
+    size_t size() const { return h_ ? pvacb_group_batch_count(h_) : 0; }
+    pvacb_gbatch* handle() const { return h_; }
+private:
+    pvacb_gbatch* h_ = nullptr;
+};
+
+class Group {
+public:
+    explicit Group(const std::vector<int>& devices, int prf_mode = PVACB_PRF_FAITHFUL) {
+        int rc = pvacb_group_create(devices.data(), (int)devices.size(), &g_);
+        if (rc) throw Error(rc, "pvacb_group_create failed");
+        for (int k = 0; k < size(); k++) pvacb_set_prf_mode(pvacb_group_ctx(g_, k), prf_mode);
+    }
+    ~Group() { if (g_) pvacb_group_destroy(g_); }
+    Group(const Group&) = delete;
+    Group& operator=(const Group&) = delete;
+    int size() const { return pvacb_group_size(g_); }
+    void keygen(const pvacb_params* prm = nullptr, const uint8_t* seed32 = nullptr) { ck(pvacb_group_keygen_params(g_, prm, seed32)); }
+    void load_keys(const char* pk_path, const char* sk_path) { ck(pvacb_group_keys_import_file(g_, pk_path, sk_path)); }
+    void set_tape(int kind, const uint8_t* key32 = nullptr) { ck(pvacb_group_set_tape(g_, kind, key32)); }
+    uint64_t fresh_seed() { return pvacb_fresh_seed(pvacb_group_ctx(g_, 0)); }
+    ShardedCiphers enc_value(const std::vector<uint64_t>& v, uint64_t batch_seed) { pvacb_gbatch* o = nullptr; ck(pvacb_group_enc_value(g_, v.data(), v.size(), batch_seed, &o)); return ShardedCiphers(o); }
+    ShardedCiphers ct_add(const ShardedCiphers& a, const ShardedCiphers& b) { pvacb_gbatch* o = nullptr; ck(pvacb_group_ct_add(g_, a.handle(), b.handle(), &o)); return ShardedCiphers(o); }
+    ShardedCiphers ct_sub(const ShardedCiphers& a, const ShardedCiphers& b) { pvacb_gbatch* o = nullptr; ck(pvacb_group_ct_sub(g_, a.handle(), b.handle(), &o)); return ShardedCiphers(o); }
+    ShardedCiphers ct_mul(const ShardedCiphers& a, const ShardedCiphers& b, uint64_t batch_seed) { pvacb_gbatch* o = nullptr; ck(pvacb_group_ct_mul(g_, a.handle(), b.handle(), batch_seed, &o)); return ShardedCiphers(o); }
+    std::vector<Fp> dec_value(const ShardedCiphers& c) {
+        std::vector<Fp> out(c.size());
+        ck(pvacb_group_dec_value(g_, c.handle(), reinterpret_cast<uint64_t*>(out.data())));
+        return out;
+    }
+    std::vector<std::array<uint8_t, 32>> commit_ct(const ShardedCiphers& c) {
+        std::vector<std::array<uint8_t, 32>> out(c.size());
+        ck(pvacb_group_commit_ct(g_, c.handle(), reinterpret_cast<uint8_t*>(out.data())));
+        return out;
+    }
+    // measures the members' simultaneous export bandwidth and keeps the better routing (direct / relayed over NVLink); GB/s of both
+    std::pair<double, double> tune_export() { double a = 0, b = 0; ck(pvacb_group_tune_export(g_, &a, &b)); return {a, b}; }
+    pvacb_group* handle() const { return g_; }
+private:
+    void ck(int rc) { if (rc) throw Error(rc, pvacb_group_last_error(g_)); }
+    pvacb_group* g_ = nullptr;
 };
 
 }  // namespace pvacb

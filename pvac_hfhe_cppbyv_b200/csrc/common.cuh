@@ -101,11 +101,13 @@ struct Tape {
     uint64_t k;           // next word
     uint64_t blk;         // CHACHA20: index of the cached block (~0 = none)
     uint64_t buf[8];
-    bool overrun;         // TAPE_WORDS: a word beyond the supplied ones was asked for (it reads as 0)
+    bool overrun;         // TAPE_WORDS: a word beyond the supplied ones was asked for
     PV_HD uint64_t at(uint64_t kk) {
         if (kind == TAPE_SPLITMIX) return splitmix_word(s0, kk);
         if (kind == TAPE_WORDS) {
-            if (kk >= nwords) { overrun = true; return 0; }
+            // past the supplied words: remember it (the call then fails) and hand out varying filler, so that the rejection loops of the
+            // walk (distinct indices, non-zero field elements) still terminate
+            if (kk >= nwords) { overrun = true; return splitmix_word(0x6F76657272756E21ull, kk); }
             return words[kk];
         }
         const uint64_t b = kk >> 3;

@@ -475,7 +475,7 @@ def test_export_relay_two_devices(api):
         eng.close()
 
 
-@pytest.mark.timeout(1500)
+@pytest.mark.timeout(400)
 def test_reference_example_program_unmodified_on_gpu():
     """BASELINE config 1 as a drop-in: the reference's OWN examples/basic_usage.cpp, unmodified, compiled against the reference headers
     plus the GPU binding (tests/cpp/ref_binding: functions with the reference's signatures over libpvacb.so; oracle/Makefile builds
@@ -488,10 +488,31 @@ def test_reference_example_program_unmodified_on_gpu():
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/basic_usage_on_gpu not built (reference tree absent at build time)")
     env = dict(os.environ, PVAC_GPU_SOFT_SHAPE="1", PVAC_GPU_PRF_LIVE="1")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=1400, env=env)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
     out = r.stdout
     fails = [ln for ln in out.splitlines() if "FAIL" in ln]
     assert len(fails) <= 1 and all("65536" in ln for ln in fails), out[-3000:] + r.stderr[-2000:]
     oks = [ln for ln in out.splitlines() if ln.strip().startswith("ok:") or ln.rstrip().endswith(" ok")]
     assert len(oks) >= 40, out[-3000:] + r.stderr[-2000:]
     assert "ascii roundtrip" in out and "2^10 = 1024" in out and "6! = 720" in out
+
+
+@pytest.mark.timeout(900)
+def test_cpp_group_pipeline(tmp_path):
+    """the C++ twin of profiles/mixed_pipeline.py (BASELINE config 5) through pvacb::Group: every product verified against a*b mod p, and
+    the digest of all decrypts is the same on one GPU and on all GPUs of the box"""
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "pvac_hfhe_cppbyv_b200")
+    exe = str(tmp_path / "group_pipeline")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "group_pipeline.cpp"),
+                           "-L", pkg, "-lpvacb", f"-Wl,-rpath,{pkg}", "-o", exe])
+    outs = []
+    for ngpu in sorted({1, torch.cuda.device_count()}):
+        r = subprocess.run([exe, "16384", "4096", str(ngpu)], capture_output=True, text=True, timeout=200)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["mismatches"] == 0 and d["products_checked"] == 8192 and d["gpus"] == ngpu
+        outs.append(d)
+    assert len({d["decrypt_digest"] for d in outs}) == 1, outs

@@ -68,8 +68,8 @@ enum { PVACB_TAPE_SPLITMIX = 0, PVACB_TAPE_CHACHA20 = 1, PVACB_TAPE_WORDS = 2 };
 /* struct Params, core/types.hpp:36-70, field for field. The kernels are built for the shapes of the default set: B, m_bits, n_bits,
  * h_col_wt, x_col_wt, err_wt, lpn_n and lpn_tau must keep their defaults (anything else is refused with PVACB_E_ARG and a
  * message naming the field); noise_entropy_bits, tuple2_fraction, depth_slope_bits, edge_budget (4096..2^32-1), lpn_t (127..16384:
- * every value in that range gives identical ciphertexts, 16384 evaluates all rows like the reference, less evaluates the live
- * rows) and the recrypt fields (which the reference never reads either) are run-time values. */
+ * every value in that range gives identical ciphertexts; less than 16384 switches the context to the live-row evaluation, 16384 leaves
+ * its PRF mode alone) and the recrypt fields (which the reference never reads either) are run-time values. */
 typedef struct pvacb_params {
     int32_t B, m_bits, n_bits, h_col_wt, x_col_wt, err_wt;
     double noise_entropy_bits, tuple2_fraction, depth_slope_bits;

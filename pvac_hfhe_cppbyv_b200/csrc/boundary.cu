@@ -56,9 +56,9 @@ static void apply_params(Ctx* ctx, const pvacb_params* p) {
     ctx->edge_budget = (uint32_t)p->edge_budget;
     ctx->lpn_t = p->lpn_t;
     ctx->recrypt_lo = p->recrypt_lo; ctx->recrypt_hi = p->recrypt_hi; ctx->recrypt_rounds = p->recrypt_rounds;
-    // every lpn_t >= 127 gives the same PRF values (toep_127 reads rows 0..126 only): all 16384 rows are evaluated when the caller
-    // asks for the reference's row count, the live rows otherwise
-    ctx->prf_mode = p->lpn_t == kLpnT ? PRF_FAITHFUL : PRF_LIVE;
+    // every lpn_t >= 127 gives the same PRF values (toep_127 reads rows 0..126 only): fewer rows than the reference's 16384 means the
+    // live-row evaluation; with lpn_t = 16384 the mode of the context stays what it is (all rows by default, pvacb_set_prf_mode)
+    if (p->lpn_t != kLpnT) ctx->prf_mode = PRF_LIVE;
 }
 
 namespace pvacb {

@@ -584,9 +584,15 @@ int pvacb_batch_export_soa_async(pvacb_ctx* x, const pvacb_batch* pb, uint32_t* 
 int pvacb_export_wait(pvacb_ctx* x) {
     Ctx* ctx = C(x);
     cudaSetDevice(ctx->device);
-    PV_CUDA(cudaStreamSynchronize(ctx->stream2));
-    for (cudaEvent_t e : ctx->export_events) cudaEventDestroy(e);
+    // every outstanding export, whichever stream carries it (the second stream of this device, or a stream of the relay device)
+    cudaError_t err = cudaSuccess;
+    for (cudaEvent_t e : ctx->export_events) {
+        cudaError_t q = cudaEventSynchronize(e);
+        if (err == cudaSuccess) err = q;
+        cudaEventDestroy(e);
+    }
     ctx->export_events.clear();
+    PV_CUDA(err);
     return PV_OK;
 }
 

@@ -252,6 +252,7 @@ def test_params_and_keygen_from_seed(api, port, port_keys):
         e2 = api.Engine(0, prf_mode=api.PRF_LIVE)
         e2.keygen_params(None, KEY)
         assert e2.export_keys(with_H=False)["canon_tag"] == k1["canon_tag"] and e2.get_params().lpn_t == 16384
+        assert e2.L.pvacb_get_prf_mode(e2.h) == api.PRF_LIVE               # lpn_t = 16384 leaves the mode the caller chose
         e2.keygen_params()                                                  # OS seed
         assert e2.export_keys(with_H=False)["canon_tag"] != k1["canon_tag"]
         e2.close()

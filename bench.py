@@ -393,9 +393,10 @@ def main():
                         tape_states=item_states(2999, g0, Me))
     probe_bytes = eng.blob_info(Pprobe)[3]
 
-    def link_probe(reps=4):
+    def link_probe(reps=6):
         """aggregate GB/s of all ranks exporting the image of a product batch `reps` times between two barriers, and this rank's own rate"""
-        eng.export_blob_async(Pprobe, out_bufs[0][1]); eng.export_wait()          # warm-up (relay staging buffers, peer mappings)
+        for _ in range(2):                                                         # warm-up (relay staging buffer, peer mappings)
+            eng.export_blob_async(Pprobe, out_bufs[0][1]); eng.export_wait()
         barrier()
         t0 = time.perf_counter()
         for r in range(reps):
@@ -455,7 +456,7 @@ def main():
     e2e = {"value": world * Me * args.steps / e2e_secs, "unit": "ct_mul/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_step),
            "pairs_per_step_per_gpu": Me, "ms_per_step": 1e3 * e2e_secs / args.steps,
            "roofline": {"bound": "host link (pinned device->host copies of every rank at once)", "achieved": d2h_gbs, "peak": link_peak, "unit": "GB/s",
-                        "frac": d2h_gbs / link_peak, "peak_source": "measured live before the timed region: all ranks export a product batch 4 times between two barriers "
+                        "frac": d2h_gbs / link_peak, "peak_source": "measured live before the timed region: all ranks export a product batch 6 times between two barriers "
                         "(profiles/r02_hostlink_probe.txt has the same numbers from a stand-alone probe)", "link": link},
            "note": "per step: two pinned host batch images -> pvacb_batch_import_blob x2 (one H2D copy each, validated on the device) -> pvacb_ct_mul_ex -> "
                    "pvacb_batch_export_blob_async (one D2H copy, 1.3 MB per product); double-buffered so the device->host read of step k overlaps step k+1; all inside the timed region"}

@@ -1,7 +1,7 @@
 """ncu workload for the kernels that only matter on DEEP ciphertexts: the dense path of mul_pairs_kernel
-(products of products), dec_edges_kernel on 172 544-edge ciphertexts, commit_kernel on products, the compact_edges sort + merge.
+(products of products), dec_edges_kernel on 172 544-edge ciphertexts, commit_kernel on products.
 
-    ncu --set full --clock-control none --import-source on -k regex:'mul_pairs|dec_edges|commit_kernel|cmp_' -c 12 -o gpurun_out/r02_deep python profiles/prof_deep.py
+    ncu --set full --clock-control none --import-source on -k regex:'mul_pairs_kernel|dec_edges_kernel|commit_kernel' -c 8 -o gpurun_out/r02_deep python profiles/prof_deep.py
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,9 +24,5 @@ print("chain ok; step-3 batch:", len(c), "ciphertexts,", c.totals())
 X, Y = eng.enc_value(np.arange(2048, dtype=np.uint64), 2), eng.enc_value(np.arange(2048, dtype=np.uint64) + 9, 3)
 Pm = eng.ct_mul(X, Y, 4)
 dg = eng.commit_ct(Pm)                                    # commit_kernel: 2048 chains of ~20 000 compressions
-big = eng.slice(c, 0, 2)
-for _ in range(3):
-    big = eng.ct_add(big, big)
-eng.compact_edges(big)                                    # 2 x 1 380 352 edges
 print("prof_deep ok", eng.stats())
 eng.close()

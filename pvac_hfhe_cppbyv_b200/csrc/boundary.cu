@@ -410,9 +410,10 @@ int pvacb_batch_export_blob_async(pvacb_ctx* x, const pvacb_batch* pb, void* hos
     PV_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     PV_CUDA(cudaEventRecord(ready, ctx->stream));
     if (ctx->relay.device >= 0) {
+        // one in-order stream on the relay GPU and one staging buffer: peer copy, then the device->host copy, export after export --
+        // the configuration profiles/r02_hostlink_relay.txt measured (the NVLink hop costs ~5 % of the time of the PCIe hop)
         Ctx::Relay& r = ctx->relay;
-        const int slot = r.next & 1;
-        r.next++;
+        const int slot = 0;
         int rc = relay_prepare(ctx, b->bytes, slot);
         if (rc) { cudaEventDestroy(ready); return rc; }
         cudaError_t e = cudaStreamWaitEvent(r.stream[slot], ready, 0);

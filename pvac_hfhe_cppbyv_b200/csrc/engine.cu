@@ -103,12 +103,19 @@ int batch_clone(Ctx* ctx, const Batch* s, Batch** out) {
 }
 void batch_free(Batch* b) {
     if (!b) return;
+    // a batch may be freed from any host thread, whatever device is current there (the group's batches die on the caller's thread):
+    // the stream-ordered free has to run with the owning device current, or the memory never goes back to its pool
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != b->ctx->device) cudaSetDevice(b->ctx->device);
     dev_free(b->ctx, b->base);
+    if (cur >= 0 && cur != b->ctx->device) cudaSetDevice(cur);
     delete b;
 }
 
 // ------------------------------------------------------------------ keys
 static int derive_key_view(Ctx* ctx) {
+    cudaSetDevice(ctx->device);
     const uint64_t* h = ctx->h_hdr.data();
     KeyView& kv = ctx->kv;
     kv.canon_tag = h[0];
@@ -139,6 +146,7 @@ static int derive_key_view(Ctx* ctx) {
 // arithmetic on the low word (one IMAD per column instead of a 64-bit add on the ALU pipe that bounds it).
 static int ensure_blob(Ctx* ctx) {
     if (ctx->d_blob) return PV_OK;
+    cudaSetDevice(ctx->device);          // the calling host thread may have another device current (the group's worker threads do)
     void* held[4] = {nullptr, nullptr, nullptr, nullptr};
     int nheld = 0;
     int rc = PV_OK;
@@ -311,6 +319,7 @@ int pvacb_profile_collect(pvacb_ctx* x, float* ms_out /*8*/, uint32_t* launches_
 int pvacb_keys_copy_blob_to(pvacb_ctx* x, void* dst_device) {
     Ctx* ctx = C(x);
     if (!ctx->have_keys) return PV_E_NOKEYS;
+    cudaSetDevice(ctx->device);
     PV_CUDA(cudaMemcpyAsync(dst_device, ctx->d_blob, kBlobBytes, cudaMemcpyDeviceToDevice, ctx->stream));
     PV_CUDA(cudaStreamSynchronize(ctx->stream));
     return PV_OK;
@@ -385,6 +394,7 @@ int pvacb_keys_adopt_blob(pvacb_ctx* x);
 int pvacb_keys_adopt_blob(pvacb_ctx* x) {
     Ctx* ctx = C(x);
     if (!ctx->d_blob) return PV_E_NOKEYS;
+    cudaSetDevice(ctx->device);
     ctx->h_hdr.resize(kBlobHdrWords);
     PV_CUDA(cudaMemcpy(ctx->h_hdr.data(), ctx->d_blob, kBlobHdrWords * 8, cudaMemcpyDeviceToHost));
     return derive_key_view(ctx);

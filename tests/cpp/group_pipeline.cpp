@@ -42,15 +42,22 @@ int main(int argc, char** argv) {
         auto rates = g.tune_export();
         const uint64_t pairs = items / 2;
         uint64_t bad = 0, checked = 0, digest = 0;
+        double t_enc = 0, t_mul = 0, t_dec = 0, t_host = 0;
+        auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         auto t0 = std::chrono::steady_clock::now();
         for (uint64_t f0 = 0; f0 < pairs; f0 += tile) {                      // a tile is a GLOBAL batch: the group shards it over its GPUs
             const uint64_t c = std::min<uint64_t>(tile, pairs - f0);
             std::vector<uint64_t> va(c), vb(c);
             for (uint64_t j = 0; j < c; j++) { va[j] = mix64(2 * (f0 + j) + 0x1234); vb[j] = mix64(2 * (f0 + j) + 0x1235); }
             // one seed per tile and operand: (seed, global item index inside the tile) never repeats across tiles
+            double q0 = now();
             pvacb::ShardedCiphers A = g.enc_value(va, 3 * (f0 / tile) + 1), B = g.enc_value(vb, 3 * (f0 / tile) + 2);
+            double q1 = now();
             pvacb::ShardedCiphers P = g.ct_mul(A, B, 3 * (f0 / tile) + 3);
+            double q2 = now();
             std::vector<pvacb::Fp> d = g.dec_value(P);
+            double q3 = now();
+            t_enc += q1 - q0; t_mul += q2 - q1; t_dec += q3 - q2;
             if (f0 == 0)                                                    // ciphertext bytes too: commit_ct digests of the first tile's products
                 for (const auto& cm : g.commit_ct(P))
                     for (int q = 0; q < 4; q++) { uint64_t w; memcpy(&w, cm.data() + 8 * q, 8); digest = mix64(digest ^ w); }
@@ -65,12 +72,13 @@ int main(int argc, char** argv) {
                 digest = mix64(digest ^ d[j].lo) + mix64(d[j].hi + j + f0);
             }
             checked += c;
+            t_host += now() - q3;
         }
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("{\"gpus\": %d, \"items\": %llu, \"tile_pairs\": %llu, \"products_checked\": %llu, \"mismatches\": %llu, \"seconds\": %.3f, \"items_per_s\": %.0f, "
-               "\"decrypt_digest\": \"%016llx\", \"export_gbs_direct\": %.1f, \"export_gbs_relayed\": %.1f}\n",
+               "\"decrypt_digest\": \"%016llx\", \"export_gbs_direct\": %.1f, \"export_gbs_relayed\": %.1f, \"seconds_enc\": %.3f, \"seconds_mul\": %.3f, \"seconds_dec\": %.3f, \"seconds_host_check\": %.3f}\n",
                ngpu, (unsigned long long)items, (unsigned long long)tile, (unsigned long long)checked, (unsigned long long)bad, secs, items / secs,
-               (unsigned long long)digest, rates.first, rates.second);
+               (unsigned long long)digest, rates.first, rates.second, t_enc, t_mul, t_dec, t_host);
         return bad ? 1 : 0;
     } catch (const pvacb::Error& e) {
         fprintf(stderr, "%s\n", e.what());

@@ -42,7 +42,7 @@ AES_LDS_PER_BLOCK = 197         # T-table lookups per AES-256 block after hoisti
 ALU_LANE_OPS_PER_S = 18.55e12    # measured LOP3/SHF/PRMT rate of this GPU (profiles/micro/int_pipes.cu): 63.8 lanes/clk/SM
 SHA_ALU_INSTR = 1024            # ALU-pipe instructions (SHF + LOP3) of one compression in the rolled form (cuobjdump); the adds run as IMAD on the FMA pipe
 INT_LANE_OPS_PER_S = 124.5 * 148 * 1.965e9   # IMAD + LOP3/SHF issued together: 124.5 lanes/clk/SM (profiles/r01_int_pipes.txt)
-DEC_INSTR_PER_EDGE = 190        # SASS instructions in the per-edge loop body of dec_edges_kernel (cuobjdump, round 2)
+DEC_INSTR_PER_EDGE = 240        # thread instructions per edge of dec_edges_kernel (ncu r02: 20.69 M warp instructions for 2 760 704 edges, profiles/r02_ncu_deep_metrics.csv)
 ALU_WARP_INSTR_PER_EDGE = 3395  # fallback for profiles/r01_ncu_summary.json: ALU-pipe warp instructions per edge of sigma_fused_kernel (ncu)
 
 

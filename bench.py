@@ -394,19 +394,31 @@ def main():
     probe_bytes = eng.blob_info(Pprobe)[3]
 
     def link_probe(reps=6):
-        """aggregate GB/s of all ranks exporting the image of a product batch `reps` times between two barriers, and this rank's own rate"""
-        for _ in range(2):                                                         # warm-up (relay staging buffer, peer mappings)
-            eng.export_blob_async(Pprobe, out_bufs[0][1]); eng.export_wait()
+        """aggregate GB/s of all ranks exporting the image of a product batch `reps` times between two barriers, this rank's own rate, and
+        whether every rank got through (a rank whose routing fails still takes part in the collectives, so nobody hangs)"""
+        ok, mine = True, 1e9
+        try:
+            for _ in range(2):                                                     # warm-up (relay staging buffer, peer mappings)
+                eng.export_blob_async(Pprobe, out_bufs[0][1]); eng.export_wait()
+        except api.PvacbError as ex:
+            ok = False
+            print(f"rank {rank}: export routing failed: {ex}", file=sys.stderr)
         barrier()
         t0 = time.perf_counter()
-        for r in range(reps):
-            eng.export_blob_async(Pprobe, out_bufs[r & 1][1])
-        eng.export_wait()
-        mine = time.perf_counter() - t0
+        try:
+            if ok:
+                for r in range(reps):
+                    eng.export_blob_async(Pprobe, out_bufs[r & 1][1])
+                eng.export_wait()
+                mine = time.perf_counter() - t0
+        except api.PvacbError as ex:
+            ok = False
+            print(f"rank {rank}: export routing failed: {ex}", file=sys.stderr)
         slowest = max_over_ranks(mine)
-        return world * probe_bytes * reps / slowest / 1e9, probe_bytes * reps / mine / 1e9
+        all_ok = max_over_ranks(0.0 if ok else 1.0) == 0.0
+        return (world * probe_bytes * reps / slowest / 1e9 if all_ok else 0.0), probe_bytes * reps / mine / 1e9, all_ok
     link = {"direct_gbs": None, "relay_gbs": None, "routing": "direct", "per_rank_gbs_direct": None}
-    agg0, mine0 = link_probe()
+    agg0, mine0, _ = link_probe()
     link["direct_gbs"] = agg0
     rates = [mine0]
     if world > 1:
@@ -420,10 +432,13 @@ def main():
         half = world // 2
         relay_of = {order[i]: order[world - half + i] for i in range(half)}       # slow rank -> device of a fast rank (local rank = device)
         if rank in relay_of:
-            eng.set_export_relay(relay_of[rank])
-        agg1, _ = link_probe()
-        link["relay_gbs"] = agg1
-        if agg1 > 1.05 * agg0:
+            try:
+                eng.set_export_relay(relay_of[rank])
+            except api.PvacbError as ex:
+                print(f"rank {rank}: relay refused: {ex}", file=sys.stderr)
+        agg1, _, relay_ok = link_probe()
+        link["relay_gbs"] = agg1 if relay_ok else None
+        if relay_ok and agg1 > 1.05 * agg0:
             link["routing"] = "slower half of the GPUs relayed through the faster half over NVLink: " + ", ".join(f"{a}->{b}" for a, b in sorted(relay_of.items()))
         else:
             eng.set_export_relay(-1)

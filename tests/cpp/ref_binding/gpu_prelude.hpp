@@ -21,3 +21,14 @@
 #define commit_ct gpu_commit_ct
 #define enc_text gpu_enc_text
 #define dec_text gpu_dec_text
+#define ct_scale gpu_ct_scale
+#define ct_neg gpu_ct_neg
+#define ct_div_const gpu_ct_div_const
+#define compact_edges gpu_compact_edges
+#define ubk_apply gpu_ubk_apply
+#define sigma_density gpu_sigma_density
+#define enc_value_depth gpu_enc_value_depth
+#define enc_fp_depth gpu_enc_fp_depth
+#define enc_zero_depth gpu_enc_zero_depth
+#define make_evalkey gpu_make_evalkey
+#define ct_recrypt gpu_ct_recrypt

@@ -28,7 +28,7 @@ namespace gpu {
 struct Device {
     pvacb_ctx* ctx = nullptr;
     uint64_t loaded_tag = 0;
-    bool have = false;
+    bool have = false, have_sk = false;
     Device() {
         int rc = pvacb_ctx_create(0, &ctx);
         if (rc) die(nullptr, "pvacb_ctx_create (an sm_100-class GPU is required; there is no CPU path)", rc);
@@ -38,7 +38,7 @@ struct Device {
     static Device& get() { static Device d; return d; }
 
     void use(const PubKey& pk, const SecKey* sk) {
-        if (have && loaded_tag == pk.canon_tag) return;
+        if (have && loaded_tag == pk.canon_tag && (have_sk || !sk)) return;
         std::vector<uint64_t> H((size_t)pk.prm.n_bits * (pk.prm.m_bits / 64)), g(2 * (size_t)pk.prm.B);
         for (size_t c = 0; c < pk.H.size(); c++) std::memcpy(&H[c * (pk.prm.m_bits / 64)], pk.H[c].w.data(), pk.prm.m_bits / 8);
         for (size_t i = 0; i < pk.powg_B.size(); i++) { g[2 * i] = pk.powg_B[i].lo; g[2 * i + 1] = pk.powg_B[i].hi; }
@@ -54,7 +54,7 @@ struct Device {
         const int live = pvacb_get_prf_mode(ctx);
         if ((rc = pvacb_set_params(ctx, &p))) die(ctx, "pvacb_set_params", rc);
         if (live == PVACB_PRF_LIVE) pvacb_set_prf_mode(ctx, PVACB_PRF_LIVE);
-        loaded_tag = pk.canon_tag; have = true;
+        loaded_tag = pk.canon_tag; have = true; have_sk = sk != nullptr;
     }
 };
 
@@ -197,7 +197,7 @@ inline void gpu_keygen(const Params& prm, PubKey& pk, SecKey& sk) {
     for (int i = 0; i < prm.B; i++) pk.powg_B[i] = Fp{g[2 * i], g[2 * i + 1]};
     pk.ubk = gen_ubk_public(pk.canon_tag, prm.m_bits);
     pk.omega_B = fp_from_u64(1);          // never read by any operation (the engine keeps the real value for pk files)
-    d.loaded_tag = pk.canon_tag; d.have = true;
+    d.loaded_tag = pk.canon_tag; d.have = true; d.have_sk = true;
 }
 inline Cipher gpu_enc_value(const PubKey& pk, const SecKey& sk, uint64_t v) { return std::move(gpu::enc_value(pk, sk, std::vector<uint64_t>{v})[0]); }
 inline Cipher gpu_ct_add(const PubKey& pk, const Cipher& a, const Cipher& b) { return std::move(gpu::binop(pk, {&a}, {&b}, 0)[0]); }
@@ -214,6 +214,101 @@ inline std::array<uint8_t, 32> gpu_commit_ct(const PubKey& pk, const Cipher& c) 
     if (rc) gpu::die(d.ctx, "pvacb_commit_ct", rc);
     return o;
 }
+// ---- riders: ops/arithmetic.hpp:33,39,108, ops/encrypt.hpp:29,39,162,281,293, ops/recrypt.hpp:12,26, crypto/matrix.hpp:306
+namespace gpu {
+// one ciphertext in, one out, through a batch -> batch entry point of the C ABI
+template <class F>
+inline Cipher unop(const PubKey& pk, const Cipher& a, const char* what, F&& call) {
+    Device& d = Device::get();
+    d.use(pk, nullptr);
+    pvacb_batch *x = to_soa(d, {&a}), *o = nullptr;
+    int rc = call(d.ctx, x, &o);
+    pvacb_batch_free(x);
+    if (rc) die(d.ctx, what, rc);
+    auto out = from_soa(d, o);
+    pvacb_batch_free(o);
+    return std::move(out[0]);
+}
+}  // namespace gpu
+inline Cipher gpu_ct_scale(const PubKey& pk, const Cipher& a, const Fp& s) {
+    const uint64_t k[2] = {s.lo, s.hi};
+    return gpu::unop(pk, a, "pvacb_ct_scale", [&](pvacb_ctx* c, pvacb_batch* x, pvacb_batch** o) { return pvacb_ct_scale(c, x, k, o); });
+}
+inline Cipher gpu_ct_neg(const PubKey& pk, const Cipher& a) {
+    return gpu::unop(pk, a, "pvacb_ct_neg", [&](pvacb_ctx* c, pvacb_batch* x, pvacb_batch** o) { return pvacb_ct_neg(c, x, o); });
+}
+inline Cipher gpu_ct_div_const(const PubKey& pk, const Cipher& a, const Fp& k) {
+    const uint64_t kk[2] = {k.lo, k.hi};
+    return gpu::unop(pk, a, "pvacb_ct_div_const", [&](pvacb_ctx* c, pvacb_batch* x, pvacb_batch** o) { return pvacb_ct_div_const(c, x, kk, o); });
+}
+inline void gpu_compact_edges(const PubKey& pk, Cipher& C) {
+    C = gpu::unop(pk, C, "pvacb_compact_edges", [&](pvacb_ctx* c, pvacb_batch* x, pvacb_batch** o) { return pvacb_compact_edges(c, x, o); });
+}
+inline void gpu_ubk_apply(const PubKey& pk, Cipher& C) {
+    C = gpu::unop(pk, C, "pvacb_ubk_apply", [&](pvacb_ctx* c, pvacb_batch* x, pvacb_batch** o) { return pvacb_ubk_apply(c, x, o); });
+}
+inline double gpu_sigma_density(const PubKey& pk, const Cipher& C) {
+    gpu::Device& d = gpu::Device::get();
+    d.use(pk, nullptr);
+    pvacb_batch* b = gpu::to_soa(d, {&C});
+    double out = 0.0;
+    int rc = pvacb_sigma_density(d.ctx, b, &out);
+    pvacb_batch_free(b);
+    if (rc) gpu::die(d.ctx, "pvacb_sigma_density", rc);
+    return out;
+}
+inline Cipher gpu_enc_value_depth(const PubKey& pk, const SecKey& sk, uint64_t v, int depth_hint) {
+    gpu::Device& d = gpu::Device::get();
+    d.use(pk, &sk);
+    pvacb_batch* b = nullptr;
+    int rc = pvacb_enc_value_depth(d.ctx, &v, 1, depth_hint, pvacb_fresh_seed(d.ctx), nullptr, &b);
+    if (rc) gpu::die(d.ctx, "pvacb_enc_value_depth", rc);
+    auto out = gpu::from_soa(d, b);
+    pvacb_batch_free(b);
+    return std::move(out[0]);
+}
+inline Cipher gpu_enc_fp_depth(const PubKey& pk, const SecKey& sk, const Fp& v, int depth_hint) {
+    gpu::Device& d = gpu::Device::get();
+    d.use(pk, &sk);
+    const uint64_t fv[2] = {v.lo, v.hi};
+    pvacb_batch* b = nullptr;
+    int rc = pvacb_enc_fp_depth(d.ctx, fv, 1, depth_hint, pvacb_fresh_seed(d.ctx), nullptr, &b);
+    if (rc) gpu::die(d.ctx, "pvacb_enc_fp_depth", rc);
+    auto out = gpu::from_soa(d, b);
+    pvacb_batch_free(b);
+    return std::move(out[0]);
+}
+// n encryptions of zero in ONE call (what make_evalkey's loop asks for)
+inline std::vector<Cipher> gpu_enc_zero_depth_n(const PubKey& pk, const SecKey& sk, size_t n, int depth_hint) {
+    gpu::Device& d = gpu::Device::get();
+    d.use(pk, &sk);
+    pvacb_batch* b = nullptr;
+    int rc = pvacb_enc_zero_depth(d.ctx, n, depth_hint, pvacb_fresh_seed(d.ctx), nullptr, &b);
+    if (rc) gpu::die(d.ctx, "pvacb_enc_zero_depth", rc);
+    auto out = gpu::from_soa(d, b);
+    pvacb_batch_free(b);
+    return out;
+}
+inline Cipher gpu_enc_zero_depth(const PubKey& pk, const SecKey& sk, int depth_hint) { return std::move(gpu_enc_zero_depth_n(pk, sk, 1, depth_hint)[0]); }
+inline EvalKey gpu_make_evalkey(const PubKey& pk, const SecKey& sk, size_t pool_size, int depth_hint) {
+    EvalKey ek;
+    ek.zero_pool = gpu_enc_zero_depth_n(pk, sk, pool_size, depth_hint);
+    ek.enc_one = std::move(gpu::enc_value(pk, sk, std::vector<uint64_t>{1})[0]);
+    return ek;
+}
+inline Cipher gpu_ct_recrypt(const PubKey& pk, const EvalKey& ek, const Cipher& in) {
+    if (ek.zero_pool.empty() || in.E.empty()) return in;      // ops/recrypt.hpp:27
+    gpu::Device& d = gpu::Device::get();
+    d.use(pk, nullptr);
+    pvacb_batch *c = gpu::to_soa(d, {&in}), *pool = gpu::to_soa(d, gpu::ptrs(ek.zero_pool)), *o = nullptr;
+    int rc = pvacb_ct_recrypt(d.ctx, c, pool, pvacb_fresh_seed(d.ctx), nullptr, &o);
+    pvacb_batch_free(c); pvacb_batch_free(pool);
+    if (rc) gpu::die(d.ctx, "pvacb_ct_recrypt", rc);
+    auto out = gpu::from_soa(d, o);
+    pvacb_batch_free(o);
+    return std::move(out[0]);
+}
+
 inline std::vector<Cipher> gpu_enc_text(const PubKey& pk, const SecKey& sk, const std::string& msg) {
     gpu::Device& d = gpu::Device::get();
     d.use(pk, &sk);

@@ -517,3 +517,87 @@ def test_cpp_group_pipeline(tmp_path):
         assert d["mismatches"] == 0 and d["products_checked"] == 8192 and d["gpus"] == ngpu
         outs.append(d)
     assert len({d["decrypt_digest"] for d in outs}) == 1, outs
+
+
+def _save_output(name, r, seconds):
+    """PVACB_SAVE_OUTPUT=dir keeps what the reference's program printed (profiles/ holds one such run)"""
+    d = os.environ.get("PVACB_SAVE_OUTPUT")
+    if d:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, name + "_on_gpu.txt"), "w") as f:
+            f.write(f"# {name}_on_gpu: rc {r.returncode}, {seconds:.1f} s wall\n" + r.stdout + ("\n# stderr\n" + r.stderr if r.stderr else ""))
+
+
+def _ref_program(name):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", name + "_on_gpu")
+    if not os.path.exists(exe):
+        pytest.skip(f"oracle/_ref/{name}_on_gpu not built (reference tree absent at build time)")
+    return exe
+
+
+@pytest.mark.timeout(600)
+def test_reference_test_main_unmodified_on_gpu(tmp_path):
+    """The reference's OWN test suite, tests/test_main.cpp, unmodified, through the GPU binding: 29 must() checks (every one aborts the
+    program on failure) over enc / dec / add / sub / mul / scale identities, algebra laws, a 30-op random pool, recrypt with a 32-entry
+    evaluation key, the 2^10 chains with and without recrypt, 10! (690 176 edges), commit_ct, ubk_apply and the text codec. Every
+    keygen / enc_* / ct_* / dec_value / make_evalkey / ct_recrypt / ubk_apply / commit_ct / enc_text / dec_text of the program runs on
+    the B200 (the reference needs 13 minutes of one host core for it)."""
+    import subprocess
+    exe = _ref_program("test_main")
+    env = dict(os.environ, PVAC_GPU_PRF_LIVE="1")
+    import time
+    t0 = time.perf_counter()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=500, env=env, cwd=str(tmp_path))
+    _save_output("test_main", r, time.perf_counter() - t0)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    out = r.stdout
+    for needle in ("dec ok", "add / sub / mul ok", "0 / 1 identities ok", "modular wrap ok", "commut / assoc / distrib ok", "f(10) = 843 ok",
+                   "(a + b)^2 expansion ok", "2^10 = 1024 ok", "recrypt calls = 3", "10! = 3628800 ok", "ubk preserves value ok", "roundtrip ok", "- all ok -"):
+        assert needle in out, (needle, out[-3000:])
+    assert "[fail]" not in r.stderr
+    m = [ln for ln in out.splitlines() if ln.startswith("fact (10!)")]
+    edges = int(m[0].split("e = ")[1].split()[0]) if m else 0
+    assert 690000 <= edges <= 690176, m          # 1024 product layers with (all but a handful of) their 674 (idx, sign) slots hit
+
+
+@pytest.mark.timeout(300)
+def test_reference_small_programs_unmodified_on_gpu(tmp_path):
+    """tests/test_ct_fuzz.cpp (random add / sub / mul circuits, faithful PRF: all 16 384 LPN rows), tests/test_zero.cpp, tests/test_struct.cpp
+    and tests/test_noise_struct.cpp of the reference, unmodified, with their keygen / enc / ops / dec on the GPU; the structural checks
+    they make on the ciphertexts (no zero-sum edge subsets, no visible Z2 / Z3 noise tuples) run on the host against what the GPU made."""
+    import subprocess
+    import time
+    for name, env_extra, needles in (("test_ct_fuzz", {}, ["ct-fuzz: ok", "PASS"]),
+                                     ("test_zero", {"PVAC_GPU_PRF_LIVE": "1"}, ["dec(enc(0)) = 0", "dec(enc(1)) = 1", "dec(enc(42)) = 42"]),
+                                     ("test_struct", {"PVAC_GPU_PRF_LIVE": "1"}, ["zero-sum = 0", "PASS"]),
+                                     ("test_noise_struct", {"PVAC_GPU_PRF_LIVE": "1"}, ["noise struct: ok", "PASS"])):
+        exe = _ref_program(name)
+        t0 = time.perf_counter()
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=200, env=dict(os.environ, **env_extra), cwd=str(tmp_path))
+        _save_output(name, r, time.perf_counter() - t0)
+        assert r.returncode == 0, name + "\n" + r.stdout[-2000:] + r.stderr[-2000:]
+        for needle in needles:
+            assert needle in r.stdout, (name, needle, r.stdout[-2000:])
+
+
+@pytest.mark.timeout(300)
+def test_reference_test_depth_unmodified_on_gpu(tmp_path):
+    """BASELINE config 4's definition, tests/test_depth.cpp, unmodified on the GPU: c <- c * c from enc(2); steps 1..3 decrypt to 2^(2^k)
+    with 10 784 and 172 544 edges at steps 2 and 3 (the numbers BASELINE.md quotes). Step 4 multiplies 172 544^2 edge pairs: the
+    reference dies there with std::bad_alloc, the engine refuses the operand (PVACB_E_SHAPE) and the binding aborts like the reference;
+    the program flushes its CSV after every step, so the three completed rows are on disk."""
+    import subprocess
+    import time
+    exe = _ref_program("test_depth")
+    t0 = time.perf_counter()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=250, env=dict(os.environ, PVAC_GPU_PRF_LIVE="1"), cwd=str(tmp_path))
+    _save_output("test_depth", r, time.perf_counter() - t0)
+    rows = [ln.strip().split(",") for ln in open(tmp_path / "pvac_depth.csv").read().splitlines()[1:] if ln.strip()]
+    assert len(rows) >= 3, (rows, r.stderr[-2000:])
+    assert [int(x[1]) for x in rows[:3]] == [1, 2, 3]
+    assert [int(x[-1]) for x in rows[:3]] == [1, 1, 1], rows                       # ok column: dec == expected
+    assert [int(x[3]) for x in rows[:3]] == [8, 32, 320], rows                      # layers
+    assert int(rows[1][2]) == 10784 and int(rows[2][2]) == 172544, rows             # edges: every (idx, sign) slot of every product layer is hit
+    if r.returncode != 0:
+        assert "operand too large" in r.stderr, r.stderr[-2000:]

@@ -542,8 +542,14 @@ def test_reference_test_main_unmodified_on_gpu(tmp_path):
     program on failure) over enc / dec / add / sub / mul / scale identities, algebra laws, a 30-op random pool, recrypt with a 32-entry
     evaluation key, the 2^10 chains with and without recrypt, 10! (690 176 edges), commit_ct, ubk_apply and the text codec. Every
     keygen / enc_* / ct_* / dec_value / make_evalkey / ct_recrypt / ubk_apply / commit_ct / enc_text / dec_text of the program runs on
-    the B200 (the reference needs 13 minutes of one host core for it)."""
+    the B200 (the reference needs 13 minutes of one host core for it).
+    OPT-IN (PVACB_REF_TEST_MAIN=1) and, unlike the other programs below, NOT yet run to completion on a GPU: the program's own statistics
+    (s_byte_ent: one std::map update per syndrome byte, 38 s per 690 176-edge ciphertext, called four times -- measured on the host,
+    profiles/r02_notes.md section 6) keep the process busy for about 2.5 minutes whatever executes the homomorphic operations, and the one
+    attempt of round 2 was cut off after 75 s when the round's GPU time ended."""
     import subprocess
+    if os.environ.get("PVACB_REF_TEST_MAIN") != "1":
+        pytest.skip("opt-in: PVACB_REF_TEST_MAIN=1 (about 3 minutes, most of it the program's own host-side statistics)")
     exe = _ref_program("test_main")
     env = dict(os.environ, PVAC_GPU_PRF_LIVE="1")
     import time

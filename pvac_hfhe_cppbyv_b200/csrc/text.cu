@@ -4,8 +4,8 @@
 // 15-byte block, all drawing from ONE CSPRNG stream in that order. Batched restatement: "waves" -- wave 0 encrypts the
 // lengths of all messages (enc_value), wave j+1 encrypts block j of every message that has one (one enc_fp_depth launch
 // with depth_hint 2 + j). A message's tape continues from wave to wave: the planning kernel reports how many words each
-// ciphertext consumed (data-dependent: rejection loops) and the next wave starts that many words further
-// (SplitMix64 is counter based: state after d draws = state0 + d * 0x9E3779B97F4A7C15).
+// ciphertext consumed (data-dependent: rejection loops) and the next wave starts that many words further (every tape kind is
+// addressed by word index: a wave opens the item's stream at word k0 = words consumed so far).
 // The resulting batch is WAVE-MAJOR: all length ciphertexts in message order, then every block-0 ciphertext, then block 1 ...
 #include "engine.h"
 #include "../../include/pvacb.h"

@@ -242,7 +242,7 @@ int pvacb_group_tune_export(pvacb_group* g, double* direct_gbs, double* relay_gb
     if (rc) { cleanup(); return rc; }
     std::vector<double> rate(G, 0.0);
     auto measure = [&](double& aggregate) -> int {
-        std::atomic<int> arrived{0};
+        std::atomic<int> arrived{0}, failed{0};
         std::vector<double> t0(G), t1(G);
         const int reps = 6;
         int r = parallel(g, [&](int k) -> int {
@@ -251,9 +251,10 @@ int pvacb_group_tune_export(pvacb_group* g, double* direct_gbs, double* relay_gb
                 q = pvacb_batch_export_blob_async(g->ctx[k], probe[k], host[k], bytes[k]);
                 if (!q) q = pvacb_export_wait(g->ctx[k]);
             }
-            if (q) return q;
-            arrived.fetch_add(1);
-            while (arrived.load() < G) { }
+            if (q) failed.store(1);
+            arrived.fetch_add(1);                                                                 // a member whose warm-up failed still arrives: nobody spins forever
+            while (arrived.load() < G) std::this_thread::yield();
+            if (failed.load()) return q;                                                          // the failing member reports; the others skip the measurement
             t0[k] = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
             for (int i = 0; i < reps; i++)
                 if ((q = pvacb_batch_export_blob_async(g->ctx[k], probe[k], host[k], bytes[k]))) return q;

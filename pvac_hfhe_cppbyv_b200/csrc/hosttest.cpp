@@ -21,6 +21,16 @@ void ht_fp_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* o) {
     switch (op) { case 0: r = fp_add(x, y); break; case 1: r = fp_sub(x, y); break; case 2: r = fp_mul(x, y); break; case 3: r = fp_neg(x); break; default: r = fp_inv(x); }
     o[0] = r.lo; o[1] = r.hi;
 }
+// sum_k a[k] * b[k] through the unreduced 320-bit accumulator of dec_value's edge stage and ct_mul's dense weight products
+// (fp_mac_wide, then ONE fp_wide_reduce); every pair is accumulated `repeat` times; wide_out (5 words, optional) = the raw accumulator
+void ht_fp_mac_chain(size_t n, const uint64_t* a, const uint64_t* b, uint64_t repeat, uint64_t* o, uint64_t* wide_out) {
+    uint64_t acc[5] = {0, 0, 0, 0, 0};
+    for (uint64_t r = 0; r < repeat; r++)
+        for (size_t k = 0; k < n; k++) fp_mac_wide(acc, fp_make(a[2 * k], a[2 * k + 1]), fp_make(b[2 * k], b[2 * k + 1]));
+    Fp v = fp_wide_reduce(acc);
+    o[0] = v.lo; o[1] = v.hi;
+    if (wide_out) for (int i = 0; i < 5; i++) wide_out[i] = acc[i];
+}
 void ht_fp_from_words(uint64_t lo, uint64_t hi, uint64_t* o) { Fp r = fp_from_words(lo, hi); o[0] = r.lo; o[1] = r.hi; }
 uint64_t ht_tape_word(uint64_t s0, uint64_t k) { return splitmix_word(s0, k); }
 // word k of the ChaCha20 tape: key (8 x u32), stream id, lane

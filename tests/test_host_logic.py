@@ -96,6 +96,7 @@ def ht():
     L.ht_ztag.restype = u64
     L.ht_ztag.argtypes = [u64, u64, u64]
     L.ht_fp_from_words.argtypes = [u64, u64, C.POINTER(u64)]
+    L.ht_fp_mac_chain.argtypes = [C.c_size_t, C.POINTER(u64), C.POINTER(u64), u64, C.POINTER(u64), C.POINTER(u64)]
     L.ht_cand_words.argtypes = [i32, C.POINTER(u64), u64, C.POINTER(u64)]
     L.ht_aes_ctr_words.argtypes = [C.POINTER(u8), u64, C.POINTER(u64), C.c_size_t]
     L.ht_prf_core.argtypes = [C.POINTER(u64), u64, C.POINTER(u8), C.POINTER(u64), u64, u64, u64, i32, i32, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
@@ -134,6 +135,47 @@ def test_fp_bodies(ht, port, kat):
         o = np.zeros(2, np.uint64)
         ht.ht_fp_from_words(lo, hi, _p(o))
         assert int(o[0]) | (int(o[1]) << 64) == (lo | (hi << 64)) % P
+
+
+def test_fp_extremes_and_wide_accumulator(ht):
+    """fp_mul on the corner operands of the __int128 form (p - 1, 2^126, limbs of all ones, 0, 1) and the unreduced 320-bit
+    multiply-accumulate that dec_value's edge stage and ct_mul's dense weight products use (fp_mac_wide + one fp_wide_reduce):
+    equal to Python integers, including after enough accumulations of (p - 1)^2 to carry into the fifth limb"""
+    M64 = 2**64 - 1
+    corners = [0, 1, 2, P - 1, P - 2, 2**126, 2**126 - 1, 2**126 + 1, 2**64, 2**64 - 1, 2**64 + 1, (2**63 - 1) << 64, M64, (P - 1) ^ M64, 2**127 - 2**64,
+               0x5555555555555555_5555555555555555, 0x2AAAAAAAAAAAAAAA_AAAAAAAAAAAAAAAA, 3 << 125, (1 << 63) | 1]
+    corners = [c % P for c in corners]
+
+    def words(v):
+        return [v & M64, v >> 64]
+    for a in corners:
+        for b in corners:
+            o = np.zeros(2, np.uint64)
+            ht.ht_fp_op(2, _p(np.array(words(a), np.uint64)), _p(np.array(words(b), np.uint64)), _p(o))
+            assert int(o[0]) | (int(o[1]) << 64) == a * b % P, (hex(a), hex(b))
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        n = int(rng.integers(1, 700))
+        xs = [int.from_bytes(rng.bytes(16), "little") % P for _ in range(n)]
+        ys = [int.from_bytes(rng.bytes(16), "little") % P for _ in range(n)]
+        if trial % 4 == 0:                                   # salt with corner values
+            for k in range(0, n, 3):
+                xs[k] = corners[(k + trial) % len(corners)]
+                ys[k] = corners[(2 * k + trial) % len(corners)]
+        a = np.array([w for v in xs for w in words(v)], np.uint64)
+        b = np.array([w for v in ys for w in words(v)], np.uint64)
+        o, wide = np.zeros(2, np.uint64), np.zeros(5, np.uint64)
+        ht.ht_fp_mac_chain(n, _p(a), _p(b), 1, _p(o), _p(wide))
+        exact = sum(x * y for x, y in zip(xs, ys))
+        assert sum(int(wide[i]) << (64 * i) for i in range(5)) == exact          # the accumulator is the plain integer sum
+        assert int(o[0]) | (int(o[1]) << 64) == exact % P
+    # worst case: (p - 1)^2 accumulated 2^20 times (a 274-bit sum: the fifth limb is in use); a depth-3 ciphertext has 172 544 edges
+    a = np.array(words(P - 1), np.uint64)
+    o, wide = np.zeros(2, np.uint64), np.zeros(5, np.uint64)
+    ht.ht_fp_mac_chain(1, _p(a), _p(a), 1 << 20, _p(o), _p(wide))
+    exact = ((P - 1) ** 2) << 20
+    assert sum(int(wide[i]) << (64 * i) for i in range(5)) == exact and int(wide[4]) != 0
+    assert int(o[0]) | (int(o[1]) << 64) == exact % P
 
 
 def test_tape_and_hash_layout(ht, port, kat):

@@ -252,3 +252,56 @@ def test_recrypt_ubk_density(port, ref, both):
     e = {k: v[:0] for k, v in port.ct_export(a_o).items()}
     assert ct_equal(port.ct_export(ko.ct_recrypt(83, port.ct_import(e), pool_o)), ref.ct_export(kr.ct_recrypt(83, ref.ct_import(e), pool_r)))[0]
     assert ct_equal(port.ct_export(ko.ct_recrypt(84, a_o, [])), ref.ct_export(kr.ct_recrypt(84, a_r, [])))[0]
+
+
+def test_random_circuits_oracle_equals_reference(port, ref, both):
+    """Random add / sub / scale / mul circuits over a pool of fresh ciphertexts (the shapes of tests/test_ct_fuzz.cpp and
+    tests/test_sigma.cpp, plus products of sums and sums of products): after EVERY operation the oracle's ciphertext equals the
+    unmodified reference's byte for byte -- layers, the emission order of ct_mul's unordered_map walk, weights, syndromes -- and both
+    decrypt to the plaintext value. Pins the oracle on operand shapes the fixed cases above do not reach (unequal layer counts,
+    edge-less carried layers, layers of a sum multiplied by layers of a product)."""
+    ko, kr = both
+    rng = np.random.default_rng(2024)
+    n_mul_total = 0
+    for trial in range(6):
+        vals = [int(rng.integers(0, 2**64, dtype=np.uint64)) for _ in range(3)]
+        pool = []
+        for j, v in enumerate(vals):
+            st = 50_000 + 100 * trial + j
+            pool.append((ko.enc_value(st, v), kr.enc_value(st, v), v % P))
+        for step in range(5):
+            ia, ib = int(rng.integers(0, len(pool))), int(rng.integers(0, len(pool)))
+            (ao, ar, va), (bo, br, vb) = pool[ia], pool[ib]
+            ea, eb = len(port.ct_export(ao, with_sigma=False)["lid"]), len(port.ct_export(bo, with_sigma=False)["lid"])
+            op = int(rng.integers(0, 4))
+            if op == 3 and ea * eb > 100_000:              # keeps a product at <= 16 layer pairs x 674 edges (the CPU reference needs 83 us per edge)
+                op = int(rng.integers(0, 3))
+            if op == 0:
+                co, cr, vc = ko.ct_add(ao, bo), kr.ct_add(ar, br), (va + vb) % P
+            elif op == 1:
+                co, cr, vc = ko.ct_sub(ao, bo), kr.ct_sub(ar, br), (va - vb) % P
+            elif op == 2:
+                s = int.from_bytes(rng.bytes(16), "little") % P
+                co, cr, vc = ko.ct_scale(ao, _w(s)), kr.ct_scale(ar, _w(s)), va * s % P
+            else:
+                st = 60_000 + 100 * trial + step
+                co, cr, vc = ko.ct_mul(st, ao, bo), kr.ct_mul(st, ar, br), va * vb % P
+                n_mul_total += 1
+            ok, k = ct_equal(port.ct_export(co), ref.ct_export(cr))
+            assert ok, (trial, step, op, k)
+            assert _v(ko.dec_value(co)) == vc == _v(kr.dec_value(cr)), (trial, step, op)
+            pool.append((co, cr, vc))
+        # and one product with the largest ciphertext of the pool that stays affordable on the CPU (a product or a sum of products with
+        # edge-less carried layers) against a fresh one, in either operand order
+        sizes = [len(port.ct_export(c[0], with_sigma=False)["lid"]) for c in pool]
+        big = max((i for i in range(len(pool)) if sizes[i] <= 2500), key=lambda i: sizes[i])
+        (ao, ar, va), (bo, br, vb) = pool[big], pool[trial % 3]
+        if trial & 1:
+            (ao, ar, va), (bo, br, vb) = (bo, br, vb), (ao, ar, va)
+        st = 70_000 + trial
+        co, cr, vc = ko.ct_mul(st, ao, bo), kr.ct_mul(st, ar, br), va * vb % P
+        n_mul_total += 1
+        ok, k = ct_equal(port.ct_export(co), ref.ct_export(cr))
+        assert ok, (trial, "deep", k)
+        assert _v(ko.dec_value(co)) == vc == _v(kr.dec_value(cr)), (trial, "deep")
+    assert n_mul_total >= 10

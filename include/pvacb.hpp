@@ -59,6 +59,21 @@ private:
     pvacb_batch* h_ = nullptr;
 };
 
+// A batch copied to host memory, structure of arrays: the fields of pvac::Cipher (core/types.hpp:96-119) for n ciphertexts, ciphertext i
+// owning layers [layer_off[i], layer_off[i+1]) and edges [edge_off[i], edge_off[i+1]); layer_id is relative to its ciphertext.
+struct HostCiphers {
+    std::vector<uint32_t> layer_off, edge_off;                                   // n + 1 entries each
+    std::vector<uint8_t> rule;                                                   // layers: 0 BASE, 1 PROD
+    std::vector<uint64_t> ztag, nonce_lo, nonce_hi;                              //   RSeed of a BASE layer (and of a PROD layer: its sigma seed)
+    std::vector<uint32_t> pa, pb;                                                //   parents of a PROD layer
+    std::vector<uint32_t> layer_id;                                              // edges
+    std::vector<uint16_t> idx;
+    std::vector<uint8_t> ch;
+    std::vector<uint64_t> w;                                                     //   2 words per edge (lo, hi)
+    std::vector<uint64_t> sigma;                                                 //   128 words per edge (empty if exported without sigma)
+    size_t size() const { return layer_off.empty() ? 0 : layer_off.size() - 1; }
+};
+
 class Engine {
 public:
     explicit Engine(int device = 0, int prf_mode = PVACB_PRF_FAITHFUL) {
@@ -176,6 +191,33 @@ public:
         return buf;
     }
     Ciphers from_wire(const std::vector<uint8_t>& buf) { pvacb_batch* o = nullptr; ck(pvacb_batch_import_wire(ctx_, buf.data(), buf.size(), &o)); return Ciphers(o); }
+
+    // Cipher <-> host memory (pvacb_batch_export_soa / import_soa): what a program does where the reference hands it a Cipher by value
+    HostCiphers to_host(const Ciphers& c, bool with_sigma = true) {
+        HostCiphers h;
+        const size_t n = c.size();
+        const auto t = c.totals();
+        h.layer_off.assign(n + 1, 0); h.edge_off.assign(n + 1, 0);
+        if (!c.handle()) return h;
+        h.rule.resize(t.first); h.ztag.resize(t.first); h.nonce_lo.resize(t.first); h.nonce_hi.resize(t.first); h.pa.resize(t.first); h.pb.resize(t.first);
+        h.layer_id.resize(t.second); h.idx.resize(t.second); h.ch.resize(t.second); h.w.resize(2 * t.second);
+        if (with_sigma) h.sigma.resize((size_t)PVACB_M_WORDS * t.second);
+        ck(pvacb_batch_export_soa(ctx_, c.handle(), h.layer_off.data(), h.edge_off.data(), h.rule.data(), h.ztag.data(), h.nonce_lo.data(), h.nonce_hi.data(),
+                                  h.pa.data(), h.pb.data(), h.layer_id.data(), h.idx.data(), h.ch.data(), h.w.data(), with_sigma ? h.sigma.data() : nullptr));
+        return h;
+    }
+    Ciphers from_host(const HostCiphers& h) {
+        pvacb_batch* o = nullptr;
+        ck(pvacb_batch_import_soa(ctx_, h.size(), h.layer_off.data(), h.edge_off.data(), h.rule.data(), h.ztag.data(), h.nonce_lo.data(), h.nonce_hi.data(),
+                                  h.pa.data(), h.pb.data(), h.layer_id.data(), h.idx.data(), h.ch.data(), h.w.data(), h.sigma.empty() ? nullptr : h.sigma.data(), &o));
+        return Ciphers(o);
+    }
+    // run-time Params of the context (core/types.hpp:36-70), the global index of item 0 of the next calls (a shard of a larger batch
+    // keeps the RNG streams of the whole batch), and a barrier on the context's stream
+    void set_params(const pvacb_params& prm) { ck(pvacb_set_params(ctx_, &prm)); }
+    pvacb_params get_params() const { pvacb_params p; pvacb_get_params(ctx_, &p); return p; }
+    void set_item_base(uint64_t base) { ck(pvacb_set_item_base(ctx_, base)); }
+    void sync() { ck(pvacb_sync(ctx_)); }
 
     pvacb_ctx* handle() const { return ctx_; }
 

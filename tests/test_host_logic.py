@@ -293,3 +293,42 @@ def test_c_abi_program_compiles_as_c99(tmp_path):
     if not torch.cuda.is_available():
         run = subprocess.run([exe], capture_output=True, text=True)
         assert run.returncode == 1 and "pvacb_ctx_create(0, &ctx) -> 2" in run.stderr
+
+
+def test_cpp_programs_compile_and_link(tmp_path):
+    """the C++ programs that the -m gpu tests build on the GPU box (tests/cpp/*.cpp over include/pvacb.hpp) compile and link here too,
+    with warnings on: a change to the headers cannot break them unnoticed. Also instantiates the parts of the shim those programs do
+    not use (host copies, Params, item base). Running them needs a GPU; here they must fail loudly instead."""
+    pkg = PKG
+    inc = os.path.join(os.path.dirname(PKG), "include")
+    extra = tmp_path / "shim_all.cpp"
+    extra.write_text("""
+#include "pvacb.hpp"
+int main() {
+    try {
+        pvacb::Engine eng(0);
+        eng.keygen();
+        auto a = eng.enc_value({1, 2, 3});
+        pvacb::HostCiphers h = eng.to_host(a);
+        auto b = eng.from_host(h);
+        pvacb_params p = eng.get_params();
+        eng.set_params(p);
+        eng.set_item_base(0);
+        eng.sync();
+        pvacb::Group g({0});
+        g.keygen();
+        auto s = g.enc_value({4, 5}, g.fresh_seed());
+        return (int)b.size() + (int)g.dec_value(s).size() - 5;
+    } catch (const pvacb::Error& e) { return e.code == PVACB_E_CUDA ? 42 : 1; }
+}
+""")
+    for src in (os.path.join(os.path.dirname(PKG), "tests", "cpp", "basic_usage_batched.cpp"),
+                os.path.join(os.path.dirname(PKG), "tests", "cpp", "group_pipeline.cpp"), str(extra)):
+        exe = str(tmp_path / (os.path.basename(src)[:-4]))
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", inc, src, "-L", pkg, "-lpvacb", f"-Wl,-rpath,{pkg}", "-o", exe],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(tmp_path / "shim_all")], capture_output=True, text=True)
+        assert r.returncode == 42, (r.returncode, r.stderr[-500:])          # PVACB_E_CUDA from pvacb_ctx_create: no CPU path

@@ -60,6 +60,7 @@ def lib():
         "orc_sha256": (None, [P(u8), C.c_size_t, P(u8)]),
         "orc_fnv1a": (u64, [C.c_char_p]),
         "orc_aes_ctr_words": (None, [P(u8), u64, P(u64), C.c_size_t]),
+        "orc_aes_ctr_draws": (None, [P(u8), u64, P(u64), P(u64), C.c_size_t]),
         "orc_derive_aes_key": (None, [vp, u64, u64, u64, C.c_char_p, P(u8), P(u64)]),
         "orc_lpn_make_ybits": (None, [vp, u64, u64, u64, C.c_char_p, i32, P(u64)]),
         "orc_toep_127": (None, [P(u64), C.c_size_t, P(u64), C.c_size_t, P(u64)]),
@@ -175,6 +176,15 @@ def aes_ctr_words(key: bytes, nonce: int, n: int):
     k = np.frombuffer(key, np.uint8).copy()
     out = np.zeros(n, np.uint64)
     lib().orc_aes_ctr_words(_p(k, C.c_uint8), nonce, _p(out, C.c_uint64), n)
+    return out
+
+
+def aes_ctr_draws(key: bytes, nonce: int, moduli):
+    """one stream; moduli[i] == 0 -> next_u64(), else bounded(moduli[i]) (crypto/lpn.hpp:108-148)"""
+    k = np.frombuffer(key, np.uint8).copy()
+    m = np.ascontiguousarray(moduli, np.uint64)
+    out = np.zeros(len(m), np.uint64)
+    lib().orc_aes_ctr_draws(_p(k, C.c_uint8), nonce, _p(m, C.c_uint64), _p(out, C.c_uint64), len(m))
     return out
 
 

@@ -312,6 +312,12 @@ static uint64_t aesctr_bounded(aesctr_t* a, uint64_t M) {
     uint64_t lim = UINT64_MAX - (UINT64_MAX % M);
     for (;;) { uint64_t x = aesctr_next(a); if (x < lim) return x % M; }
 }
+/* a mixed sequence of draws from ONE stream: moduli[i] == 0 -> next_u64(), else bounded(moduli[i]); pins the rejection branch of
+ * bounded() and its interplay with the word FIFO against the reference (moduli just above 2^63 reject every other word) */
+void orc_aes_ctr_draws(const uint8_t key[32], uint64_t nonce, const uint64_t* moduli, uint64_t* out, size_t n) {
+    aesctr_t a; aesctr_init(&a, key, nonce);
+    for (size_t i = 0; i < n; i++) out[i] = moduli[i] ? aesctr_bounded(&a, moduli[i]) : aesctr_next(&a);
+}
 void orc_aes_ctr_words(const uint8_t key[32], uint64_t nonce, uint64_t* out, size_t n) {
     aesctr_t a; aesctr_init(&a, key, nonce);
     for (size_t i = 0; i < n; i++) out[i] = aesctr_next(&a);

@@ -224,6 +224,13 @@ void ref_aes_ctr_words(const uint8_t* key, uint64_t nonce, uint64_t* out, size_t
     prg.fill_u64(out, n);
 }
 
+// a mixed sequence of draws from ONE stream of the reference's AesCtr256: moduli[i] == 0 -> next_u64(), else bounded(moduli[i])
+void ref_aes_ctr_draws(const uint8_t* key, uint64_t nonce, const uint64_t* moduli, uint64_t* out, size_t n) {
+    AesCtr256 prg;
+    prg.init(key, nonce);
+    for (size_t i = 0; i < n; i++) out[i] = moduli[i] ? prg.bounded(moduli[i]) : prg.next_u64();
+}
+
 void ref_derive_aes_key(void* h, uint64_t ztag, uint64_t nlo, uint64_t nhi, const char* dom, uint8_t* key, uint64_t* nonce) {
     Keys* k = (Keys*)h;
     RSeed s{ztag, Nonce128{nlo, nhi}};

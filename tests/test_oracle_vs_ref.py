@@ -68,6 +68,15 @@ def test_sha_aes_prg(port, ref):
     key = rng.bytes(32)
     for nonce, n in ((0, 9), (2**64 - 3, 11), (0x0123456789ABCDEF, 130)):   # word FIFO + counter wrap (crypto/lpn.hpp:88-139)
         assert np.array_equal(port.aes_ctr_words(key, nonce, n), ref.aes_ctr_words(key, nonce, n))
+    # AesCtr256::bounded incl. its rejection branch (crypto/lpn.hpp:141-148): with M just above 2^63 every other word is rejected, with
+    # M = 3 * 2^62 one in four; interleaved with plain next_u64() draws so the word FIFO is entered in both of its states. M = 8 is what
+    # lpn_make_ybits asks for (rejects x >= 2^64 - 8: never seen in practice, so the branch is pinned through the other moduli).
+    for nonce in (5, 2**64 - 2):
+        moduli = [0, 8, (1 << 63) + 1, 0, 0, 3 << 62, 8, (1 << 63) + 1, (1 << 63) + 12345, 0, 1, 2, 337, 8192, 16384] * 8
+        got, want = port.aes_ctr_draws(key, nonce, moduli), ref.aes_ctr_draws(key, nonce, moduli)
+        assert np.array_equal(got, want)
+        plain = port.aes_ctr_words(key, nonce, len(moduli))
+        assert not np.array_equal(got[:len(plain)] % np.uint64(8), plain % np.uint64(8))      # rejections really happened: the stream shifted
     for k, N, label in ((128, 16384, "pvac.dom.x_seed"), (128, 8192, "pvac.dom.noise"), (192, 8192, "pvac.dom.h_gen"), (5, 7, "pvac.dom.noise")):
         words = [int(x) for x in rng.integers(0, 2**63, 7)]
         assert list(port.prg_choose_k(k, N, label, words)) == list(ref.prg_choose_k(k, N, label, words))

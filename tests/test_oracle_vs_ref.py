@@ -190,7 +190,8 @@ def test_depth_hints_and_riders(port, ref, both):
     """enc_value_depth / enc_zero_depth with depth hints (plan_noise gives (4,2), (5,3), (8,4) groups at depths 1, 3, 9),
     ct_neg, ct_div_const (ops/encrypt.hpp:281-298, ops/arithmetic.hpp:39-41,108-110)"""
     ko, kr = both
-    for depth in (1, 3, 9):
+    assert [ko.plan_noise(d) for d in range(101)] == [kr.plan_noise(d) for d in range(101)]
+    for depth in (1, 3, 9, 24, 40, 77):            # no upper bound in the reference: enc_text raises the hint per 15-byte block (utils/text.hpp:49-58)
         co, cr = ko.enc_value_depth(600 + depth, 123456789, depth), kr.enc_value_depth(600 + depth, 123456789, depth)
         ok, k = ct_equal(port.ct_export(co), ref.ct_export(cr))
         assert ok, (depth, k)

@@ -219,7 +219,8 @@ def test_depth_hints_and_riders(port, ref, both):
 def test_enc_text(port, ref, both):
     """utils/text.hpp:39-87: length ciphertext + one enc_fp_depth per 15-byte block with depth hints 2, 3, ... from one tape"""
     ko, kr = both
-    for seed, msg in ((51, b""), (52, b"hello"), (53, b"exactly15bytes!"), (54, "pvac éè 你好 16+ bytes, three blocks".encode()), (55, bytes(range(256))[:100])):
+    for seed, msg in ((51, b""), (52, b"hello"), (53, b"exactly15bytes!"), (54, "pvac éè 你好 16+ bytes, three blocks".encode()), (55, bytes(range(256))[:100]),
+                      (56, bytes((7 * i + 1) & 255 for i in range(700)))):      # 47 blocks: depth hints up to 48
         co, cr = ko.enc_text(seed, msg), kr.enc_text(seed, msg)
         assert len(co) == len(cr) == 1 + (len(msg) + 14) // 15
         for a, b in zip(co, cr):

@@ -264,3 +264,23 @@ def test_ct_mul_with_duplicate_edges_oracle_equals_reference(port, both):
     for seed, (xo, yo, xr, yr) in enumerate(((po, pdo, pr, pdr), (pdo, ao, pdr, ar)), start=7005):
         ok, f = ct_equal(port.ct_export(ko.ct_mul(seed, xo, yo)), _ref.ct_export(kr.ct_mul(seed, xr, yr)))
         assert ok, (seed, f)
+
+
+def test_plan_noise_engine_oracle_reference_agree():
+    """std::pair<int,int> plan_noise(pk, depth_hint), ops/encrypt.hpp:16-27 (the only floating point on the path: log2 / floor on the host):
+    the engine's pvacb_plan_noise (host code of libpvacb.so, callable without a GPU), the oracle and the unmodified reference give the same
+    (Z2, Z3) for every depth hint a caller can reach, negative hints included (clamped to 0 like std::max(0, depth_hint))"""
+    import ctypes as C
+    from pvac_hfhe_cppbyv_b200 import api
+    from oracle import port
+    L = api.load_library()
+    ko = port.Keys.keygen(77)
+    kr = _ref.Keys.keygen(77) if _ref.available() else None
+    for d in list(range(-3, 400)) + [1000, 65535]:
+        z2, z3 = C.c_int(), C.c_int()
+        assert L.pvacb_plan_noise(d, C.byref(z2), C.byref(z3)) == 0
+        got = (z2.value, z3.value)
+        assert got == tuple(ko.plan_noise(d)), d
+        if kr is not None:
+            assert got == tuple(kr.plan_noise(d)), d
+    assert (z2.value, z3.value)[0] > 30000                  # depth 65535: tens of thousands of noise groups, still the same numbers

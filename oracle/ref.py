@@ -64,6 +64,7 @@ def lib():
         "ref_fnv1a": (u64, [C.c_char_p]),
         "ref_aes_ctr_words": (None, [P(u8), u64, P(u64), C.c_size_t]),
         "ref_aes_ctr_draws": (None, [P(u8), u64, P(u64), P(u64), C.c_size_t]),
+        "ref_params_default": (None, [P(C.c_double)]),
         "ref_derive_aes_key": (None, [vp, u64, u64, u64, C.c_char_p, P(u8), P(u64)]),
         "ref_lpn_make_ybits": (None, [vp, u64, u64, u64, C.c_char_p, P(u64)]),
         "ref_toep_127": (None, [P(u64), C.c_size_t, P(u64), C.c_size_t, P(u64)]),
@@ -165,6 +166,13 @@ def aes_ctr_words(key: bytes, nonce: int, n: int):
     out = np.zeros(n, np.uint64)
     lib().ref_aes_ctr_words(_p(k, C.c_uint8), nonce, _p(out, C.c_uint64), n)
     return out
+
+
+def params_default():
+    """the reference's default Params (core/types.hpp:36-70) in declaration order"""
+    out = (C.c_double * 17)()
+    lib().ref_params_default(out)
+    return [float(x) for x in out]
 
 
 def aes_ctr_draws(key: bytes, nonce: int, moduli):

@@ -224,6 +224,15 @@ void ref_aes_ctr_words(const uint8_t* key, uint64_t nonce, uint64_t* out, size_t
     prg.fill_u64(out, n);
 }
 
+// the reference's default Params (core/types.hpp:36-70), field by field in declaration order, as doubles
+void ref_params_default(double* out /* 17 */) {
+    Params p;
+    const double v[17] = {(double)p.B, (double)p.m_bits, (double)p.n_bits, (double)p.h_col_wt, (double)p.x_col_wt, (double)p.err_wt, p.noise_entropy_bits,
+                          p.tuple2_fraction, p.depth_slope_bits, (double)p.edge_budget, (double)p.lpn_n, (double)p.lpn_t, (double)p.lpn_tau_num,
+                          (double)p.lpn_tau_den, p.recrypt_lo, p.recrypt_hi, (double)p.recrypt_rounds};
+    for (int i = 0; i < 17; i++) out[i] = v[i];
+}
+
 // a mixed sequence of draws from ONE stream of the reference's AesCtr256: moduli[i] == 0 -> next_u64(), else bounded(moduli[i])
 void ref_aes_ctr_draws(const uint8_t* key, uint64_t nonce, const uint64_t* moduli, uint64_t* out, size_t n) {
     AesCtr256 prg;

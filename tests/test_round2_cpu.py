@@ -284,3 +284,40 @@ def test_plan_noise_engine_oracle_reference_agree():
         if kr is not None:
             assert got == tuple(kr.plan_noise(d)), d
     assert (z2.value, z3.value)[0] > 30000                  # depth 65535: tens of thousands of noise groups, still the same numbers
+
+
+def test_params_struct_matches_header_and_reference(tmp_path):
+    """pvacb_params: (1) pvacb_params_default gives the reference's defaults field for field (core/types.hpp:36-70, read from the
+    unmodified reference through oracle/_ref); (2) the ctypes mirror in api.py has the layout a C compiler gives the struct in
+    include/pvacb.h (size and every offset), so a Python caller and a C caller hand the library the same bytes"""
+    import ctypes as C
+    import subprocess
+    from pvac_hfhe_cppbyv_b200 import api
+    p = api.Params.default()
+    names = [f[0] for f in api.Params._fields_]
+    assert names == ["B", "m_bits", "n_bits", "h_col_wt", "x_col_wt", "err_wt", "noise_entropy_bits", "tuple2_fraction", "depth_slope_bits", "edge_budget",
+                     "lpn_n", "lpn_t", "lpn_tau_num", "lpn_tau_den", "recrypt_lo", "recrypt_hi", "recrypt_rounds"]
+    if _ref.available():
+        assert [float(getattr(p, n)) for n in names] == _ref.params_default()
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "pvacb.h"\nint main(void) {\n  printf("%zu", sizeof(pvacb_params));\n'
+                   + "".join(f'  printf(" %zu", offsetof(pvacb_params, {n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include"), str(src), "-o", exe])
+    nums = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert nums[0] == C.sizeof(api.Params)
+    assert nums[1:] == [getattr(api.Params, n).offset for n in names]
+
+
+def test_blob_layout_properties():
+    """pvacb_blob_layout (host code, no GPU needed): the 13 arrays of a batch image in declaration order, 256-byte aligned, no overlap,
+    each at least as large as its contents, total = off[13]; the counts (0, 0, 0) give a valid (tiny) image"""
+    from pvac_hfhe_cppbyv_b200 import api
+    unit = [4, 4, 1, 8, 8, 8, 4, 4, 4, 2, 1, 16, 1024]                    # bytes per entry: loff, eoff, rule, ztag, nlo, nhi, pa, pb, lid, idx, ch, w, sigma
+    for n, nl, ne in ((0, 0, 0), (1, 2, 40), (3, 0, 0), (512, 4096, 614400), (4096, 8 * 4096, 1234 * 4096), (1 << 20, 2 << 20, 40 << 20)):
+        off = api.blob_layout(n, nl, ne)
+        assert len(off) == 14 and off[0] == 0
+        counts = [n + 1, n + 1] + [nl] * 6 + [ne] * 5
+        for k in range(13):
+            assert off[k] % 256 == 0 and off[k + 1] - off[k] >= counts[k] * unit[k] and off[k + 1] - off[k] < counts[k] * unit[k] + 512, (n, nl, ne, k)
+    assert api.blob_layout(4096, 8 * 4096, 1234 * 4096)[13] > 1234 * 4096 * 1024
